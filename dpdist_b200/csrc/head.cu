@@ -1,0 +1,205 @@
+// Implicit distance head: host orchestration, weight packing, C ABI.
+// Replaces DPDist conv_version 1 (reference utils/dpdist_util.py:412-544, 688-700).
+#include "head_simt.cuh"
+#include "head_tc.cuh"
+
+namespace dpd {
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+constexpr int MAX_CHUNK_ROWS = 1 << 18;
+
+struct HeadLayout {
+  int impl;      // DPD_HEAD_SIMT or DPD_HEAD_TC (resolved)
+  int E, K1, Kp1;
+  // packed blob (byte offsets)
+  size_t w1p, w2, w3, w4, b1, b2, b3, b4, tc, total;
+  // workspace per chunk (byte offsets as a function of chunk rows)
+};
+
+size_t up(size_t x) { return round_up<size_t>(x, ALIGN); }
+
+int resolve_impl(const dpd_head_config& c) {
+  if (c.flags == DPD_HEAD_SIMT) return DPD_HEAD_SIMT;
+  if (c.flags == DPD_HEAD_TC) return DPD_HEAD_TC;
+  return tc_supported(c) ? DPD_HEAD_TC : DPD_HEAD_SIMT;
+}
+
+int check_cfg(const dpd_head_config* c, const char* who) {
+  DPD_REQUIRE(c != nullptr, DPD_E_INVALID, "%s: null config", who);
+  DPD_REQUIRE(c->n_clouds >= 0 && c->n_query > 0, DPD_E_INVALID, "%s: bad sizes", who);
+  DPD_REQUIRE(c->G >= 2 && c->G <= DPD_MAX_GRID, DPD_E_UNSUPPORTED, "%s: G=%d outside [2,%d]", who, c->G, DPD_MAX_GRID);
+  DPD_REQUIRE(c->C > 0 && c->k > 0 && c->k <= 2 * DPD_MAX_GRID, DPD_E_INVALID, "%s: bad C/k", who);
+  DPD_REQUIRE(c->H > 0 && c->H % 16 == 0, DPD_E_UNSUPPORTED, "%s: H=%d must be a positive multiple of 16", who, c->H);
+  DPD_REQUIRE(c->flags == DPD_HEAD_AUTO || c->flags == DPD_HEAD_SIMT || c->flags == DPD_HEAD_TC, DPD_E_INVALID, "%s: bad flags", who);
+  if (c->flags == DPD_HEAD_TC)
+    DPD_REQUIRE(tc_supported(*c), DPD_E_UNSUPPORTED, "%s: tensor-core head needs H %% 256 == 0 and C %% 4 == 0", who);
+  return 0;
+}
+
+HeadLayout make_layout(const dpd_head_config& c) {
+  HeadLayout L;
+  L.impl = resolve_impl(c);
+  L.E = c.k * c.k * c.k * c.C;
+  L.K1 = L.E + 3;
+  L.Kp1 = round_up(L.K1, 32);
+  size_t o = 0;
+  const size_t H = c.H;
+  L.w1p = o; o += up((size_t)L.Kp1 * H * 4);
+  L.w2 = o;  o += up(H * H * 4);
+  L.w3 = o;  o += up(H * H * 4);
+  L.w4 = o;  o += up(H * 3 * 4);
+  L.b1 = o;  o += up(H * 4);
+  L.b2 = o;  o += up(H * 4);
+  L.b3 = o;  o += up(H * 4);
+  L.b4 = o;  o += up(16);
+  L.tc = o;
+  if (L.impl == DPD_HEAD_TC) o += up(tc_packed_bytes(c, L.Kp1));
+  L.total = o;
+  return L;
+}
+
+struct WsLayout {
+  size_t idx, mask, off, ha, hb, tc, total;
+};
+
+WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
+  WsLayout W;
+  size_t o = 0;
+  W.idx = o;  o += up(rows * 4);
+  W.mask = o; o += up(rows * 4);
+  W.off = o;  o += up(rows * 12);
+  W.ha = o;   o += up(rows * (size_t)c.H * 4);
+  W.hb = o;   o += up(rows * (size_t)c.H * 4);
+  W.tc = o;
+  if (L.impl == DPD_HEAD_TC) o += up(tc_workspace_bytes(c, rows));
+  W.total = o;
+  return W;
+}
+
+size_t total_rows(const dpd_head_config& c) { return (size_t)c.n_clouds * c.n_query; }
+
+// W1p[kk][n] : patch rows first, then the 3 offset rows, then zero padding
+__global__ void pack_w1_kernel(const float* __restrict__ w1, float* __restrict__ w1p, int E, int Kp1, int H) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Kp1 * H) return;
+  const int kk = (int)(i / H), n = (int)(i % H);
+  float v = 0.f;
+  if (kk < E) v = w1[(size_t)(3 + kk) * H + n];
+  else if (kk < E + 3) v = w1[(size_t)(kk - E) * H + n];
+  w1p[i] = v;
+}
+
+}  // namespace
+}  // namespace dpd
+
+extern "C" size_t dpd_head_packed_bytes(const dpd_head_config* cfg) {
+  using namespace dpd;
+  if (check_cfg(cfg, "dpd_head_packed_bytes") != 0) return 0;
+  return make_layout(*cfg).total;
+}
+
+extern "C" size_t dpd_head_workspace_bytes(const dpd_head_config* cfg) {
+  using namespace dpd;
+  if (check_cfg(cfg, "dpd_head_workspace_bytes") != 0) return 0;
+  const HeadLayout L = make_layout(*cfg);
+  size_t rows = total_rows(*cfg);
+  if (rows > (size_t)MAX_CHUNK_ROWS) rows = MAX_CHUNK_ROWS;
+  rows = round_up<size_t>(rows > 0 ? rows : 1, 128);
+  return make_ws(*cfg, L, rows).total;
+}
+
+extern "C" int dpd_head_pack_weights(const dpd_head_config* cfg, const float* d_w1, const float* d_b1,
+                                     const float* d_w2, const float* d_b2, const float* d_w3,
+                                     const float* d_b3, const float* d_w4, const float* d_b4,
+                                     void* d_packed, void* stream) {
+  using namespace dpd;
+  int rc = check_cfg(cfg, "dpd_head_pack_weights");
+  if (rc) return rc;
+  DPD_REQUIRE(d_w1 && d_b1 && d_w2 && d_b2 && d_w3 && d_b3 && d_w4 && d_b4 && d_packed, DPD_E_INVALID, "dpd_head_pack_weights: null pointer");
+  DPD_REQUIRE(aligned16(d_packed), DPD_E_INVALID, "dpd_head_pack_weights: d_packed must be 16-byte aligned");
+  const HeadLayout L = make_layout(*cfg);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)d_packed;
+  const size_t H = cfg->H;
+  const size_t n1 = (size_t)L.Kp1 * H;
+  DPD_LAUNCH("pack_w1", st, pack_w1_kernel<<<(unsigned)ceil_div<size_t>(n1, 256), 256, 0, st>>>(d_w1, (float*)(base + L.w1p), L.E, L.Kp1, cfg->H));
+  DPD_CUDA_CHECK_LAUNCH("pack_w1_kernel");
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.w2, d_w2, H * H * 4, cudaMemcpyDeviceToDevice, st));
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.w3, d_w3, H * H * 4, cudaMemcpyDeviceToDevice, st));
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.w4, d_w4, H * 3 * 4, cudaMemcpyDeviceToDevice, st));
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b1, d_b1, H * 4, cudaMemcpyDeviceToDevice, st));
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b2, d_b2, H * 4, cudaMemcpyDeviceToDevice, st));
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b3, d_b3, H * 4, cudaMemcpyDeviceToDevice, st));
+  DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b4, d_b4, 3 * 4, cudaMemcpyDeviceToDevice, st));
+  if (L.impl == DPD_HEAD_TC) {
+    rc = tc_pack_weights(*cfg, L.Kp1, (const float*)(base + L.w1p), (const float*)(base + L.w2),
+                         (const float*)(base + L.w3), base + L.tc, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, const float* d_query,
+                                const float* h_centers, const float* h_lo, const float* h_hi,
+                                const void* d_packed, float* d_out, int32_t* d_idx,
+                                void* d_workspace, size_t workspace_bytes, void* stream) {
+  using namespace dpd;
+  int rc = check_cfg(cfg, "dpd_head_forward");
+  if (rc) return rc;
+  DPD_REQUIRE(d_fv && d_query && h_centers && h_lo && h_hi && d_packed && d_out && d_workspace, DPD_E_INVALID, "dpd_head_forward: null pointer");
+  DPD_REQUIRE(aligned16(d_fv) && aligned16(d_packed) && aligned16(d_workspace), DPD_E_INVALID, "dpd_head_forward: pointers must be 16-byte aligned");
+  const size_t M = total_rows(*cfg);
+  if (M == 0) return 0;
+  const HeadLayout L = make_layout(*cfg);
+  // largest chunk (multiple of 128 rows) that fits the caller's workspace
+  size_t chunk = round_up<size_t>(M < (size_t)MAX_CHUNK_ROWS ? M : (size_t)MAX_CHUNK_ROWS, 128);
+  while (chunk > 128 && make_ws(*cfg, L, chunk).total > workspace_bytes) chunk = round_up<size_t>(chunk / 2, 128);
+  DPD_REQUIRE(make_ws(*cfg, L, chunk).total <= workspace_bytes, DPD_E_WORKSPACE,
+              "dpd_head_forward: workspace %zu B too small (need >= %zu B)", workspace_bytes, make_ws(*cfg, L, 128).total);
+  const WsLayout W = make_ws(*cfg, L, chunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)d_workspace;
+  const char* pk = (const char*)d_packed;
+  GridTables t;
+  fill_tables(t, cfg->G, h_centers, h_lo, h_hi);
+
+  for (size_t r0 = 0; r0 < M; r0 += chunk) {
+    const int rows = (int)((M - r0 < chunk) ? (M - r0) : chunk);
+    int32_t* idx = (int32_t*)(ws + W.idx);
+    float* mask = (float*)(ws + W.mask);
+    float* off = (float*)(ws + W.off);
+    float* ha = (float*)(ws + W.ha);
+    float* hb = (float*)(ws + W.hb);
+    // rows are independent: assign this chunk's queries as a flat list of `rows` points
+    rc = dpd_voxel_assign(d_query + r0 * 3, 1, rows, cfg->G, h_centers, h_lo, h_hi, idx, mask, off, stream);
+    if (rc) return rc;
+    if (d_idx) DPD_CUDA_CALL(cudaMemcpyAsync(d_idx + r0, idx, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
+    GatherDesc g;
+    g.fv = d_fv; g.idx = idx; g.offset = off; g.row0 = (long long)r0;
+    g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
+    const float* h3 = nullptr;
+    if (L.impl == DPD_HEAD_TC) {
+      rc = tc_head_layers(*cfg, L.Kp1, g, rows, pk + L.tc, (const float*)(pk + L.b1), (const float*)(pk + L.b2),
+                          (const float*)(pk + L.b3), ha, hb, ws + W.tc, &h3, st);
+      if (rc) return rc;
+    } else {
+      SimtGemmParams p;
+      p.g = g; p.M = rows; p.N = cfg->H; p.relu = 1;
+      p.A = nullptr; p.lda = 0; p.B = (const float*)(pk + L.w1p); p.bias = (const float*)(pk + L.b1); p.Cout = ha; p.Kp = L.Kp1;
+      rc = launch_simt_gemm(p, true, st);
+      if (rc) return rc;
+      p.A = ha; p.lda = cfg->H; p.B = (const float*)(pk + L.w2); p.bias = (const float*)(pk + L.b2); p.Cout = hb; p.Kp = cfg->H;
+      rc = launch_simt_gemm(p, false, st);
+      if (rc) return rc;
+      p.A = hb; p.B = (const float*)(pk + L.w3); p.bias = (const float*)(pk + L.b3); p.Cout = ha;
+      rc = launch_simt_gemm(p, false, st);
+      if (rc) return rc;
+      h3 = ha;
+    }
+    rc = launch_head_out(h3, cfg->H, (const float*)(pk + L.w4), (const float*)(pk + L.b4), mask, d_out + r0 * 3, rows, cfg->H, st);
+    if (rc) return rc;
+  }
+  return 0;
+}

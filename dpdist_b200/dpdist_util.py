@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's op library `utils/dpdist_util.py` for the hot path.
+
+Same function names, argument order and defaults as the reference; torch CUDA tensors in and
+out; every op is one or more calls into libdpdist_b200.so (include/dpdist_b200.h).  There is no
+CPU implementation here: a CPU tensor or a missing extension raises.
+
+Reference anchors (relative to the reference repo):
+  get_3dmfv_tf      utils/dpdist_util.py:22-141
+  local_z / _3d     utils/dpdist_util.py:850-854, 911-960
+  get_grid_centers  utils/dpdist_util.py:982-992
+  DPDist            utils/dpdist_util.py:412-544, 688-700 (conv_version 1, k > 0)
+  get_loss          utils/dpdist_util.py:962-980
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import tf_util
+
+FV_CHANNELS = {True: 20, False: 7}
+
+
+# --------------------------------------------------------------------------------------
+# host-side grid tables, built exactly as the reference builds them (numpy fp64 -> fp32)
+# --------------------------------------------------------------------------------------
+def _fv_grid(n_gaussians, D=3):
+    if D != 3:
+        raise NotImplementedError("only NUM_DIMS == 3 is on the DPDist hot path")
+    grid_size = int(np.ceil(np.power(n_gaussians, 1 / 3)))                    # :41
+    if grid_size ** 3 != n_gaussians:
+        raise ValueError("n_gaussians=%d is not a perfect cube (the reference's graph fails with a "
+                         "shape error at utils/dpdist_util.py:73)" % n_gaussians)
+    l = np.linspace(-1, 1, grid_size, False) + (1 / grid_size)                # :42
+    return grid_size, np.ascontiguousarray(l.astype(np.float32))              # :50 tf.constant(x, tf.float32)
+
+
+def get_grid_centers(Embedding_Size, NUM_DIMS=2):
+    """utils/dpdist_util.py:982-992 (numpy, as in the reference)."""
+    if NUM_DIMS == 2:
+        vec_size = int(np.floor(np.sqrt(Embedding_Size)))
+    else:
+        vec_size = int(np.ceil(np.power(Embedding_Size, 1 / 3)))
+    grid_step = 2 / vec_size
+    l = np.arange(-1, 1, grid_step) + grid_step / 2
+    if NUM_DIMS == 2:
+        return np.meshgrid(l, l)
+    return np.meshgrid(l, l, l)
+
+
+def _assign_tables(C):
+    """Per-axis centre / interval tables from the [V,3] fp32 centre list C, the reference's way:
+    grid_size = |C[0].z - C[1].z| / 2 (:468); lo = C - grid_size, hi = C + grid_size in fp32 (:478-487).
+    C[g] = (l[i1], l[i0], l[i2]) for g = i0*G^2 + i1*G + i2, so C[:G, 2] is the axis vector l."""
+    cached = getattr(C, "_dpd_tables", None)
+    if cached is not None:
+        return cached
+    Cn = C.detach().cpu().numpy() if torch.is_tensor(C) else np.asarray(C)   # device sync: only for foreign C
+    Cn = Cn.astype(np.float32)
+    V = Cn.shape[0]
+    G = int(np.round(np.power(V, 1 / 3)))
+    if G ** 3 != V:
+        raise ValueError("C must list G^3 voxel centres")
+    l = np.ascontiguousarray(Cn[:G, 2])
+    gs = np.float32(np.abs(Cn[0][2] - Cn[1][2]) / np.float32(2))
+    lo = np.ascontiguousarray((l - gs).astype(np.float32))
+    hi = np.ascontiguousarray((l + gs).astype(np.float32))
+    # sanity: C really is the meshgrid('xy') product of l (otherwise the separable search is invalid)
+    i = np.arange(V)
+    exp = np.stack([l[(i // G) % G], l[i // (G * G)], l[i % G]], -1)
+    if not np.array_equal(exp, Cn):
+        raise ValueError("C is not the reference's get_grid_centers layout")
+    return G, l, lo, hi
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_cuda(t, name):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise _lib.DPDistNativeError("%s must be a CUDA tensor: dpdist_b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32" % name)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# --------------------------------------------------------------------------------------
+# 3DmFV
+# --------------------------------------------------------------------------------------
+def get_3dmfv_tf(points, n_gaussians=9, sigma=0.0625, flatten=True, normalize=True, full_fv=True):
+    """points [B,N,3] -> fv [B, n_gaussians, 20|7] (flatten=False) or [B, (20|7)*n_gaussians].
+    `normalize` is accepted and ignored: the reference hard-wires it to True (:111)."""
+    lib = _lib.load()
+    points = _check_cuda(points, "points")
+    if points.dim() != 3 or points.shape[-1] != 3:
+        raise ValueError("points must be [B,N,3]")
+    B, N, _ = points.shape
+    G, l = _fv_grid(n_gaussians, 3)
+    C = FV_CHANNELS[bool(full_fv)]
+    V = G ** 3
+    out = torch.empty((B, C * V) if flatten else (B, V, C), device=points.device, dtype=torch.float32)
+    with torch.cuda.device(points.device):
+        rc = lib.dpd_fv_forward(_ptr(points), B, N, G, _lib.fptr(l), float(sigma), int(bool(full_fv)),
+                                int(bool(flatten)), _ptr(out), _stream())
+    _lib.check(rc, "dpd_fv_forward")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# local patches
+# --------------------------------------------------------------------------------------
+class LocalPatches:
+    """What `local_z` returns in place of the reference's [B,V,k^3*E] tensor (5.12 MB per cloud at
+    the defaults): the FV tensor plus k.  `DPDist` gathers patch rows on the fly from `fv`;
+    `materialize()` produces the reference's dense tensor on request (embedding_set, parity tests)."""
+
+    def __init__(self, fv, k):
+        self.fv, self.k = fv, int(k)
+
+    @property
+    def shape(self):
+        B, V, E = self.fv.shape
+        return torch.Size((B, V, self.k ** 3 * E))
+
+    def materialize(self):
+        lib = _lib.load()
+        fv = _check_cuda(self.fv, "fv")
+        B, V, E = fv.shape
+        G = int(np.round(np.power(V, 1 / 3)))
+        out = torch.empty((B, V, self.k ** 3 * E), device=fv.device, dtype=torch.float32)
+        with torch.cuda.device(fv.device):
+            rc = lib.dpd_local_patches(_ptr(fv), B, G, E, self.k, _ptr(out), _stream())
+        _lib.check(rc, "dpd_local_patches")
+        return out
+
+
+def local_z(net, is_training, reuse=False, NUM_DIMS=2, k=3, overlap=True):
+    """utils/dpdist_util.py:850-854."""
+    if NUM_DIMS == 2:
+        raise NotImplementedError("local_z_2d is not on the DPDist hot path (NUM_DIMS=3)")
+    return local_z_3d(net, is_training, reuse=reuse, NUM_DIMS=NUM_DIMS, k=k, overlap=overlap)
+
+
+def local_z_3d(net, is_training, reuse=False, NUM_DIMS=3, k=3, overlap=True):
+    """net [B,V,E] -> (LocalPatches standing for [B,V,k^3*E], C [V,3] fp32 voxel centres)."""
+    net = _check_cuda(net, "net")
+    num_vox = net.shape[1]
+    grid_len = int(np.round(np.power(num_vox, 1 / 3)))                        # :916
+    if grid_len ** NUM_DIMS != num_vox:
+        net = net[:, :int(grid_len ** NUM_DIMS), :].contiguous()              # :918
+    X, Y, Z = get_grid_centers(num_vox, NUM_DIMS)
+    C = np.stack([X, Y, Z], -1).astype(np.float32).reshape(-1, NUM_DIMS)      # :927-929
+    Ct = torch.from_numpy(C).to(net.device)
+    Ct._dpd_tables = _assign_tables(C)      # host copy of the interval tables: no D2H sync in DPDist
+    return LocalPatches(net, k), Ct
+
+
+# --------------------------------------------------------------------------------------
+# voxel assignment
+# --------------------------------------------------------------------------------------
+def get_pc_grid_binary_mask_from_centers(Centers, point_cloud):
+    """utils/dpdist_util.py:459-492 without the [B,N,V] mask and [B,N,V,3] offsets: returns the three
+    things the reference gathers out of them (:436-447): (binary_vect [B,N], offset [B,N,3],
+    argmax [B,N] int32)."""
+    lib = _lib.load()
+    pc = _check_cuda(point_cloud, "point_cloud")
+    B, N, _ = pc.shape
+    G, l, lo, hi = _assign_tables(Centers)
+    idx = torch.empty((B, N), device=pc.device, dtype=torch.int32)
+    mask = torch.empty((B, N), device=pc.device, dtype=torch.float32)
+    off = torch.empty((B, N, 3), device=pc.device, dtype=torch.float32)
+    with torch.cuda.device(pc.device):
+        rc = lib.dpd_voxel_assign(_ptr(pc), B, N, G, _lib.fptr(l), _lib.fptr(lo), _lib.fptr(hi),
+                                  _ptr(idx), _ptr(mask), _ptr(off), _stream())
+    _lib.check(rc, "dpd_voxel_assign")
+    return mask, off, idx
+
+
+# --------------------------------------------------------------------------------------
+# implicit distance head
+# --------------------------------------------------------------------------------------
+class _PackedHead:
+    """Kernel-layout copy of the four conv layers, rebuilt when any variable changes."""
+
+    def __init__(self):
+        self.key = None
+        self.blob = None
+        self.ws = None
+
+    def get(self, lib, cfg, ws_list):
+        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags) + tuple((w.data_ptr(), w._version) for w in ws_list)
+        if key != self.key:
+            nbytes = lib.dpd_head_packed_bytes(ctypes.byref(cfg))
+            if nbytes == 0:
+                _lib.check(-1, "dpd_head_packed_bytes")
+            if self.blob is None or self.blob.numel() < nbytes or self.blob.device != ws_list[0].device:
+                self.blob = torch.empty(nbytes, device=ws_list[0].device, dtype=torch.uint8)
+            rc = lib.dpd_head_pack_weights(ctypes.byref(cfg), *[_ptr(w) for w in ws_list], _ptr(self.blob), _stream())
+            _lib.check(rc, "dpd_head_pack_weights")
+            self.key = key
+        return self.blob
+
+    def workspace(self, lib, cfg, device):
+        nbytes = lib.dpd_head_workspace_bytes(ctypes.byref(cfg))
+        if nbytes == 0:
+            _lib.check(-1, "dpd_head_workspace_bytes")
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
+            self.ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        return self.ws
+
+
+_PACKED = {}
+HEAD_IMPL = _lib.HEAD_AUTO   # module-level switch: _lib.HEAD_AUTO / HEAD_SIMT / HEAD_TC
+
+
+def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
+    """out[c,q,:] = mask * relu6(MLP([query - centre | patch_k(fv[c], voxel(query))])) / 3.
+    fv [n_clouds,V,Cc], query [n_clouds,NP,3], weights = [w1,b1,w2,b2,w3,b3,w4,b4] in the
+    reference's HWIO layouts."""
+    lib = _lib.load()
+    fv = _check_cuda(fv, "fv")
+    query = _check_cuda(query, "query")
+    n_clouds, V, Cc = fv.shape
+    if query.shape[0] != n_clouds:
+        raise ValueError("fv and query disagree on the number of clouds")
+    NP = query.shape[1]
+    G, l, lo, hi = _assign_tables(C)
+    if G ** 3 != V:
+        raise ValueError("C and fv disagree on the grid")
+    ws_list = [_check_cuda(w.detach(), "variable") for w in weights]
+    w1 = ws_list[0]
+    H = w1.shape[-1]
+    if w1.numel() != (3 + k ** 3 * Cc) * H:
+        raise ValueError("mapper_conv1/weights has %d elements, expected (3+k^3*C)*H = %d" % (w1.numel(), (3 + k ** 3 * Cc) * H))
+    cfg = _lib.HeadConfig(n_clouds, NP, G, Cc, int(k), H, HEAD_IMPL if impl is None else impl)
+    out = torch.empty((n_clouds, NP, 3), device=fv.device, dtype=torch.float32)
+    idx = torch.empty((n_clouds, NP), device=fv.device, dtype=torch.int32) if return_idx else None
+    with torch.cuda.device(fv.device):
+        cache = _PACKED.setdefault((fv.device, cfg.flags), _PackedHead())
+        blob = cache.get(lib, cfg, ws_list)
+        ws = cache.workspace(lib, cfg, fv.device)
+        rc = lib.dpd_head_forward(ctypes.byref(cfg), _ptr(fv), _ptr(query), _lib.fptr(l), _lib.fptr(lo),
+                                  _lib.fptr(hi), _ptr(blob), _ptr(out),
+                                  _ptr(idx) if idx is not None else None, _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "dpd_head_forward")
+    return (out, idx) if return_idx else out
+
+
+def _as_fv(embedding, k):
+    """Accept what `local_z` returns (LocalPatches) or the reference's dense [B,V,k^3*E] tensor; in a
+    dense patch tensor the FV record of voxel v is its own centre tap (a0=a1=a2=(k-1)//2)."""
+    if isinstance(embedding, LocalPatches):
+        if embedding.k != k:
+            raise ValueError("DPDist k=%d but the patches were extracted with k=%d" % (k, embedding.k))
+        return embedding.fv
+    emb = _check_cuda(embedding, "embedding")
+    E = emb.shape[2] // (k ** 3)
+    pb = (k - 1) // 2
+    centre = (pb * k + pb) * k + pb
+    return emb[:, :, centre * E:(centre + 1) * E].contiguous()
+
+
+def DPDist(point_cloud, point_cloudB, embedding,
+           embeddingB, C, is_training, bn_decay=None, reuse=None,
+           bn=True, wd=0.0,
+           sig=True, Embedding_Size=512,
+           NUM_DIMS=2, mlp=[32, 16, 16], k=3, conv_version=1, output_act='relu'):
+    """utils/dpdist_util.py:412-700 for k > 0, conv_version 1, NUM_DIMS 3, bn off.
+    Returns [pred_AB, pred_BA], each [B,NP,1,3]: queries point_cloudB against A's field and
+    queries point_cloud against B's field (:494-500), masked to the unit cube (:697-698)."""
+    if k <= 0:
+        raise NotImplementedError("k == 0 (global embedding) is not the DPDist hot path")
+    if conv_version != 1:
+        raise NotImplementedError("conv_version %d: only the shared-MLP head (1) is implemented" % conv_version)
+    if NUM_DIMS != 3:
+        raise NotImplementedError("NUM_DIMS must be 3")
+    if bn:
+        raise NotImplementedError("bn=True: batch norm is off at the reference defaults (--BN 0) and not implemented")
+    if output_act != 'relu':
+        raise NotImplementedError("output_act must be 'relu' (models/dpdist_and_aue.py:74)")
+    if len(mlp) != 3 or not (mlp[0] == mlp[1] == mlp[2]):
+        raise NotImplementedError("mlp must be three equal widths (reference default [1024,1024,1024])")
+    pcA = _check_cuda(point_cloud, "point_cloud")
+    pcB = _check_cuda(point_cloudB, "point_cloudB")
+    fvA, fvB = _as_fv(embedding, k), _as_fv(embeddingB, k)
+    if pcA.shape != pcB.shape:
+        raise ValueError("point_cloud and point_cloudB must have the same shape (the reference concatenates "
+                         "their rows on the batch axis, utils/dpdist_util.py:511)")
+    B, NP, _ = pcA.shape
+    E = fvA.shape[2] * k ** 3
+    H = mlp[0]
+    with tf_util.variable_scope('dpdist_local', reuse=reuse):                 # :514
+        w1, b1 = tf_util.conv2d_variables(1, H, [1, E + NUM_DIMS], 'mapper_conv1', reuse=reuse)   # :516-521
+        w2, b2 = tf_util.conv2d_variables(H, mlp[1], [1, 1], 'mapper_conv2', reuse=reuse)         # :529-533
+        w3, b3 = tf_util.conv2d_variables(mlp[1], mlp[2], [1, 1], 'mapper_conv3', reuse=reuse)    # :535-539
+        w4, b4 = tf_util.conv2d_variables(mlp[2], NUM_DIMS, [1, 1], 'mapper_conv4', reuse=reuse)  # :541-545
+    fv_all = torch.cat([fvA, fvB], 0)             # rows [A-field | B-field]  (:511)
+    query = torch.cat([pcB, pcA], 0)              # A's field is queried at B's points and vice versa (:494,498)
+    out = head_forward(fv_all, query, C, [w1, b1, w2, b2, w3, b3, w4, b4], k)
+    out = out.view(2, B, NP, 1, 3)
+    return [out[0], out[1]]                                                    # :695
+
+
+def get_loss(pred_set, end_points, labels, loss_type='l1_dist'):
+    """utils/dpdist_util.py:962-980.  Like the reference it RETURNS (loss_samples, loss_pred) where
+    `loss_samples` is the squeezed prediction pred_AB[...,0] (:967-968, :980), and publishes the
+    two scalar losses through the collections 'loss_samples' (mean |pred - labels|, :972-974) and
+    'loss_pred' (:976-979), which is where the trainer reads them (train...py:262-265)."""
+    pred_listAB = pred_set['pred_listAB']
+    pred_listBA = pred_set['pred_listBA']
+    if loss_type != 'l1_dist':
+        raise NotImplementedError("only 'l1_dist' is implemented in the reference")
+    loss_samples = pred_listAB[:, :, :, 0]
+    loss_samples = loss_samples.squeeze()
+    loss = torch.mean(torch.abs(loss_samples - labels))
+    tf_util.add_to_collection('loss_samples', loss)
+    loss_pred = (torch.mean(pred_listAB[:, :, :, 0]) + torch.mean(pred_listBA[:, :, :, 0])) / 2
+    tf_util.add_to_collection('loss_pred', loss_pred)
+    return loss_samples, loss_pred

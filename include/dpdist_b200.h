@@ -1,0 +1,130 @@
+/*
+ * dpdist_b200 -- C ABI of the B200-native DPDist hot path (libdpdist_b200.so).
+ *
+ * The reference (dahliau/DPDist) has no FFI: the path lives behind Python functions that build a
+ * TF1 graph.  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference code it replaces, paths relative to the
+ * reference repo root.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (16-byte aligned, contiguous,
+ *     row-major); h_* is HOST memory.  The library never allocates, frees or retains them.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs.
+ *   - return 0 = ok, <0 = invalid argument / unsupported configuration (DPD_E_*), >0 = cudaError_t.
+ *     dpd_last_error() returns a thread-local message for the last non-zero return.
+ *   - "cloud" = one point set; a DPDist pair (A,B) is two clouds.  The host concatenates
+ *     [A-clouds | B-clouds] on the leading axis, mirroring tf.concat([net, netB], 0)
+ *     (utils/dpdist_util.py:511).
+ *   - grid tables are built on the HOST exactly as the reference builds them (numpy fp64 -> fp32):
+ *     h_centers[G] = float32(np.linspace(-1,1,G,False)+1/G)  (utils/dpdist_util.py:42,50)
+ *     h_lo[G], h_hi[G] = float32(c) -/+ float32(gs), c from get_grid_centers (:982-992),
+ *     gs = |C[0].z-C[1].z|/2 (:468), so the float comparisons are the reference's own.
+ *   - flat Gaussian / voxel index g = i0*G*G + i1*G + i2 has centre (x=l[i1], y=l[i0], z=l[i2])
+ *     (np.meshgrid 'xy' indexing, utils/dpdist_util.py:47-48, 990-992).
+ */
+#ifndef DPDIST_B200_H
+#define DPDIST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPD_ABI_VERSION 1
+#define DPD_MAX_GRID 16
+#define DPD_FV_CHANNELS_FULL 20
+#define DPD_FV_CHANNELS_SMALL 7
+
+#define DPD_E_INVALID (-1)     /* null pointer, non-positive size, misalignment */
+#define DPD_E_UNSUPPORTED (-2) /* configuration outside what the kernels implement */
+#define DPD_E_WORKSPACE (-3)   /* workspace too small */
+
+/* head implementation selector (flags argument of dpd_head_forward) */
+#define DPD_HEAD_AUTO 0
+#define DPD_HEAD_SIMT 1 /* fp32 FFMA GEMMs (sanity path) */
+#define DPD_HEAD_TC 2   /* tcgen05 tensor-core GEMMs, split-precision */
+
+int dpd_version(void);
+const char* dpd_last_error(void);
+
+/* 3DmFV encoding: replaces get_3dmfv_tf (utils/dpdist_util.py:22-141; second copy
+ * pcrnet-registration/models/ipcr_model.py:53-172).
+ *   d_points [n_clouds, n_points, 3] fp32
+ *   d_fv     flatten=0: [n_clouds, G^3, C]   (C = 20 if full_fv else 7; order pi(mean[,max]),
+ *                        mu(mean xyz[,max xyz,min xyz]), sigma(same))          (:134-137)
+ *            flatten=1: [n_clouds, C*G^3]    channel-major                      (:129-132)     */
+int dpd_fv_forward(const float* d_points, int n_clouds, int n_points, int G, const float* h_centers,
+                   float sigma, int full_fv, int flatten, float* d_fv, void* stream);
+
+/* Voxel assignment of query points: replaces DPDist.get_pc_grid_binary_mask_from_centers +
+ * the mask / offset gathers of get_emb_and_concat (utils/dpdist_util.py:459-492, 434-447).
+ *   d_query  [n_clouds, n_query, 3] fp32
+ *   d_idx    [n_clouds, n_query]    int32 flat voxel index (first match; 0 if none)   (:490)
+ *   d_mask   [n_clouds, n_query]    fp32 1/0 in-cube flag (binary_vect at idx)        (:436-440)
+ *   d_offset [n_clouds, n_query, 3] fp32 query - centre(idx)                          (:443-447, 491)
+ * any output pointer may be NULL.                                                               */
+int dpd_voxel_assign(const float* d_query, int n_clouds, int n_query, int G, const float* h_centers,
+                     const float* h_lo, const float* h_hi, int32_t* d_idx, float* d_mask,
+                     float* d_offset, void* stream);
+
+/* Materialised local patches: replaces local_z / local_z_3d (utils/dpdist_util.py:850-854,
+ * 911-960).  Only for callers that ask for embedding_set; the head never materialises this.
+ *   d_fv [n_clouds, G^3, C] -> d_patches [n_clouds, G^3, k^3*C], element order (a0,a1,a2,c),
+ *   zero outside the grid, SAME padding ((k-1)/2 before, k/2 after).                           */
+int dpd_local_patches(const float* d_fv, int n_clouds, int G, int C, int k, float* d_patches,
+                      void* stream);
+
+/* Implicit distance head: replaces DPDist conv_version 1 (utils/dpdist_util.py:412-544, 688-700)
+ * + tf_util.conv2d x4 (utils/tf_util.py:161-228), evaluated per cloud:
+ *   out[c, q, :] = mask * relu6(MLP([query - centre(idx) | patch_k(fv[c], idx)])) / 3
+ * Weights are given in the reference's own layouts (HWIO flattened, row-major [K_in, K_out]):
+ *   d_w1 [3 + k^3*C, H] (offset rows FIRST, :455), d_w2 [H,H], d_w3 [H,H], d_w4 [H,3], biases [H],[H],[H],[3].
+ * dpd_head_pack_weights re-lays them out for the kernels (call again whenever they change).      */
+typedef struct dpd_head_config {
+  int n_clouds; /* 2*B for a DPDist batch of B pairs */
+  int n_query;  /* queries per cloud (NP) */
+  int G;        /* voxels per axis */
+  int C;        /* FV channels per voxel (20) */
+  int k;        /* local patch edge */
+  int H;        /* MLP width (1024) */
+  int flags;    /* DPD_HEAD_* */
+} dpd_head_config;
+
+size_t dpd_head_packed_bytes(const dpd_head_config* cfg);
+size_t dpd_head_workspace_bytes(const dpd_head_config* cfg);
+
+int dpd_head_pack_weights(const dpd_head_config* cfg, const float* d_w1, const float* d_b1,
+                          const float* d_w2, const float* d_b2, const float* d_w3,
+                          const float* d_b3, const float* d_w4, const float* d_b4, void* d_packed,
+                          void* stream);
+
+/*   d_fv    [n_clouds, G^3, C]      fp32 (output of dpd_fv_forward, flatten=0)
+ *   d_query [n_clouds, n_query, 3]  fp32
+ *   d_out   [n_clouds, n_query, 3]  fp32
+ *   d_idx   optional [n_clouds, n_query] int32 out (voxel index actually used)                  */
+int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, const float* d_query,
+                     const float* h_centers, const float* h_lo, const float* h_hi,
+                     const void* d_packed, float* d_out, int32_t* d_idx, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Measurement hooks (used by bench.py; no effect on results).
+ * dpd_launch_count : kernels this library has launched in this process (cumulative).
+ * dpd_profile_enable(1) brackets every kernel launch with CUDA events on the launching stream;
+ * dpd_profile_read synchronises them, writes per-kernel totals (device ms, launches) and
+ * returns the number of entries written (reset != 0 clears the totals afterwards).            */
+typedef struct dpd_profile_entry {
+  char name[48];
+  double ms;
+  long long launches;
+} dpd_profile_entry;
+
+long long dpd_launch_count(void);
+int dpd_profile_enable(int on);
+int dpd_profile_read(dpd_profile_entry* h_entries, int max_entries, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPDIST_B200_H */

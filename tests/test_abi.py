@@ -1,0 +1,82 @@
+"""CPU checks of the C-ABI boundary: the library builds/loads, exports every symbol the header
+declares, and validates arguments before touching the GPU.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from dpdist_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dpdist_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dpd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert "dpd_fv_forward" in declared and "dpd_head_forward" in declared
+    for name in declared:
+        assert hasattr(lib, name), "libdpdist_b200.so does not export %s" % name
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and include/dpdist_b200.h disagree"
+    assert lib.dpd_version() == 1
+
+
+def test_header_cites_reference_lines():
+    src = open(HEADER).read()
+    for anchor in ("utils/dpdist_util.py:22-141", "utils/dpdist_util.py:459-492", "utils/dpdist_util.py:412-544",
+                   "utils/tf_util.py:161-228"):
+        assert anchor in src
+
+
+def test_invalid_arguments_are_rejected_before_any_launch():
+    lib = _lib.load()
+    c = np.zeros(8, np.float32)
+    rc = lib.dpd_fv_forward(None, 1, 64, 8, _lib.fptr(c), 0.125, 1, 0, None, None)
+    assert rc == -1 and b"null" in lib.dpd_last_error()
+    rc = lib.dpd_fv_forward(ctypes.c_void_p(256), 1, 64, 99, _lib.fptr(c), 0.125, 1, 0, ctypes.c_void_p(256), None)
+    assert rc == -2 and b"G=99" in lib.dpd_last_error()
+    rc = lib.dpd_fv_forward(ctypes.c_void_p(256), 1, 64, 8, _lib.fptr(c), -1.0, 1, 0, ctypes.c_void_p(256), None)
+    assert rc == -1
+    rc = lib.dpd_voxel_assign(None, 1, 1, 8, _lib.fptr(c), _lib.fptr(c), _lib.fptr(c), None, None, None, None)
+    assert rc == -1
+    cfg = _lib.HeadConfig(2, 64, 8, 20, 5, 1000, 0)      # H not a multiple of 16
+    assert lib.dpd_head_packed_bytes(ctypes.byref(cfg)) == 0
+    assert b"H=1000" in lib.dpd_last_error()
+
+
+def test_head_sizes_are_consistent():
+    lib = _lib.load()
+    for flags in (_lib.HEAD_AUTO, _lib.HEAD_SIMT):
+        cfg = _lib.HeadConfig(2048, 64, 8, 20, 5, 1024, flags)
+        pb = lib.dpd_head_packed_bytes(ctypes.byref(cfg))
+        wb = lib.dpd_head_workspace_bytes(ctypes.byref(cfg))
+        assert pb >= 4666371 * 4
+        rows = 2048 * 64
+        assert wb >= 2 * rows * 1024 * 4
+        assert wb < 64 * rows * 1024 * 4
+
+
+def test_no_cpu_fallback():
+    from dpdist_b200 import dpdist_util
+    with pytest.raises(_lib.DPDistNativeError):
+        dpdist_util.get_3dmfv_tf(torch.zeros(1, 4, 3), n_gaussians=27)
+    with pytest.raises(_lib.DPDistNativeError):
+        dpdist_util.local_z(torch.zeros(1, 27, 20), None, NUM_DIMS=3, k=3)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dpdist_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f

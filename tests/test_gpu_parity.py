@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the reference-shaped
+Python API, against the CPU oracle on the same seeded inputs.  Run with -m gpu on the B200 box."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dpdist_b200 import _lib, dpdist_and_aue as MODEL, dpdist_util, synthetic, tf_util
+from oracle import dpdist_oracle as O
+from tolerances import assert_fv_close, assert_out_close
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def _cloud(seed, B, N, scale=0.9):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-scale, scale, size=(B, N, 3)).astype(np.float32)
+
+
+def _oracle_fv(pts, V, sigma, **kw):
+    with O.tf_cpu_numerics():
+        return O.get_3dmfv(torch.tensor(pts), V, sigma, **kw)
+
+
+def _store_from(var):
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    return store
+
+
+# ------------------------------------------------------------------ 3DmFV
+@pytest.mark.parametrize("G,N,sigma", [(8, 64, 0.125), (8, 1, 0.125), (8, 7, 0.125), (8, 200, 0.125), (8, 512, 0.125),
+                                       (5, 64, 0.2), (3, 33, 0.25), (4, 64, 0.25), (8, 64, 0.25), (10, 40, 0.1)])
+@pytest.mark.parametrize("full_fv", [True, False])
+def test_fv_matches_oracle(G, N, sigma, full_fv):
+    pts = _cloud(G * 1000 + N, 3, N)
+    want = _oracle_fv(pts, G ** 3, sigma, flatten=False, full_fv=full_fv)
+    got = dpdist_util.get_3dmfv_tf(torch.tensor(pts, device=DEV), n_gaussians=G ** 3, sigma=sigma, flatten=False, full_fv=full_fv)
+    assert got.shape == want.shape
+    assert_fv_close(got, want, "fv G=%d N=%d" % (G, N))
+
+
+def test_fv_flatten_and_batch_independence():
+    pts = _cloud(1, 5, 64)
+    d = torch.tensor(pts, device=DEV)
+    a = dpdist_util.get_3dmfv_tf(d, n_gaussians=512, sigma=0.125, flatten=False)
+    b = dpdist_util.get_3dmfv_tf(d, n_gaussians=512, sigma=0.125, flatten=True)
+    assert torch.equal(b.view(5, 20, 512), a.transpose(1, 2))
+    one = dpdist_util.get_3dmfv_tf(d[2:3].contiguous(), n_gaussians=512, sigma=0.125, flatten=False)
+    assert torch.equal(one[0], a[2])                               # no cross-cloud coupling, deterministic
+    assert_fv_close(b, _oracle_fv(pts, 512, 0.125, flatten=True), "fv flatten")
+
+
+def test_fv_chair_clouds_and_far_points():
+    pcA, pcB, _ = synthetic.chair_batch(3, 4, 64)
+    pts = np.concatenate([pcA, pcB], 0)
+    pts[0, :4] = [[1.4, 0, 0], [0, -1.2, 0.3], [0.99, 0.99, 0.99], [-1.0, -1.0, -1.0]]   # outside the cube: legal FV input
+    assert_fv_close(dpdist_util.get_3dmfv_tf(torch.tensor(pts, device=DEV), n_gaussians=512, sigma=0.125, flatten=False),
+                    _oracle_fv(pts, 512, 0.125, flatten=False), "fv chairs")
+
+
+def test_fv_large_batch_properties():
+    """BASELINE size (2048 clouds): size-independent properties instead of an oracle run."""
+    pcA, pcB, _ = synthetic.uniform_batch(2, 1024, 64)
+    pts = torch.tensor(np.concatenate([pcA, pcB], 0), device=DEV)
+    fv = dpdist_util.get_3dmfv_tf(pts, n_gaussians=512, sigma=0.125, flatten=False)
+    assert torch.isfinite(fv).all()
+    ss = (fv.double() ** 2).sum(1)
+    assert torch.allclose(ss, torch.ones_like(ss), atol=1e-5)              # every channel L2-normalised
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).to(DEV)
+    fv_p = dpdist_util.get_3dmfv_tf(pts[:, perm].contiguous(), n_gaussians=512, sigma=0.125, flatten=False)
+    assert (fv - fv_p).abs().max() < 2e-6                                   # permutation invariance
+    sub = _oracle_fv(pts[1000:1004].cpu().numpy(), 512, 0.125, flatten=False)
+    assert_fv_close(fv[1000:1004], sub, "fv slice of the large batch")
+
+
+# ------------------------------------------------------------------ voxel assignment / patches
+@pytest.mark.parametrize("G", [8, 5, 3, 4])
+def test_voxel_assign_bit_exact(G):
+    V = G ** 3
+    X, Y, Z = O.get_grid_centers(V, 3)
+    C = torch.tensor(np.stack([X, Y, Z], -1).astype(np.float32).reshape(-1, 3))
+    rng = np.random.default_rng(G)
+    pc = rng.uniform(-1.2, 1.2, size=(4, 300, 3)).astype(np.float32)
+    l = (np.arange(-1, 1, 2 / G) + 1 / G).astype(np.float32)
+    edges = np.concatenate([l - np.float32(1 / G), l + np.float32(1 / G), [np.float32(-1), np.float32(1)]]).astype(np.float32)
+    # points exactly on cell edges, one ulp either side, and non-finite coordinates
+    e = rng.choice(edges, size=(4, 120, 3)).astype(np.float32)
+    pc[:, :40] = e[:, :40]
+    pc[:, 40:80] = np.nextafter(e[:, 40:80], np.float32(2))
+    pc[:, 80:120] = np.nextafter(e[:, 80:120], np.float32(-2))
+    pc[0, 120] = [np.nan, 0, 0]; pc[0, 121] = [np.inf, 0, 0]; pc[0, 122] = [0, -np.inf, 0]
+    bv, off, am = O.get_pc_grid_binary_mask_from_centers(C, torch.tensor(pc))
+    bi = torch.arange(4)[:, None].expand(4, 300); ni = torch.arange(300)[None].expand(4, 300)
+    want_mask, want_off = bv[bi, ni, am], off[bi, ni, am]
+    mask, goff, idx = dpdist_util.get_pc_grid_binary_mask_from_centers(C.to(DEV), torch.tensor(pc, device=DEV))
+    assert idx.dtype == torch.int32
+    assert torch.equal(idx.cpu().long(), am)
+    assert torch.equal(mask.cpu(), want_mask)
+    fin = torch.isfinite(want_off)
+    assert torch.equal(goff.cpu()[fin], want_off[fin])
+    assert int((want_mask == 0).sum()) > 0 and int((want_mask == 1).sum()) > 0
+
+
+@pytest.mark.parametrize("G,k,C", [(8, 5, 20), (5, 3, 20), (4, 4, 7), (3, 5, 20), (8, 1, 20)])
+def test_local_patches_bit_exact(G, k, C):
+    fv = torch.randn(3, G ** 3, C, generator=torch.Generator().manual_seed(G * k))
+    want, Cw = O.local_z_3d(fv, k=k)
+    lp, Cg = dpdist_util.local_z(fv.to(DEV), None, NUM_DIMS=3, k=k)
+    assert lp.shape == want.shape
+    assert torch.equal(lp.materialize().cpu(), want)
+    assert torch.equal(Cg.cpu(), Cw)
+
+
+# ------------------------------------------------------------------ head + full model
+def _run_model(pcA, pcB, var, impl, k=5, V=512, sigma=0.125, H=1024):
+    dpdist_util.HEAD_IMPL = impl
+    try:
+        with tf_util.use_store(_store_from(var)):
+            p, _, emb = MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), False, bn=0,
+                                        Embedding_Size=V, k=k, localSNmlp=[H, H, H], sigma3dmfv=sigma, reuse=True)
+        torch.cuda.synchronize()
+        return p, emb
+    finally:
+        dpdist_util.HEAD_IMPL = _lib.HEAD_AUTO
+
+
+IMPLS = [_lib.HEAD_SIMT, _lib.HEAD_AUTO]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_model_anchor_matches_golden_and_oracle(impl):
+    z = np.load(os.path.join(GOLDEN, "anchor_A.npz"))
+    var = O.unit_scale_variables(int(z["weight_seed"]))
+    p, emb = _run_model(z["pcA"], z["pcB"], var, impl)
+    assert p["pred_listAB"].shape == (1, 64, 1, 3)
+    assert_fv_close(emb["embedding_A"].fv, z["fvA"], "fvA vs golden")
+    assert_fv_close(emb["embedding_B"].fv, z["fvB"], "fvB vs golden")
+    assert_out_close(p["pred_listAB"], z["pred_AB"], "pred_AB vs golden")
+    assert_out_close(p["pred_listBA"], z["pred_BA"], "pred_BA vs golden")
+    with O.tf_cpu_numerics():
+        po, _, _ = O.get_model(torch.tensor(z["pcA"]), torch.tensor(z["pcB"]), var)
+    assert_out_close(p["pred_listAB"], po["pred_listAB"], "pred_AB vs oracle")
+    assert_out_close(p["pred_listBA"], po["pred_listBA"], "pred_BA vs oracle")
+    tf_util.clear_collections()
+    MODEL.get_loss(p, {}, torch.tensor(z["labels"], device=DEV))
+    assert abs(float(tf_util.get_collection("loss_samples")[-1]) - float(z["loss"])) < 1e-5
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("B,seed", [(16, 7), (3, 8)])
+def test_model_batch_matches_oracle(impl, B, seed):
+    pcA, pcB, _ = synthetic.uniform_batch(seed, B, 64, outside_frac=0.05)
+    var = O.unit_scale_variables(seed)
+    p, _ = _run_model(pcA, pcB, var, impl)
+    with O.tf_cpu_numerics():
+        ab, ba = O.forward_chunked(torch.tensor(pcA), torch.tensor(pcB), var, chunk=8)
+    assert_out_close(p["pred_listAB"], ab, "pred_AB")
+    assert_out_close(p["pred_listBA"], ba, "pred_BA")
+    outside = (np.abs(pcB) > 1.0).any(-1)
+    assert outside.any() and float(p["pred_listAB"][torch.tensor(outside, device=DEV)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_model_xavier_init_matches_oracle(impl):
+    """Reference initial state (Xavier weights, zero biases): outputs ~1e-4, comparison is atol-level."""
+    pcA, pcB, _ = synthetic.chair_batch(1, 4, 64)
+    var = O.init_variables(seed=5)
+    p, _ = _run_model(pcA, pcB, var, impl)
+    with O.tf_cpu_numerics():
+        ab, ba = O.forward_chunked(torch.tensor(pcA), torch.tensor(pcB), var, chunk=4)
+    assert_out_close(p["pred_listAB"], ab)
+    assert_out_close(p["pred_listBA"], ba)
+
+
+@pytest.mark.parametrize("G,k,H", [(5, 3, 256), (4, 5, 512), (8, 3, 256)])
+def test_model_other_grids_simt(G, k, H):
+    pcA, pcB, _ = synthetic.uniform_batch(G + k, 4, 32, outside_frac=0.05)
+    var = O.init_variables(k=k, mlp=(H, H, H), seed=2, bias_std=0.05, weight_gain=(600.0, 2.0, 2.0, 1.0), out_bias=1.0)
+    p, _ = _run_model(pcA, pcB, var, _lib.HEAD_AUTO, k=k, V=G ** 3, sigma=1.0 / G, H=H)
+    with O.tf_cpu_numerics():
+        po, _, _ = O.get_model(torch.tensor(pcA), torch.tensor(pcB), var, Embedding_Size=G ** 3, k=k, sigma3dmfv=1.0 / G)
+    assert_out_close(p["pred_listAB"], po["pred_listAB"])
+    assert_out_close(p["pred_listBA"], po["pred_listBA"])
+
+
+def test_dense_patch_tensor_is_accepted_like_the_reference():
+    pcA, pcB, _ = synthetic.uniform_batch(4, 2, 64)
+    var = O.unit_scale_variables(2)
+    a, b = torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV)
+    with tf_util.use_store(_store_from(var)), tf_util.variable_scope("pc_compare", reuse=True):
+        fvA = dpdist_util.get_3dmfv_tf(a, 512, 0.125, flatten=False)
+        fvB = dpdist_util.get_3dmfv_tf(b, 512, 0.125, flatten=False)
+        eA, C = dpdist_util.local_z(fvA, False, NUM_DIMS=3, k=5)
+        eB, _ = dpdist_util.local_z(fvB, False, NUM_DIMS=3, k=5)
+        lazy = dpdist_util.DPDist(a, b, eA, eB, C, False, bn=False, NUM_DIMS=3, mlp=[1024] * 3, k=5, reuse=True)
+        dense = dpdist_util.DPDist(a, b, eA.materialize(), eB.materialize(), C, False, bn=False, NUM_DIMS=3,
+                                   mlp=[1024] * 3, k=5, reuse=True)
+    assert torch.equal(lazy[0], dense[0]) and torch.equal(lazy[1], dense[1])
+
+
+def test_full_size_batch_properties():
+    """BASELINE config B (1024 pairs): run the whole path; check range, mask, determinism, and a slice vs the oracle."""
+    pcA, pcB, _ = synthetic.uniform_batch(2, 1024, 64)
+    var = O.unit_scale_variables(4)
+    p, _ = _run_model(pcA, pcB, var, _lib.HEAD_AUTO)
+    ab, ba = p["pred_listAB"], p["pred_listBA"]
+    assert ab.shape == (1024, 64, 1, 3) and torch.isfinite(ab).all() and torch.isfinite(ba).all()
+    assert float(ab.min()) >= 0 and float(ab.max()) <= 2.0
+    p2, _ = _run_model(pcA, pcB, var, _lib.HEAD_AUTO)
+    assert torch.equal(p2["pred_listAB"], ab)
+    with O.tf_cpu_numerics():
+        oab, oba = O.forward_chunked(torch.tensor(pcA[500:508]), torch.tensor(pcB[500:508]), var, chunk=8)
+    assert_out_close(ab[500:508], oab)
+    assert_out_close(ba[500:508], oba)
+    # pairs are independent: the same pair alone gives the same answer
+    p1, _ = _run_model(pcA[500:501], pcB[500:501], var, _lib.HEAD_AUTO)
+    assert_out_close(p1["pred_listAB"], ab[500:501])

@@ -1,0 +1,46 @@
+"""Parity tolerances, written once.
+
+FV features : |a-b| <= 1e-4*|b| + 2e-6.  The absolute term covers the reference's discontinuity
+              sign(x)*sqrt(max(|x|,1e-12)) (utils/dpdist_util.py:118-121): an entry whose true value
+              underflows is 0 or +-1e-6 before the L2 normalisation depending on where exp()
+              flushes, i.e. <= 1e-6/norm after it.
+distances   : |a-b| <= 1e-4*|b| + 3e-6 on outputs in [0,2] (the fp32 oracle itself is 1.3e-6 away
+              from its fp64 twin on the anchor).
+indices     : bit-exact.
+"""
+import numpy as np
+
+FV_RTOL, FV_ATOL = 1e-4, 2e-6
+OUT_RTOL, OUT_ATOL = 1e-4, 3e-6
+
+
+def _np(x):
+    try:
+        import torch
+        if torch.is_tensor(x):
+            return x.detach().cpu().double().numpy()
+    except ImportError:
+        pass
+    return np.asarray(x, dtype=np.float64)
+
+
+def assert_close(got, want, rtol, atol, what=""):
+    g, w = _np(got), _np(want)
+    assert g.shape == w.shape, "%s: shape %s vs %s" % (what, g.shape, w.shape)
+    assert np.isfinite(g).all(), "%s: non-finite values" % what
+    err = np.abs(g - w)
+    tol = rtol * np.abs(w) + atol
+    bad = err > tol
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError("%s: %d/%d entries out of tolerance; worst at %s got %.9g want %.9g (err %.3g, tol %.3g)"
+                             % (what, bad.sum(), bad.size, i, g[i], w[i], err[i], tol[i]))
+    return float(err.max())
+
+
+def assert_fv_close(got, want, what="fv"):
+    return assert_close(got, want, FV_RTOL, FV_ATOL, what)
+
+
+def assert_out_close(got, want, what="out"):
+    return assert_close(got, want, OUT_RTOL, OUT_ATOL, what)
