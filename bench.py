@@ -278,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1:
         # bounded sample of the same workload on this box's host cores (about 10-30 s of CPU work)
         v1, t1 = cpu_reference_rate(16, 8)
-        pairs = int(min(512, max(32, 12.0 / max(t1 / 16, 1e-6))))
+        pairs = int(min(16384, max(32, 12.0 / max(t1 / 16, 1e-6))))
         pairs -= pairs % 8
         v, t = cpu_reference_rate(pairs, 8)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

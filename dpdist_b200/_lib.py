@@ -52,6 +52,9 @@ class ProfileEntry(ctypes.Structure):
 
 
 SIGNATURES.update({
+    "dpd_debug_tc_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                         ctypes.c_void_p]),
     "dpd_launch_count": (ctypes.c_longlong, []),
     "dpd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dpd_profile_read": (ctypes.c_int, [ctypes.POINTER(ProfileEntry), ctypes.c_int, ctypes.c_int]),

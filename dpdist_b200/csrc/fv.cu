@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p
   // tables: [axis(3)][type(3: q,m,s)][FV_PCHUNK][G]
   float* tab = smem;
   float* chan_ss = smem + 9 * FV_PCHUNK * G;  // [C] sum of squares per channel
+  float* warp_ss = chan_ss + DPD_FV_CHANNELS_FULL;  // [FV_THREADS/32][C] per-warp partials (fixed-order sum)
   const int cloud = blockIdx.x;
   const float* pts = p.points + (size_t)cloud * N * 3;
   float* out = p.fv + (size_t)cloud * V * C;
@@ -149,7 +150,13 @@ __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p
       float sq = x * x;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      if ((tid & 31) == 0) atomicAdd(&chan_ss[ch], sq);
+      if ((tid & 31) == 0) warp_ss[(tid >> 5) * DPD_FV_CHANNELS_FULL + ch] = sq;
+    }
+    __syncthreads();
+    if (tid < C) {   // deterministic: warps in order, Gaussian batches in order
+      float acc = chan_ss[tid];
+      for (int wv = 0; wv < FV_THREADS / 32; ++wv) acc += warp_ss[wv * DPD_FV_CHANNELS_FULL + tid];
+      chan_ss[tid] = acc;
     }
   }
   __syncthreads();
@@ -185,7 +192,7 @@ extern "C" int dpd_fv_forward(const float* d_points, int n_clouds, int n_points,
   cudaStream_t st = (cudaStream_t)stream;
   int r = fv_forward_optimized(p, st);
   if (r <= 0) return r;
-  size_t smem = (size_t)(9 * FV_PCHUNK * G + DPD_FV_CHANNELS_FULL) * sizeof(float);
+  size_t smem = (size_t)(9 * FV_PCHUNK * G + DPD_FV_CHANNELS_FULL * (1 + FV_THREADS / 32)) * sizeof(float);
   DPD_LAUNCH("fv_generic", st, fv_generic_kernel<<<n_clouds, FV_THREADS, smem, st>>>(p));
   DPD_CUDA_CHECK_LAUNCH("fv_generic_kernel");
   return 0;

@@ -165,6 +165,10 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
   GridTables t;
   fill_tables(t, cfg->G, h_centers, h_lo, h_hi);
 
+  if (L.impl == DPD_HEAD_TC) {
+    rc = tc_prepare_fv(*cfg, d_fv, ws + W.tc, chunk, st);
+    if (rc) return rc;
+  }
   for (size_t r0 = 0; r0 < M; r0 += chunk) {
     const int rows = (int)((M - r0 < chunk) ? (M - r0) : chunk);
     int32_t* idx = (int32_t*)(ws + W.idx);
@@ -181,7 +185,7 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
     g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
     const float* h3 = nullptr;
     if (L.impl == DPD_HEAD_TC) {
-      rc = tc_head_layers(*cfg, L.Kp1, g, rows, pk + L.tc, (const float*)(pk + L.b1), (const float*)(pk + L.b2),
+      rc = tc_head_layers(*cfg, L.Kp1, g, rows, chunk, pk + L.tc, (const float*)(pk + L.b1), (const float*)(pk + L.b2),
                           (const float*)(pk + L.b3), ha, hb, ws + W.tc, &h3, st);
       if (rc) return rc;
     } else {
@@ -202,4 +206,11 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
     if (rc) return rc;
   }
   return 0;
+}
+
+extern "C" int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
+                                 float* d_out, void* d_scratch, size_t scratch_bytes, void* stream) {
+  using namespace dpd;
+  DPD_REQUIRE(d_a && d_w && d_bias && d_out && d_scratch, DPD_E_INVALID, "dpd_debug_tc_gemm: null pointer");
+  return tc_debug_gemm(d_a, M, K, d_w, N, d_bias, d_out, d_scratch, scratch_bytes, (cudaStream_t)stream);
 }

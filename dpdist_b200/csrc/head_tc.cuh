@@ -12,9 +12,15 @@ size_t tc_workspace_bytes(const dpd_head_config& c, size_t rows);
 int tc_pack_weights(const dpd_head_config& c, int Kp1, const float* w1p, const float* w2, const float* w3,
                     void* tc_blob, cudaStream_t st);
 
+// once per head call: hi/lo split of the whole FV tensor into the tc workspace (laid out for ws_rows)
+int tc_prepare_fv(const dpd_head_config& c, const float* fv, void* tc_ws, size_t ws_rows, cudaStream_t st);
+
 // runs layers 1..3 for `rows` chunk-local rows; *h3 points at the fp32 [rows,H] layer-3 activations
-int tc_head_layers(const dpd_head_config& c, int Kp1, const GatherDesc& g, int rows, const void* tc_blob,
+int tc_head_layers(const dpd_head_config& c, int Kp1, const GatherDesc& g, int rows, size_t ws_rows, const void* tc_blob,
                    const float* b1, const float* b2, const float* b3, float* ha, float* hb, void* tc_ws,
                    const float** h3, cudaStream_t st);
+
+int tc_debug_gemm(const float* a, int M, int K, const float* w, int N, const float* bias, float* out, void* scratch,
+                  size_t scratch_bytes, cudaStream_t st);
 
 }  // namespace dpd

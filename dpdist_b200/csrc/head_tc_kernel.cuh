@@ -1,0 +1,295 @@
+// The persistent tcgen05 GEMM kernel of the head (included by head_tc.cu only).
+//
+// Accuracy note (measured on B200): tcgen05.mma adds into the fp32 TMEM accumulator with
+// truncation, so a long K loop drifts by ~0.5 ulp per MMA (3.5e-5 absolute at K=1024 with three
+// MMAs per K-step).  Like NVIDIA's FastF32 kernels (AccPromotionInterval), the K loop is therefore
+// cut into segments of SEG_KB K-blocks: each segment accumulates into one of two TMEM buffers
+// starting from zero, and the epilogue warps promote finished segments into per-thread fp32
+// register sums with round-to-nearest adds while the next segment runs.
+#pragma once
+
+namespace dpd {
+namespace tc {
+
+constexpr int SEG_KB = 4;            // K-blocks (of 32) per TMEM accumulation segment
+constexpr int NUM_EPI_WARPS = 8;     // 2 per TMEM lane quarter, 128 columns each
+constexpr int EPI_COLS = BN / 2;
+
+struct GatherArgs {
+  const float* fv_hi;
+  const float* fv_lo;
+  const int32_t* idx;      // [rows] chunk-local voxel index
+  const float* off4_hi;    // [rows,4]
+  const float* off4_lo;
+  long long row0;          // global row of chunk-local row 0
+  int n_query, G, C, k, E;
+};
+
+struct KernelArgs {
+  int M, N, num_kb;        // rows, output features, K / 32
+  const float* bias;       // [N]
+  float* out0;             // split ? hi : value
+  float* out1;             // split ? lo : unused
+  int split;
+  GatherArgs g;
+};
+
+struct __align__(8) SharedCtl {
+  uint64_t full[STAGES], empty[STAGES], seg_full[2], seg_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  int32_t row_base[BM];    // element offset of the row's cloud in fv (-1: row past M)
+  uint32_t row_vox[BM];    // i0 | i1<<8 | i2<<16
+};
+
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 epilogue | 12-15 gather (layer 1)
+template <bool GATHER>
+__global__ void __launch_bounds__(GATHER ? 512 : 384, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const KernelArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  SharedCtl* ctl = (SharedCtl*)(smem + STAGES * STAGE_BYTES);
+  uint32_t* lut = (uint32_t*)(ctl + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m_tiles = (args.M + BM - 1) / BM;
+  const int num_n_tiles = args.N / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 Ah, 1 Al, 2 Bh, 3 Bl
+    uint8_t* b = smem + s * STAGE_BYTES;
+    return which == 0 ? b : which == 1 ? b + A_TILE : which == 2 ? b + 2 * A_TILE : b + 2 * A_TILE + B_TILE;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
+    if (!GATHER) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&ctl->full[s], GATHER ? (1 + NUM_GATHER_THREADS) : 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ctl->seg_full[a], 1);
+      mbar_init(&ctl->seg_empty[a], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+  if (GATHER) {
+    // chunk LUT: 4-float chunk q of the virtual row -> (a0,a1,a2,part) | OFFS | ZERO
+    const int nchunks = args.num_kb * (BK / 4);
+    const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4;
+    for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
+      uint32_t code;
+      if (q < ech) {
+        const int e = q * 4, j = e / Cc, part = e - j * Cc;
+        const int a2 = j % kk, a1 = (j / kk) % kk, a0 = j / (kk * kk);
+        code = (uint32_t)part | ((uint32_t)a0 << 8) | ((uint32_t)a1 << 16) | ((uint32_t)a2 << 24);
+      } else {
+        code = (q == ech) ? LUT_OFFS : LUT_ZERO;
+      }
+      lut[q] = code;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < 4) {
+    reg_dec<56>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&ctl->full[s], GATHER ? 2 * B_TILE : STAGE_BYTES);
+          tma_load_2d(stage_ptr(s, 2), &tm_b_hi, &ctl->full[s], kb * BK, nt * BN);
+          tma_load_2d(stage_ptr(s, 3), &tm_b_lo, &ctl->full[s], kb * BK, nt * BN);
+          if (!GATHER) {
+            tma_load_2d(stage_ptr(s, 0), &tm_a_hi, &ctl->full[s], kb * BK, mt * BM);
+            tma_load_2d(stage_ptr(s, 1), &tm_a_lo, &ctl->full[s], kb * BK, mt * BM);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      int s = 0; uint32_t ph = 0;
+      int sb = 0; uint32_t sb_ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG_KB) {
+          mbar_wait(&ctl->seg_empty[sb], sb_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
+          uint32_t accumulate = 0;        // every segment starts from zero
+          const int kb1 = min(kb0 + SEG_KB, args.num_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&ctl->full[s], ph);
+            tc_fence_after();
+            const uint64_t ah = make_desc_sw128(smem_u32(stage_ptr(s, 0)));
+            const uint64_t al = make_desc_sw128(smem_u32(stage_ptr(s, 1)));
+            const uint64_t bh = make_desc_sw128(smem_u32(stage_ptr(s, 2)));
+            const uint64_t bl = make_desc_sw128(smem_u32(stage_ptr(s, 3)));
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t o = (uint64_t)(ks * 2);   // +32 bytes per K-step of 8 tf32, in 16-byte units
+              umma_tf32(d_tmem, al + o, bh + o, IDESC, accumulate);   // small correction terms first
+              umma_tf32(d_tmem, ah + o, bl + o, IDESC, 1);
+              umma_tf32(d_tmem, ah + o, bh + o, IDESC, 1);
+              accumulate = 1;
+            }
+            umma_commit(&ctl->empty[s]);     // frees the smem slot when these MMAs retire
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit(&ctl->seg_full[sb]);   // segment ready for promotion
+          if (++sb == 2) { sb = 0; sb_ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4 + NUM_EPI_WARPS) {
+    // ===================== epilogue: segment promotion + bias/ReLU/split/store =====================
+    if (GATHER) reg_inc<176>(); else reg_inc<216>();
+    const int e = warp - 4;
+    const int q = e & 3;                    // TMEM lane quarter (== warp % 4)
+    const int half = e >> 2;                // which 128 of the 256 columns
+    int sb = 0; uint32_t sb_ph = 0;
+    float sum[EPI_COLS];
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+      bool first = true;
+      for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG_KB) {
+        mbar_wait(&ctl->seg_full[sb], sb_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * BN + half * EPI_COLS);
+#pragma unroll
+        for (int c = 0; c < EPI_COLS / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (first) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        first = false;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->seg_empty[sb]);
+        if (++sb == 2) { sb = 0; sb_ph ^= 1; }
+      }
+      const int row = mt * BM + q * 32 + lane;
+      if (row < args.M) {
+        const size_t o = (size_t)row * args.N + (size_t)nt * BN + (size_t)half * EPI_COLS;
+        const float* bias = args.bias + nt * BN + half * EPI_COLS;
+        float* o0 = args.out0 + o;
+        float* o1 = args.split ? args.out1 + o : nullptr;
+#pragma unroll
+        for (int j = 0; j < EPI_COLS; j += 4) {
+          float x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = fmaxf(sum[j + u] + __ldg(bias + j + u), 0.f);
+          if (args.split) {
+            float4 hi, lo;
+            hi.x = tf32_rna(x[0]); hi.y = tf32_rna(x[1]); hi.z = tf32_rna(x[2]); hi.w = tf32_rna(x[3]);
+            lo.x = tf32_rna(x[0] - hi.x); lo.y = tf32_rna(x[1] - hi.y); lo.z = tf32_rna(x[2] - hi.z); lo.w = tf32_rna(x[3] - hi.w);
+            *reinterpret_cast<float4*>(o0 + j) = hi;
+            *reinterpret_cast<float4*>(o1 + j) = lo;
+          } else {
+            *reinterpret_cast<float4*>(o0 + j) = make_float4(x[0], x[1], x[2], x[3]);
+          }
+        }
+      }
+    }
+  } else if (GATHER) {
+    // ===================== patch-gather producers (layer 1) =====================
+    reg_dec<96>();
+    const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;   // 0..127
+    const int sub = p >> 3, chunk = p & 7;                  // 8 consecutive lanes fill one 128-byte row
+    const GatherArgs& g = args.g;
+    const int G = g.G, Cc = g.C, pb = (g.k - 1) >> 1;
+    const int V = G * G * G;
+    int s = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t / num_n_tiles;
+      // per-tile row table (the previous tile's cp.asyncs have all been issued before the barrier)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      {
+        const int m = mt * BM + p;
+        int32_t base = -1; uint32_t vox = 0;
+        if (m < args.M) {
+          const long long cloud = (g.row0 + m) / g.n_query;
+          base = (int32_t)(cloud * V * Cc);
+          const int v = g.idx[m];
+          vox = (uint32_t)(v / (G * G)) | ((uint32_t)((v / G) % G) << 8) | ((uint32_t)(v % G) << 16);
+        }
+        ctl->row_base[p] = base;
+        ctl->row_vox[p] = vox;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int kb = 0; kb < args.num_kb; ++kb) {
+        mbar_wait(&ctl->empty[s], ph ^ 1);
+        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+        const uint32_t code = lut[kb * 8 + chunk];
+#pragma unroll
+        for (int it = 0; it < BM / 16; ++it) {
+          const int r = it * 16 + sub;
+          const uint32_t dst = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+          const int32_t base = ctl->row_base[r];
+          const float* src_hi = g.fv_hi;
+          const float* src_lo = g.fv_lo;
+          uint32_t nbytes = 0;
+          if (base >= 0 && code != LUT_ZERO) {
+            if (code == LUT_OFFS) {
+              const size_t m = (size_t)mt * BM + r;
+              src_hi = g.off4_hi + m * 4; src_lo = g.off4_lo + m * 4; nbytes = 16;
+            } else {
+              const uint32_t vox = ctl->row_vox[r];
+              const int n0 = (int)(vox & 255) + (int)((code >> 8) & 255) - pb;
+              const int n1 = (int)((vox >> 8) & 255) + (int)((code >> 16) & 255) - pb;
+              const int n2 = (int)((vox >> 16) & 255) + (int)(code >> 24) - pb;
+              if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
+                const size_t el = (size_t)base + (size_t)(((n0 * G + n1) * G + n2) * Cc) + (code & 255);
+                src_hi = g.fv_hi + el; src_lo = g.fv_lo + el; nbytes = 16;
+              }
+            }
+          }
+          cp_async16(a_hi + dst, src_hi, nbytes);
+          cp_async16(a_lo + dst, src_lo, nbytes);
+        }
+        // arrive on full[s] when this thread's copies have landed (same protocol as CUTLASS's
+        // sm100 cp.async mainloop: cp.async.mbarrier.arrive, then the UMMA consumer waits on the mbarrier)
+        cp_async_arrive_noinc(&ctl->full[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace dpd

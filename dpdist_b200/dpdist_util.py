@@ -186,15 +186,18 @@ def get_pc_grid_binary_mask_from_centers(Centers, point_cloud):
 # implicit distance head
 # --------------------------------------------------------------------------------------
 class _PackedHead:
-    """Kernel-layout copy of the four conv layers, rebuilt when any variable changes."""
+    """Kernel-layout copy of the four conv layers, rebuilt when any variable changes.  The cache key is
+    the identity of the variable objects (kept alive here so ids cannot be recycled) plus their
+    in-place version counters, so optimizer steps and load_state_dict both invalidate it."""
 
     def __init__(self):
         self.key = None
+        self.owners = None
         self.blob = None
         self.ws = None
 
-    def get(self, lib, cfg, ws_list):
-        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags) + tuple((w.data_ptr(), w._version) for w in ws_list)
+    def get(self, lib, cfg, weights, ws_list):
+        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags) + tuple((id(w), w._version) for w in weights)
         if key != self.key:
             nbytes = lib.dpd_head_packed_bytes(ctypes.byref(cfg))
             if nbytes == 0:
@@ -204,6 +207,7 @@ class _PackedHead:
             rc = lib.dpd_head_pack_weights(ctypes.byref(cfg), *[_ptr(w) for w in ws_list], _ptr(self.blob), _stream())
             _lib.check(rc, "dpd_head_pack_weights")
             self.key = key
+            self.owners = list(weights)
         return self.blob
 
     def workspace(self, lib, cfg, device):
@@ -243,7 +247,7 @@ def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
     idx = torch.empty((n_clouds, NP), device=fv.device, dtype=torch.int32) if return_idx else None
     with torch.cuda.device(fv.device):
         cache = _PACKED.setdefault((fv.device, cfg.flags), _PackedHead())
-        blob = cache.get(lib, cfg, ws_list)
+        blob = cache.get(lib, cfg, list(weights), ws_list)
         ws = cache.workspace(lib, cfg, fv.device)
         rc = lib.dpd_head_forward(ctypes.byref(cfg), _ptr(fv), _ptr(query), _lib.fptr(l), _lib.fptr(lo),
                                   _lib.fptr(hi), _ptr(blob), _ptr(out),

@@ -109,6 +109,12 @@ int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, const float*
                      const void* d_packed, float* d_out, int32_t* d_idx, void* d_workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Test hook for the tensor-core GEMM used by layers 2-3 of the head:
+ *   d_out[M,N] = relu(d_a[M,K] . d_w[K,N] + d_bias[N]),  K % 32 == 0, N % 256 == 0,
+ * computed with the split-precision tcgen05 kernel.  d_scratch >= 8*(M*K + N*K) bytes.        */
+int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
+                      float* d_out, void* d_scratch, size_t scratch_bytes, void* stream);
+
 /* Measurement hooks (used by bench.py; no effect on results).
  * dpd_launch_count : kernels this library has launched in this process (cumulative).
  * dpd_profile_enable(1) brackets every kernel launch with CUDA events on the launching stream;
