@@ -275,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
                      "bytes_per_cloud": FV_BYTES_PER_CLOUD, "peak_source": peaks["source"]}
 
     cpu_baseline = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not os.environ.get("DPD_BENCH_NO_CPU"):
         # bounded sample of the same workload on this box's host cores (about 10-30 s of CPU work)
         v1, t1 = cpu_reference_rate(16, 8)
         pairs = int(min(16384, max(32, 12.0 / max(t1 / 16, 1e-6))))
