@@ -7,30 +7,12 @@
 // Per point only 3*G exps are evaluated; the N*G^3 pair work is multiplies + sum/max/min.
 //
 // fv_generic_kernel: any G <= 16, any N, full or small FV.  One CTA per cloud.
-#include "common.cuh"
+#include "fv.cuh"
 
 namespace dpd {
 
 constexpr int FV_THREADS = 256;
 constexpr int FV_PCHUNK = 32;  // points per smem table chunk (generic kernel)
-
-struct FvParams {
-  const float* points;  // [n_clouds, N, 3]
-  float* fv;            // [n_clouds, V, C] or [n_clouds, C*V]
-  int n_clouds, N, G, V, C;
-  int full_fv, flatten;
-  float sigma;
-  float c[DPD_MAX_GRID];
-};
-
-// channel bookkeeping: raw accumulators per Gaussian, in the reference's output order
-//   full : [pi_mean, pi_max, mu_mean xyz, mu_max xyz, mu_min xyz, sig_mean xyz, sig_max xyz, sig_min xyz]
-//   small: [pi_mean, mu_mean xyz, sig_mean xyz]
-__device__ __forceinline__ float power_norm(float x) {
-  // sign(x) * pow(max(|x|, 1e-12), 0.5)   (utils/dpdist_util.py:118-121); sign(0) = 0
-  if (x == 0.f) return 0.f;
-  return copysignf(sqrtf(fmaxf(fabsf(x), 1e-12f)), x);
-}
 
 __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p) {
   extern __shared__ float smem[];
@@ -168,8 +150,6 @@ __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p
     out[i] = out[i] * inv;
   }
 }
-
-int fv_forward_optimized(const FvParams& p, cudaStream_t stream);  // fv_g8.cu; returns 1 if not applicable
 
 }  // namespace dpd
 

@@ -169,6 +169,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int q = e & 3;                    // TMEM lane quarter (== warp % 4)
     const int half = e >> 2;                // which 128 of the 256 columns
     int sb = 0; uint32_t sb_ph = 0;
+    // Register sums in the tcgen05.ld 16x256b fragment layout: load (rh, cg) covers TMEM lanes
+    // 32q+16rh..+16 and columns 64cg..+64; register i = 4j+u of that load holds
+    //   row 16rh + lane/4 + 8*(u>>1),  column 64cg + 8j + 2*(lane%4) + (u&1)
+    // so a quad of lanes owns 8 consecutive columns of a row and every store is a full 32-byte sector.
     float sum[EPI_COLS];
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
@@ -176,18 +180,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG_KB) {
         mbar_wait(&ctl->seg_full[sb], sb_ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * BN + half * EPI_COLS);
 #pragma unroll
-        for (int c = 0; c < EPI_COLS / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(c * 32), v);
-          tmem_ld_wait();
-          if (first) {
+        for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[c * 32 + j] = __uint_as_float(v[j]);
-          } else {
+          for (int cg = 0; cg < 2; ++cg) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32 + rh * 16) << 16) +
+                                   (uint32_t)(sb * BN + half * EPI_COLS + cg * 64);
+            uint32_t v[32];
+            tmem_ld_16x256b_x8(taddr, v);
+            tmem_ld_wait();
+            float* sp = sum + (rh * 2 + cg) * 32;
+            if (first) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j) sp[j] = __uint_as_float(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sp[j] += __uint_as_float(v[j]);
+            }
           }
         }
         first = false;
@@ -196,25 +205,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (lane == 0) mbar_arrive(&ctl->seg_empty[sb]);
         if (++sb == 2) { sb = 0; sb_ph ^= 1; }
       }
-      const int row = mt * BM + q * 32 + lane;
-      if (row < args.M) {
-        const size_t o = (size_t)row * args.N + (size_t)nt * BN + (size_t)half * EPI_COLS;
-        const float* bias = args.bias + nt * BN + half * EPI_COLS;
-        float* o0 = args.out0 + o;
-        float* o1 = args.split ? args.out1 + o : nullptr;
+      const int col0 = nt * BN + half * EPI_COLS + 2 * (lane & 3);
 #pragma unroll
-        for (int j = 0; j < EPI_COLS; j += 4) {
-          float x[4];
+      for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = fmaxf(sum[j + u] + __ldg(bias + j + u), 0.f);
-          if (args.split) {
-            float4 hi, lo;
-            hi.x = tf32_rna(x[0]); hi.y = tf32_rna(x[1]); hi.z = tf32_rna(x[2]); hi.w = tf32_rna(x[3]);
-            lo.x = tf32_rna(x[0] - hi.x); lo.y = tf32_rna(x[1] - hi.y); lo.z = tf32_rna(x[2] - hi.z); lo.w = tf32_rna(x[3] - hi.w);
-            *reinterpret_cast<float4*>(o0 + j) = hi;
-            *reinterpret_cast<float4*>(o1 + j) = lo;
-          } else {
-            *reinterpret_cast<float4*>(o0 + j) = make_float4(x[0], x[1], x[2], x[3]);
+        for (int j = 0; j < 8; ++j) {
+          const int col = col0 + cg * 64 + j * 8;
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              const int row = mt * BM + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
+              if (row < args.M) {
+                const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
+                const float x0 = fmaxf(sp[0] + bb.x, 0.f), x1 = fmaxf(sp[1] + bb.y, 0.f);
+                const size_t o = (size_t)row * args.N + col;
+                if (args.split) {
+                  float2 hi, lo;
+                  hi.x = tf32_rna(x0); hi.y = tf32_rna(x1);
+                  lo.x = tf32_rna(x0 - hi.x); lo.y = tf32_rna(x1 - hi.y);
+                  *reinterpret_cast<float2*>(args.out0 + o) = hi;
+                  *reinterpret_cast<float2*>(args.out1 + o) = lo;
+                } else {
+                  *reinterpret_cast<float2*>(args.out0 + o) = make_float2(x0, x1);
+                }
+              }
+            }
           }
         }
       }
