@@ -1,14 +1,15 @@
 // 3DmFV kernel specialised for the reference default grid (G = 8, 512 Gaussians, full 20-channel FV).
 // Replaces get_3dmfv_tf (reference utils/dpdist_util.py:22-141) for that configuration.
 //
-// One 128-thread CTA encodes one cloud at a time (grid-stride over clouds).
-//   phase 1  per 64-point chunk: per-axis tables q, m = q*z, s = q*(z^2-1) in shared memory
-//            (3*8 exps per point; 8 lanes cooperate on one (point, axis) and reduce with shuffles)
+// One 128-thread CTA encodes one cloud at a time (grid-stride over clouds); work item = (cloud, 64-point chunk).
+//   phase 0  the next item's points are prefetched into the other half of a double buffer with cp.async
+//   phase 1  per-axis tables q, m = q*z, s = q*(z^2-1) in shared memory: one thread per (point, axis)
+//            computes the 8 cells in registers (8 independent exps, no shuffles)
 //   phase 2  thread (col = i0*8+i1, h) owns Gaussians (i0, i1, 4h..4h+3): per point 5 LDS.128, 5 products,
 //            then 7 channels x 4 Gaussians of multiply / add / max / min.  Products and sums use the
 //            packed fp32x2 instructions (FMUL2 / FADD2), max/min fold two points per FMNMX3.
 //   phase 3  scale + power-normalise into a channel-major staging tile, per-channel L2 norm over the 512
-//            Gaussians (fixed-order warp reductions), coalesced float4 copy-out.
+//            Gaussians (fixed-order reductions, deterministic), coalesced float4 copy-out.
 // Algorithmic HBM traffic: 4*(3N + 20*512) bytes per cloud (read points once, write the FV once).
 #include "fv.cuh"
 
@@ -23,13 +24,15 @@ constexpr int PITCH = V8 + 4;    // staging pitch (floats) per channel
 struct __align__(16) Smem {
   union {
     struct {
-      float4 tx[PC][G8];         // x axis (<-> i1): {q, m, s, 0}
-      float4 ty[PC][G8];         // y axis (<-> i0)
-      float4 qz[PC][2], mz[PC][2], sz[PC][2];   // z axis (<-> i2), 8 values as two float4
+      // row pitches of 9 / 3 float4 (not 8 / 2) so that the phase-1 stores of consecutive points,
+      // which come from different lanes of one warp, fall into different 16-byte bank groups
+      float4 tx[PC][G8 + 1];     // x axis (<-> i1): {q, m, s, 0}
+      float4 ty[PC][G8 + 1];     // y axis (<-> i0)
+      float4 qz[PC][3], mz[PC][3], sz[PC][3];   // z axis (<-> i2), 8 values as two float4 (+1 pad)
     } t;
     float stage[C20 * PITCH];    // [channel][gaussian], written after the tables are dead
   } u;
-  float pts[PC * 3];
+  float pts[2][PC * 3];          // double-buffered point chunks
   float inv_norm[C20];
 };
 
@@ -46,13 +49,18 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
 
-// sign(x)*sqrt(max(|x|,1e-12)) with the 1-ulp hardware square root (sqrt.approx): 5 instructions instead
-// of ~25 for the IEEE sqrtf; 80 of these per thread per cloud.
+// sign(x)*sqrt(max(|x|,1e-12)) with the hardware square root (sqrt.approx, ~1 ulp)
 __device__ __forceinline__ float power_norm_fast(float x) {
   float r;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(fabsf(x), 1e-12f)));
   return x == 0.f ? 0.f : copysignf(r, x);
 }
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // per-thread running statistics for its 4 Gaussians (two packed pairs)
 struct Acc {
@@ -61,7 +69,6 @@ struct Acc {
   float2 mn[6][2];    // minima: mu xyz, sigma xyz
 };
 
-// the 7 per-pair values of one point for Gaussian pair jp: [Q, dmx, dmy, dmz, dsx, dsy, dsz]
 struct PointTerms {
   float a, bx, by, cx, cy;       // qy*qx, qy*mx, my*qx, qy*sx, sy*qx
   float4 qz, mz, sz;
@@ -75,6 +82,7 @@ __device__ __forceinline__ PointTerms load_terms(const Smem& sm, int p, int i0, 
   return t;
 }
 
+// the 7 per-pair values of one point for Gaussian pair jp: [Q, dmx, dmy, dmz, dsx, dsy, dsz]
 __device__ __forceinline__ void pair_values(const PointTerms& t, int jp, float2 (&v)[7]) {
   const float2 qz = jp ? make_float2(t.qz.z, t.qz.w) : make_float2(t.qz.x, t.qz.y);
   const float2 mz = jp ? make_float2(t.mz.z, t.mz.w) : make_float2(t.mz.x, t.mz.y);
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = tid >> 6, col = tid & 63, i0 = col >> 3, i1 = col & 7;
   const int N = p.N;
-  const float ci = p.c[tid & 7];                 // this thread's table column in phase 1
+  const int nchunk = (N + PC - 1) / PC;
   const float w = 1.0f / (float)V8;              // tf.ones/n_gaussians (:49)
   const float sqrt_w = sqrtf(w);
   const float c_pi = 1.0f / (sqrt_w * (float)N); // (:78)
@@ -103,8 +111,17 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
   const float inv_n = 1.0f / (float)N;
   const float inv_sigma = 1.0f / p.sigma;        // exact for the reference's power-of-two sigmas
 
+  auto prefetch = [&](int cloud, int chunk, int buf) {
+    const int n0 = chunk * PC, np = min(PC, N - n0);
+    const float* src = p.points + ((size_t)cloud * N + n0) * 3;
+    for (int i = tid; i < np * 3; i += T8) cp_async4(&sm.pts[buf][i], src + i);
+    cp_async_commit();
+  };
+
+  int buf = 0;
+  if ((int)blockIdx.x < p.n_clouds) prefetch(blockIdx.x, 0, 0);
+
   for (int cloud = blockIdx.x; cloud < p.n_clouds; cloud += gridDim.x) {
-    const float* pts = p.points + (size_t)cloud * N * 3;
     Acc acc;
 #pragma unroll
     for (int c = 0; c < 7; ++c)
@@ -115,36 +132,44 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
         if (c < 6) acc.mn[c][jp] = make_float2(INFINITY, INFINITY);
       }
 
-    for (int n0 = 0; n0 < N; n0 += PC) {
-      const int np = min(PC, N - n0);
-      __syncthreads();   // previous chunk's tables / previous cloud's staging are dead
-      for (int i = tid; i < np * 3; i += T8) sm.pts[i] = pts[(size_t)n0 * 3 + i];
-      __syncthreads();
-      // ---- phase 1: tables.  task = (point, axis, cell); 8 consecutive lanes share (point, axis)
-      const int ntask = np * 24;
-      for (int t0 = 0; t0 < ntask; t0 += T8) {
-        const int t = t0 + tid;
-        const bool ok = t < ntask;
-        const int pa = ok ? (t >> 3) : 0;
-        const int pp = pa / 3, a = pa - pp * 3;
-        const float x = sm.pts[pp * 3 + a];
-        const float z = (x - ci) * inv_sigma;
-        const float e = __expf(-0.5f * z * z);
-        float S = e;
-        S += __shfl_xor_sync(0xffffffffu, S, 1);
-        S += __shfl_xor_sync(0xffffffffu, S, 2);
-        S += __shfl_xor_sync(0xffffffffu, S, 4);
-        const float q = __fdividef(e, S);
-        const float m = q * z, s = q * (z * z - 1.0f);
-        if (ok) {
-          const int i = tid & 7;
-          if (a == 0) sm.u.t.tx[pp][i] = make_float4(q, m, s, 0.f);
-          else if (a == 1) sm.u.t.ty[pp][i] = make_float4(q, m, s, 0.f);
-          else {
-            reinterpret_cast<float*>(&sm.u.t.qz[pp][0])[i] = q;
-            reinterpret_cast<float*>(&sm.u.t.mz[pp][0])[i] = m;
-            reinterpret_cast<float*>(&sm.u.t.sz[pp][0])[i] = s;
-          }
+    for (int chunk = 0; chunk < nchunk; ++chunk) {
+      const int np = min(PC, N - chunk * PC);
+      cp_async_wait_all();
+      __syncthreads();   // this item's points have landed; previous tables / staging are dead
+      {                  // phase 0: prefetch the next item into the other buffer
+        int ncloud = cloud, nchk = chunk + 1;
+        if (nchk == nchunk) { nchk = 0; ncloud += gridDim.x; }
+        if (ncloud < p.n_clouds) prefetch(ncloud, nchk, buf ^ 1);
+      }
+      // ---- phase 1: tables, one thread per (point, axis); task index == offset into the chunk's xyz list
+      for (int task = tid; task < np * 3; task += T8) {
+        const int pp = task / 3, a = task - pp * 3;
+        const float x = sm.pts[buf][task];
+        float q[8], m[8], s[8];
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = (x - p.c[i]) * inv_sigma;
+          m[i] = z;
+          q[i] = __expf(-0.5f * z * z);
+          S += q[i];
+        }
+        const float inv = __fdividef(1.0f, S);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = m[i];
+          q[i] *= inv;
+          m[i] = q[i] * z;
+          s[i] = q[i] * (z * z - 1.0f);
+        }
+        if (a == 2) {
+          sm.u.t.qz[pp][0] = make_float4(q[0], q[1], q[2], q[3]); sm.u.t.qz[pp][1] = make_float4(q[4], q[5], q[6], q[7]);
+          sm.u.t.mz[pp][0] = make_float4(m[0], m[1], m[2], m[3]); sm.u.t.mz[pp][1] = make_float4(m[4], m[5], m[6], m[7]);
+          sm.u.t.sz[pp][0] = make_float4(s[0], s[1], s[2], s[3]); sm.u.t.sz[pp][1] = make_float4(s[4], s[5], s[6], s[7]);
+        } else {
+          float4* dst = (a == 0) ? sm.u.t.tx[pp] : sm.u.t.ty[pp];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(q[i], m[i], s[i], 0.f);
         }
       }
       __syncthreads();
@@ -188,6 +213,7 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
           }
         }
       }
+      buf ^= 1;
     }
     __syncthreads();   // tables dead -> staging
     // ---- phase 3a: scale, power-normalise, stage channel-major.  Output channel order (:134-137):
@@ -215,37 +241,54 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
     }
     __syncthreads();
     // ---- phase 3b: per-channel L2 norm over the 512 Gaussians (tf.nn.l2_normalize(dim=1), :124-126)
-    for (int ch = warp; ch < C20; ch += T8 / 32) {
-      float ss = 0.f;
+    {
+      float ss[5];
 #pragma unroll
-      for (int k = 0; k < V8 / 32; ++k) {
-        const float x = sm.u.stage[ch * PITCH + lane + 32 * k];
-        ss = fmaf(x, x, ss);
+      for (int j = 0; j < 5; ++j) {      // the warp's five channels are loaded and reduced together
+        const float4* row = reinterpret_cast<const float4*>(&sm.u.stage[(warp + 4 * j) * PITCH]);
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = row[lane + 32 * k];
+        float s0 = v[0].x * v[0].x, s1 = v[1].x * v[1].x, s2 = v[2].x * v[2].x, s3 = v[3].x * v[3].x;
+        s0 = fmaf(v[0].y, v[0].y, s0); s1 = fmaf(v[1].y, v[1].y, s1); s2 = fmaf(v[2].y, v[2].y, s2); s3 = fmaf(v[3].y, v[3].y, s3);
+        s0 = fmaf(v[0].z, v[0].z, s0); s1 = fmaf(v[1].z, v[1].z, s1); s2 = fmaf(v[2].z, v[2].z, s2); s3 = fmaf(v[3].z, v[3].z, s3);
+        s0 = fmaf(v[0].w, v[0].w, s0); s1 = fmaf(v[1].w, v[1].w, s1); s2 = fmaf(v[2].w, v[2].w, s2); s3 = fmaf(v[3].w, v[3].w, s3);
+        ss[j] = (s0 + s1) + (s2 + s3);
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      if (lane == 0) sm.inv_norm[ch] = rsqrtf(fmaxf(ss, 1e-12f));
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
+      if (lane < 5) {
+        float sel = ss[0];
+#pragma unroll
+        for (int j = 1; j < 5; ++j) sel = (lane == j) ? ss[j] : sel;
+        sm.inv_norm[warp + 4 * lane] = rsqrtf(fmaxf(sel, 1e-12f));
+      }
     }
     __syncthreads();
     // ---- phase 3c: copy-out, float4, coalesced
     float* out = p.fv + (size_t)cloud * V8 * C20;
     if (p.flatten) {
+#pragma unroll 4
       for (int e4 = tid; e4 < V8 * C20 / 4; e4 += T8) {
-        const int ch = e4 / (V8 / 4), g = (e4 - ch * (V8 / 4)) * 4;
+        const int ch = e4 >> 7, g = (e4 & 127) * 4;
         float4 v = *reinterpret_cast<const float4*>(&sm.u.stage[ch * PITCH + g]);
         const float s = sm.inv_norm[ch];
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
         reinterpret_cast<float4*>(out)[e4] = v;
       }
-    } else {
-      for (int e4 = tid; e4 < V8 * C20 / 4; e4 += T8) {
-        const int g = e4 / (C20 / 4), ch = (e4 - g * (C20 / 4)) * 4;
+    } else if (tid < 125) {
+      // thread = (g_local = tid/5, c4 = tid%5): fixed channel quad -> its 4 norms live in registers;
+      // each iteration the CTA writes 125 consecutive float4 (25 Gaussians x 20 channels)
+      const int gl = tid / 5, c4 = tid - gl * 5;
+      const float n0 = sm.inv_norm[c4 * 4], n1 = sm.inv_norm[c4 * 4 + 1], n2 = sm.inv_norm[c4 * 4 + 2], n3 = sm.inv_norm[c4 * 4 + 3];
+      const float* s0 = &sm.u.stage[(c4 * 4) * PITCH];
+#pragma unroll 3
+      for (int g = gl; g < V8; g += 25) {
         float4 v;
-        v.x = sm.u.stage[(ch + 0) * PITCH + g] * sm.inv_norm[ch + 0];
-        v.y = sm.u.stage[(ch + 1) * PITCH + g] * sm.inv_norm[ch + 1];
-        v.z = sm.u.stage[(ch + 2) * PITCH + g] * sm.inv_norm[ch + 2];
-        v.w = sm.u.stage[(ch + 3) * PITCH + g] * sm.inv_norm[ch + 3];
-        reinterpret_cast<float4*>(out)[e4] = v;
+        v.x = s0[g] * n0; v.y = s0[PITCH + g] * n1; v.z = s0[2 * PITCH + g] * n2; v.w = s0[3 * PITCH + g] * n3;
+        reinterpret_cast<float4*>(out)[g * 5 + c4] = v;
       }
     }
   }
