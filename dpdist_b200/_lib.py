@@ -24,6 +24,8 @@ class HeadConfig(ctypes.Structure):
 
 
 HEAD_AUTO, HEAD_SIMT, HEAD_TC = 0, 1, 2
+HEAD_TRAIN = 0x10
+BWD_ALL, BWD_L4, BWD_L3, BWD_L2, BWD_L1 = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); must list every symbol include/dpdist_b200.h declares
 SIGNATURES = {
@@ -52,6 +54,12 @@ class ProfileEntry(ctypes.Structure):
 
 
 SIGNATURES.update({
+    "dpd_head_backward": (ctypes.c_int, [ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int] + [ctypes.c_void_p] * 8 + [ctypes.c_void_p, ctypes.c_size_t,
+                                                                                    ctypes.c_void_p]),
+    "dpd_adam_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                     ctypes.c_void_p]),
     "dpd_debug_tc_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                          ctypes.c_void_p]),

@@ -1,5 +1,7 @@
-// Implicit distance head: host orchestration, weight packing, C ABI.
-// Replaces DPDist conv_version 1 (reference utils/dpdist_util.py:412-544, 688-700).
+// Implicit distance head: host orchestration, weight packing, C ABI (forward and backward).
+// Replaces DPDist conv_version 1 (reference utils/dpdist_util.py:412-544, 688-700) and the gradient
+// graph the trainer builds over it (train_multi_gpu_pc_compare_dist.py:274-277).
+#include "head_bwd.cuh"
 #include "head_simt.cuh"
 #include "head_tc.cuh"
 
@@ -9,20 +11,24 @@ namespace {
 
 constexpr size_t ALIGN = 256;
 constexpr int MAX_CHUNK_ROWS = 1 << 18;
+constexpr int OUT_BWD_CTAS = 296;
 
 struct HeadLayout {
   int impl;      // DPD_HEAD_SIMT or DPD_HEAD_TC (resolved)
+  bool train;
   int E, K1, Kp1;
   // packed blob (byte offsets)
-  size_t w1p, w2, w3, w4, b1, b2, b3, b4, tc, total;
-  // workspace per chunk (byte offsets as a function of chunk rows)
+  size_t w1p, w2, w3, w4, b1, b2, b3, b4, w2t, w3t, tc, total;
 };
 
 size_t up(size_t x) { return round_up<size_t>(x, ALIGN); }
 
+int impl_bits(const dpd_head_config& c) { return c.flags & 0xF; }
+bool train_bit(const dpd_head_config& c) { return (c.flags & DPD_HEAD_TRAIN) != 0; }
+
 int resolve_impl(const dpd_head_config& c) {
-  if (c.flags == DPD_HEAD_SIMT) return DPD_HEAD_SIMT;
-  if (c.flags == DPD_HEAD_TC) return DPD_HEAD_TC;
+  if (impl_bits(c) == DPD_HEAD_SIMT) return DPD_HEAD_SIMT;
+  if (impl_bits(c) == DPD_HEAD_TC) return DPD_HEAD_TC;
   return tc_supported(c) ? DPD_HEAD_TC : DPD_HEAD_SIMT;
 }
 
@@ -32,15 +38,18 @@ int check_cfg(const dpd_head_config* c, const char* who) {
   DPD_REQUIRE(c->G >= 2 && c->G <= DPD_MAX_GRID, DPD_E_UNSUPPORTED, "%s: G=%d outside [2,%d]", who, c->G, DPD_MAX_GRID);
   DPD_REQUIRE(c->C > 0 && c->k > 0 && c->k <= 2 * DPD_MAX_GRID, DPD_E_INVALID, "%s: bad C/k", who);
   DPD_REQUIRE(c->H > 0 && c->H % 16 == 0, DPD_E_UNSUPPORTED, "%s: H=%d must be a positive multiple of 16", who, c->H);
-  DPD_REQUIRE(c->flags == DPD_HEAD_AUTO || c->flags == DPD_HEAD_SIMT || c->flags == DPD_HEAD_TC, DPD_E_INVALID, "%s: bad flags", who);
-  if (c->flags == DPD_HEAD_TC)
+  DPD_REQUIRE((c->flags & ~(0xF | DPD_HEAD_TRAIN)) == 0 && impl_bits(*c) <= DPD_HEAD_TC, DPD_E_INVALID, "%s: bad flags", who);
+  if (impl_bits(*c) == DPD_HEAD_TC)
     DPD_REQUIRE(tc_supported(*c), DPD_E_UNSUPPORTED, "%s: tensor-core head needs H %% 256 == 0 and C %% 4 == 0", who);
+  if (train_bit(*c))
+    DPD_REQUIRE(c->H % 128 == 0 && c->H <= 1024, DPD_E_UNSUPPORTED, "%s: training needs H %% 128 == 0 and H <= 1024", who);
   return 0;
 }
 
 HeadLayout make_layout(const dpd_head_config& c) {
   HeadLayout L;
   L.impl = resolve_impl(c);
+  L.train = train_bit(c);
   L.E = c.k * c.k * c.k * c.C;
   L.K1 = L.E + 3;
   L.Kp1 = round_up(L.K1, 32);
@@ -54,6 +63,8 @@ HeadLayout make_layout(const dpd_head_config& c) {
   L.b2 = o;  o += up(H * 4);
   L.b3 = o;  o += up(H * 4);
   L.b4 = o;  o += up(16);
+  L.w2t = o; if (L.train) o += up(H * H * 4);
+  L.w3t = o; if (L.train) o += up(H * H * 4);
   L.tc = o;
   if (L.impl == DPD_HEAD_TC) o += up(tc_packed_bytes(c, L.Kp1));
   L.total = o;
@@ -61,17 +72,28 @@ HeadLayout make_layout(const dpd_head_config& c) {
 }
 
 struct WsLayout {
-  size_t idx, mask, off, ha, hb, tc, total;
+  size_t idx, mask, off, ha, hb, hc, g0, g1, active, part, part_bias, part4, tc, total;
 };
 
 WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
   WsLayout W;
   size_t o = 0;
+  const size_t H = c.H;
   W.idx = o;  o += up(rows * 4);
   W.mask = o; o += up(rows * 4);
   W.off = o;  o += up(rows * 12);
-  W.ha = o;   o += up(rows * (size_t)c.H * 4);
-  W.hb = o;   o += up(rows * (size_t)c.H * 4);
+  W.ha = o;   o += up(rows * H * 4);
+  W.hb = o;   o += up(rows * H * 4);
+  W.hc = W.g0 = W.g1 = W.active = W.part = W.part_bias = W.part4 = o;
+  if (L.train) {
+    W.hc = o; o += up(rows * H * 4);    // layer-3 activations (kept for the backward pass)
+    W.g0 = o; o += up(rows * H * 4);    // upstream gradients, ping-pong
+    W.g1 = o; o += up(rows * H * 4);
+    W.active = o; o += up((rows / 128 + 1) * 4);
+    W.part = o; o += up((size_t)BWD_SLICES * L.Kp1 * H * 4);
+    W.part_bias = o; o += up((size_t)BWD_SLICES * H * 4);
+    W.part4 = o; o += up((size_t)OUT_BWD_CTAS * (H * 3 + 3) * 4);
+  }
   W.tc = o;
   if (L.impl == DPD_HEAD_TC) o += up(tc_workspace_bytes(c, rows));
   W.total = o;
@@ -89,6 +111,41 @@ __global__ void pack_w1_kernel(const float* __restrict__ w1, float* __restrict__
   if (kk < E) v = w1[(size_t)(3 + kk) * H + n];
   else if (kk < E + 3) v = w1[(size_t)(kk - E) * H + n];
   w1p[i] = v;
+}
+
+struct ChunkCtx {
+  int32_t* idx; float *mask, *off, *ha, *hb, *hc;
+  GatherDesc g;
+};
+
+// forward layers 1..3 (+ voxel assignment) for rows [r0, r0+rows); *h3 = the fp32 layer-3 activations
+int forward_chunk(const dpd_head_config* cfg, const HeadLayout& L, const WsLayout& W, size_t chunk, const float* d_fv,
+                  const float* d_query, const float* h_centers, const float* h_lo, const float* h_hi, const char* pk, char* ws,
+                  size_t r0, int rows, int32_t* d_idx, ChunkCtx* cx, const float** h3, cudaStream_t st) {
+  cx->idx = (int32_t*)(ws + W.idx); cx->mask = (float*)(ws + W.mask); cx->off = (float*)(ws + W.off);
+  cx->ha = (float*)(ws + W.ha); cx->hb = (float*)(ws + W.hb); cx->hc = L.train ? (float*)(ws + W.hc) : nullptr;
+  // rows are independent: assign this chunk's queries as a flat list of `rows` points
+  int rc = dpd_voxel_assign(d_query + r0 * 3, 1, rows, cfg->G, h_centers, h_lo, h_hi, cx->idx, cx->mask, cx->off, (void*)st);
+  if (rc) return rc;
+  if (d_idx) DPD_CUDA_CALL(cudaMemcpyAsync(d_idx + r0, cx->idx, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
+  GatherDesc& g = cx->g;
+  g.fv = d_fv; g.idx = cx->idx; g.offset = cx->off; g.row0 = (long long)r0;
+  g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
+  if (L.impl == DPD_HEAD_TC) {
+    return tc_head_layers(*cfg, L.Kp1, g, rows, chunk, pk + L.tc, (const float*)(pk + L.b1), (const float*)(pk + L.b2),
+                          (const float*)(pk + L.b3), cx->ha, cx->hb, cx->hc, ws + W.tc, h3, st);
+  }
+  SimtGemmParams p;
+  p.g = g; p.M = rows; p.N = cfg->H; p.relu = 1;
+  p.A = nullptr; p.lda = 0; p.B = (const float*)(pk + L.w1p); p.bias = (const float*)(pk + L.b1); p.Cout = cx->ha; p.Kp = L.Kp1;
+  if ((rc = launch_simt_gemm(p, true, st))) return rc;
+  p.A = cx->ha; p.lda = cfg->H; p.B = (const float*)(pk + L.w2); p.bias = (const float*)(pk + L.b2); p.Cout = cx->hb; p.Kp = cfg->H;
+  if ((rc = launch_simt_gemm(p, false, st))) return rc;
+  float* out3 = L.train ? cx->hc : cx->ha;
+  p.A = cx->hb; p.B = (const float*)(pk + L.w3); p.bias = (const float*)(pk + L.b3); p.Cout = out3;
+  if ((rc = launch_simt_gemm(p, false, st))) return rc;
+  *h3 = out3;
+  return 0;
 }
 
 }  // namespace
@@ -133,6 +190,10 @@ extern "C" int dpd_head_pack_weights(const dpd_head_config* cfg, const float* d_
   DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b2, d_b2, H * 4, cudaMemcpyDeviceToDevice, st));
   DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b3, d_b3, H * 4, cudaMemcpyDeviceToDevice, st));
   DPD_CUDA_CALL(cudaMemcpyAsync(base + L.b4, d_b4, 3 * 4, cudaMemcpyDeviceToDevice, st));
+  if (L.train) {   // W^T for the dX = dZ . W^T products of the backward pass
+    if ((rc = launch_transpose(d_w2, cfg->H, cfg->H, (float*)(base + L.w2t), st))) return rc;
+    if ((rc = launch_transpose(d_w3, cfg->H, cfg->H, (float*)(base + L.w3t), st))) return rc;
+  }
   if (L.impl == DPD_HEAD_TC) {
     rc = tc_pack_weights(*cfg, L.Kp1, (const float*)(base + L.w1p), (const float*)(base + L.w2),
                          (const float*)(base + L.w3), base + L.tc, st);
@@ -158,12 +219,12 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
   while (chunk > 128 && make_ws(*cfg, L, chunk).total > workspace_bytes) chunk = round_up<size_t>(chunk / 2, 128);
   DPD_REQUIRE(make_ws(*cfg, L, chunk).total <= workspace_bytes, DPD_E_WORKSPACE,
               "dpd_head_forward: workspace %zu B too small (need >= %zu B)", workspace_bytes, make_ws(*cfg, L, 128).total);
+  DPD_REQUIRE(!L.train || chunk >= M, DPD_E_UNSUPPORTED,
+              "dpd_head_forward: training mode keeps all activations: %zu rows exceed one chunk (%zu)", M, chunk);
   const WsLayout W = make_ws(*cfg, L, chunk);
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)d_workspace;
   const char* pk = (const char*)d_packed;
-  GridTables t;
-  fill_tables(t, cfg->G, h_centers, h_lo, h_hi);
 
   if (L.impl == DPD_HEAD_TC) {
     rc = tc_prepare_fv(*cfg, d_fv, ws + W.tc, chunk, st);
@@ -171,39 +232,85 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
   }
   for (size_t r0 = 0; r0 < M; r0 += chunk) {
     const int rows = (int)((M - r0 < chunk) ? (M - r0) : chunk);
-    int32_t* idx = (int32_t*)(ws + W.idx);
-    float* mask = (float*)(ws + W.mask);
-    float* off = (float*)(ws + W.off);
-    float* ha = (float*)(ws + W.ha);
-    float* hb = (float*)(ws + W.hb);
-    // rows are independent: assign this chunk's queries as a flat list of `rows` points
-    rc = dpd_voxel_assign(d_query + r0 * 3, 1, rows, cfg->G, h_centers, h_lo, h_hi, idx, mask, off, stream);
-    if (rc) return rc;
-    if (d_idx) DPD_CUDA_CALL(cudaMemcpyAsync(d_idx + r0, idx, (size_t)rows * 4, cudaMemcpyDeviceToDevice, st));
-    GatherDesc g;
-    g.fv = d_fv; g.idx = idx; g.offset = off; g.row0 = (long long)r0;
-    g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
+    ChunkCtx cx;
     const float* h3 = nullptr;
-    if (L.impl == DPD_HEAD_TC) {
-      rc = tc_head_layers(*cfg, L.Kp1, g, rows, chunk, pk + L.tc, (const float*)(pk + L.b1), (const float*)(pk + L.b2),
-                          (const float*)(pk + L.b3), ha, hb, ws + W.tc, &h3, st);
-      if (rc) return rc;
-    } else {
-      SimtGemmParams p;
-      p.g = g; p.M = rows; p.N = cfg->H; p.relu = 1;
-      p.A = nullptr; p.lda = 0; p.B = (const float*)(pk + L.w1p); p.bias = (const float*)(pk + L.b1); p.Cout = ha; p.Kp = L.Kp1;
-      rc = launch_simt_gemm(p, true, st);
-      if (rc) return rc;
-      p.A = ha; p.lda = cfg->H; p.B = (const float*)(pk + L.w2); p.bias = (const float*)(pk + L.b2); p.Cout = hb; p.Kp = cfg->H;
-      rc = launch_simt_gemm(p, false, st);
-      if (rc) return rc;
-      p.A = hb; p.B = (const float*)(pk + L.w3); p.bias = (const float*)(pk + L.b3); p.Cout = ha;
-      rc = launch_simt_gemm(p, false, st);
-      if (rc) return rc;
-      h3 = ha;
-    }
-    rc = launch_head_out(h3, cfg->H, (const float*)(pk + L.w4), (const float*)(pk + L.b4), mask, d_out + r0 * 3, rows, cfg->H, st);
+    rc = forward_chunk(cfg, L, W, chunk, d_fv, d_query, h_centers, h_lo, h_hi, pk, ws, r0, rows, d_idx, &cx, &h3, st);
     if (rc) return rc;
+    rc = launch_head_out(h3, cfg->H, (const float*)(pk + L.w4), (const float*)(pk + L.b4), cx.mask, d_out + r0 * 3, rows, cfg->H, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, const void* d_packed,
+                                 const float* d_grad_out, int stage, float* d_gw1, float* d_gb1, float* d_gw2,
+                                 float* d_gb2, float* d_gw3, float* d_gb3, float* d_gw4, float* d_gb4,
+                                 void* d_workspace, size_t workspace_bytes, void* stream) {
+  using namespace dpd;
+  int rc = check_cfg(cfg, "dpd_head_backward");
+  if (rc) return rc;
+  DPD_REQUIRE(train_bit(*cfg), DPD_E_INVALID, "dpd_head_backward: cfg.flags must carry DPD_HEAD_TRAIN (pack, forward and backward alike)");
+  DPD_REQUIRE(d_fv && d_packed && d_grad_out && d_workspace, DPD_E_INVALID, "dpd_head_backward: null pointer");
+  DPD_REQUIRE(stage >= DPD_BWD_ALL && stage <= DPD_BWD_L1, DPD_E_INVALID, "dpd_head_backward: bad stage %d", stage);
+  const size_t M = total_rows(*cfg);
+  if (M == 0) return 0;
+  const HeadLayout L = make_layout(*cfg);
+  const size_t chunk = round_up<size_t>(M, 128);
+  DPD_REQUIRE(M <= (size_t)MAX_CHUNK_ROWS && make_ws(*cfg, L, chunk).total <= workspace_bytes, DPD_E_WORKSPACE,
+              "dpd_head_backward: needs the single-chunk training workspace (%zu rows)", M);
+  const WsLayout W = make_ws(*cfg, L, chunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)d_workspace;
+  const char* pk = (const char*)d_packed;
+  const int rows = (int)M, H = cfg->H;
+  float* ha = (float*)(ws + W.ha); float* hb = (float*)(ws + W.hb); float* hc = (float*)(ws + W.hc);
+  float* g0 = (float*)(ws + W.g0); float* g1 = (float*)(ws + W.g1);
+  int* active = (int*)(ws + W.active);
+  float* part = (float*)(ws + W.part); float* part_bias = (float*)(ws + W.part_bias); float* part4 = (float*)(ws + W.part4);
+  const bool all = stage == DPD_BWD_ALL;
+  // fp32 views of the forward activations (valid after dpd_head_forward with the same cfg and workspace).
+  // SIMT forward: H1 = ha, H2 = hb.  Tensor-core forward: H1 = (ha, hb), H2 = (xh, xl) as (hi, lo) pairs,
+  // merged in place into the hi buffers by the first stage.
+  float* H1 = ha;
+  float* H2 = hb;
+  float* H2lo = nullptr;
+  if (L.impl == DPD_HEAD_TC) tc_h2_buffers(*cfg, ws + W.tc, chunk, &H2, &H2lo);
+
+  if (all || stage == DPD_BWD_L4) {
+    if (L.impl == DPD_HEAD_TC) {
+      if ((rc = launch_add_inplace(H1, hb, (size_t)rows * H, st))) return rc;
+      if ((rc = launch_add_inplace(H2, H2lo, (size_t)rows * H, st))) return rc;
+    }
+    if ((rc = launch_row_active(d_grad_out, rows, active, st))) return rc;
+    if ((rc = launch_out_backward(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
+                                  d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st))) return rc;
+    if ((rc = launch_reduce_out_partials(part4, OUT_BWD_CTAS, H, d_gw4, d_gb4, st))) return rc;
+  }
+  TnParams tp;
+  tp.M = rows; tp.N = H; tp.active = active; tp.partial = part; tp.partial_bias = part_bias; tp.lda = H;
+  SimtGemmParams gp;
+  gp.M = rows; gp.N = H; gp.Kp = H; gp.relu = 0; gp.bias = nullptr; gp.lda = H; gp.active = active;
+  if (all || stage == DPD_BWD_L3) {
+    tp.A = H2; tp.B = g0; tp.Kp = H;
+    if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
+    if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw3, d_gb3, st))) return rc;
+    gp.A = g0; gp.B = (const float*)(pk + L.w3t); gp.gate = H2; gp.Cout = g1;     // dZ2 = (dZ3 . W3^T) * (H2 > 0)
+    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+  }
+  if (all || stage == DPD_BWD_L2) {
+    tp.A = H1; tp.B = g1; tp.Kp = H;
+    if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
+    if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw2, d_gb2, st))) return rc;
+    gp.A = g1; gp.B = (const float*)(pk + L.w2t); gp.gate = H1; gp.Cout = g0;     // dZ1 = (dZ2 . W2^T) * (H1 > 0)
+    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+  }
+  if (all || stage == DPD_BWD_L1) {
+    GatherDesc g;
+    g.fv = d_fv; g.idx = (const int32_t*)(ws + W.idx); g.offset = (const float*)(ws + W.off); g.row0 = 0;
+    g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
+    tp.A = nullptr; tp.B = g0; tp.Kp = L.Kp1; tp.g = g;
+    if ((rc = launch_simt_gemm_tn(tp, true, st))) return rc;
+    if ((rc = launch_reduce_partials(part, part_bias, L.Kp1, L.K1, H, L.E, 1, d_gw1, d_gb1, st))) return rc;
   }
   return 0;
 }

@@ -1,0 +1,314 @@
+#include "head_bwd.cuh"
+
+namespace dpd {
+namespace {
+
+constexpr int TK = 128, TN = 128, TM = 16, NT = 256;   // weight-gradient tile: 128 (A cols) x 128 (B cols), 16 rows per step
+
+__global__ void row_active_kernel(const float* __restrict__ g, int M, int* __restrict__ active) {
+  const int b = blockIdx.x;
+  const int r0 = b * 128;
+  int any = 0;
+  for (int i = threadIdx.x; i < 128 * 3; i += blockDim.x) {
+    const int r = r0 + i / 3;
+    if (r < M && g[(size_t)r0 * 3 + i] != 0.f) any = 1;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) active[b] = any;
+}
+
+// One warp per row, grid-stride over rows; per-lane accumulators for H3^T dz4 (lane owns columns 4*lane + 128*i).
+__global__ void __launch_bounds__(256) out_backward_kernel(const float* __restrict__ h3, const float* __restrict__ w4,
+                                                           const float* __restrict__ b4, const float* __restrict__ mask,
+                                                           const float* __restrict__ grad_out, const int* __restrict__ active,
+                                                           float* __restrict__ dz3, float* __restrict__ partial4, int M, int H) {
+  extern __shared__ float red[];   // [8 warps][H*3 + 3]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = gridDim.x * 8;
+  constexpr int MAXQ = 8;          // H <= 1024: up to 8 column quads per lane
+  float gw[MAXQ][4][3];
+  float gb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) gw[i][e][0] = gw[i][e][1] = gw[i][e][2] = 0.f;
+  const int nq = H / 128;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += nw) {
+    if (!active[row >> 7]) continue;
+    const float* hr = h3 + (size_t)row * H;
+    float4 hv[MAXQ];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+      if (i < nq) {
+        const int n = i * 128 + lane * 4;
+        hv[i] = *reinterpret_cast<const float4*>(hr + n);
+        const float x[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s0 = fmaf(x[e], __ldg(w4 + (n + e) * 3 + 0), s0);
+          s1 = fmaf(x[e], __ldg(w4 + (n + e) * 3 + 1), s1);
+          s2 = fmaf(x[e], __ldg(w4 + (n + e) * 3 + 2), s2);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float z[3] = {s0 + b4[0], s1 + b4[1], s2 + b4[2]};
+    const float mk = mask[row];
+    float dz[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)   // d/dz [relu6(z)/3 * mask]; TF-semantics relu6 grad = 1 on 0 < z < 6
+      dz[j] = (z[j] > 0.f && z[j] < 6.f) ? grad_out[(size_t)row * 3 + j] * mk * (1.0f / 3.0f) : 0.f;
+    gb[0] += dz[0]; gb[1] += dz[1]; gb[2] += dz[2];
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+      if (i < nq) {
+        const int n = i * 128 + lane * 4;
+        const float x[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          gw[i][e][0] = fmaf(x[e], dz[0], gw[i][e][0]);
+          gw[i][e][1] = fmaf(x[e], dz[1], gw[i][e][1]);
+          gw[i][e][2] = fmaf(x[e], dz[2], gw[i][e][2]);
+          const float d = dz[0] * __ldg(w4 + (n + e) * 3 + 0) + dz[1] * __ldg(w4 + (n + e) * 3 + 1) + dz[2] * __ldg(w4 + (n + e) * 3 + 2);
+          o[e] = x[e] > 0.f ? d : 0.f;
+        }
+        *reinterpret_cast<float4*>(dz3 + (size_t)row * H + n) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  // CTA reduction in fixed warp order -> partial4[cta]
+  float* mine = red + warp * (H * 3 + 3);
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i)
+    if (i < nq)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mine[(i * 128 + lane * 4 + e) * 3 + j] = gw[i][e][j];
+  // every lane saw every active row of its warp: gb is identical across lanes
+  if (lane == 0) { mine[H * 3 + 0] = gb[0]; mine[H * 3 + 1] = gb[1]; mine[H * 3 + 2] = gb[2]; }
+  __syncthreads();
+  float* dst = partial4 + (size_t)blockIdx.x * (H * 3 + 3);
+  for (int i = threadIdx.x; i < H * 3 + 3; i += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w * (H * 3 + 3) + i];
+    dst[i] = a;
+  }
+}
+
+__global__ void reduce_out_partials_kernel(const float* __restrict__ partial4, int n_cta, int H, float* __restrict__ gw4,
+                                           float* __restrict__ gb4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * 3 + 3) return;
+  float a = 0.f;
+  for (int c = 0; c < n_cta; ++c) a += partial4[(size_t)c * (H * 3 + 3) + i];
+  if (i < H * 3) gw4[i] = a;
+  else gb4[i - H * 3] = a;
+}
+
+// partial[s][k][n] = sum over the 128-row blocks b == s (mod BWD_SLICES) of A[m,k] * B[m,n]
+template <bool GATHER>
+__global__ void __launch_bounds__(NT) simt_gemm_tn_kernel(const TnParams p) {
+  __shared__ __align__(16) float As[2][TM][TK];
+  __shared__ __align__(16) float Bs[2][TM][TN];
+  __shared__ RowInfo rows[GATHER ? 128 : 1];
+  __shared__ float bias_red[8][TN];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * TN, k0 = blockIdx.y * TK, s = blockIdx.z;
+  const bool vec = GATHER ? ((p.g.C & 3) == 0) : true;
+  const int nblk = (p.M + 127) / 128;
+  const int l_m[2] = {tid >> 5, (tid >> 5) + 8};   // row within the 16-row step
+  const int l_c = tid & 31;                        // float4 column within the 128-wide tile
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool do_bias = (blockIdx.y == 0) && (p.partial_bias != nullptr);
+
+  for (int blk = s; blk < nblk; blk += BWD_SLICES) {
+    if (!p.active[blk]) continue;
+    const int mb = blk * 128;
+    if (GATHER) {
+      __syncthreads();
+      if (tid < 128) rows[tid] = make_row_info(p.g, mb + tid, p.M);
+      __syncthreads();
+    }
+    float4 ra[2], rb[2];
+    auto load = [&](int step) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ml = step * TM + l_m[j], m = mb + ml;
+        const int kk = k0 + l_c * 4;
+        if (GATHER) ra[j] = (kk < p.Kp) ? gather_chunk(p.g, rows[ml], kk, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else ra[j] = (m < p.M && kk < p.Kp) ? ld4(p.A + (size_t)m * p.lda + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[j] = (m < p.M) ? ld4(p.B + (size_t)m * p.N + n0 + l_c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        *reinterpret_cast<float4*>(&As[buf][l_m[j]][l_c * 4]) = ra[j];
+        *reinterpret_cast<float4*>(&Bs[buf][l_m[j]][l_c * 4]) = rb[j];
+        if (do_bias) { bsum.x += rb[j].x; bsum.y += rb[j].y; bsum.z += rb[j].z; bsum.w += rb[j].w; }
+      }
+    };
+    load(0);
+    __syncthreads();          // previous block's last compute is done with both buffers
+    store(0);
+    __syncthreads();
+    for (int step = 0; step < 128 / TM; ++step) {
+      const int buf = step & 1;
+      if (step + 1 < 128 / TM) load(step + 1);
+#pragma unroll
+      for (int mm = 0; mm < TM; ++mm) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][mm][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][mm][64 + tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (step + 1 < 128 / TM) {
+        store(buf ^ 1);
+        __syncthreads();
+      }
+    }
+  }
+  float* dst = p.partial + (size_t)s * p.Kp * p.N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (k >= p.Kp) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
+      *reinterpret_cast<float4*>(dst + (size_t)k * p.N + n) =
+          make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+    }
+  }
+  if (do_bias) {   // column sums of B: threads with the same l_c live in 8 different warps
+    __syncthreads();
+    *reinterpret_cast<float4*>(&bias_red[tid >> 5][l_c * 4]) = bsum;
+    __syncthreads();
+    if (tid < TN) {
+      float a = 0.f;
+      for (int w = 0; w < 8; ++w) a += bias_red[w][tid];
+      p.partial_bias[(size_t)s * p.N + n0 + tid] = a;
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias, int Kp,
+                                       int K_valid, int N, int E, int unpermute, float* __restrict__ gw, float* __restrict__ gb) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)Kp * N;
+  if (i < total) {
+    const int k = (int)(i / N), n = (int)(i % N);
+    if (k < K_valid) {
+      float a = 0.f;
+      for (int s = 0; s < BWD_SLICES; ++s) a += partial[(size_t)s * total + i];
+      const int row = unpermute ? (k < E ? 3 + k : k - E) : k;
+      gw[(size_t)row * N + n] = a;
+    }
+  }
+  if (i < (size_t)N && gb != nullptr) {
+    float a = 0.f;
+    for (int s = 0; s < BWD_SLICES; ++s) a += partial_bias[(size_t)s * N + i];
+    gb[i] = a;
+  }
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 x = reinterpret_cast<float4*>(a)[i];
+  const float4 y = reinterpret_cast<const float4*>(b)[i];
+  x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+  reinterpret_cast<float4*>(a)[i] = x;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ wt) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? w[(size_t)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) wt[(size_t)n * K + k] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace
+
+int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st) {
+  DPD_LAUNCH("bwd_row_active", st, row_active_kernel<<<ceil_div(M, 128), 128, 0, st>>>(grad_out, M, active));
+  DPD_CUDA_CHECK_LAUNCH("row_active_kernel");
+  return 0;
+}
+
+int launch_out_backward(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
+                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st) {
+  DPD_REQUIRE(H % 128 == 0 && H <= 1024, DPD_E_UNSUPPORTED, "head backward: H=%d must be a multiple of 128, <= 1024", H);
+  const size_t smem = (size_t)8 * (H * 3 + 3) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4)); attr_done = true; }
+  DPD_LAUNCH("bwd_out_l4", st, out_backward_kernel<<<n_cta, 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3, partial4, M, H));
+  DPD_CUDA_CHECK_LAUNCH("out_backward_kernel");
+  return 0;
+}
+
+int launch_reduce_out_partials(const float* partial4, int n_cta, int H, float* gw4, float* gb4, cudaStream_t st) {
+  DPD_LAUNCH("bwd_reduce_l4", st, reduce_out_partials_kernel<<<ceil_div(H * 3 + 3, 256), 256, 0, st>>>(partial4, n_cta, H, gw4, gb4));
+  DPD_CUDA_CHECK_LAUNCH("reduce_out_partials_kernel");
+  return 0;
+}
+
+int launch_simt_gemm_tn(const TnParams& p, bool gather, cudaStream_t st) {
+  DPD_REQUIRE(p.N % TN == 0 && p.Kp % 4 == 0, DPD_E_UNSUPPORTED, "gemm_tn: N %% 128 or Kp %% 4 violated (N=%d Kp=%d)", p.N, p.Kp);
+  dim3 grid(p.N / TN, ceil_div(p.Kp, TK), BWD_SLICES);
+  if (gather) DPD_LAUNCH("bwd_dw_gather_l1", st, simt_gemm_tn_kernel<true><<<grid, NT, 0, st>>>(p));
+  else DPD_LAUNCH("bwd_dw_dense", st, simt_gemm_tn_kernel<false><<<grid, NT, 0, st>>>(p));
+  DPD_CUDA_CHECK_LAUNCH("simt_gemm_tn_kernel");
+  return 0;
+}
+
+int launch_reduce_partials(const float* partial, const float* partial_bias, int Kp, int K_valid, int N, int E, int unpermute,
+                           float* gw, float* gb, cudaStream_t st) {
+  const size_t total = (size_t)Kp * N;
+  DPD_LAUNCH("bwd_reduce_dw", st, reduce_partials_kernel<<<(unsigned)ceil_div<size_t>(total, 256), 256, 0, st>>>(
+      partial, partial_bias, Kp, K_valid, N, E, unpermute, gw, gb));
+  DPD_CUDA_CHECK_LAUNCH("reduce_partials_kernel");
+  return 0;
+}
+
+int launch_add_inplace(float* a, const float* b, size_t n, cudaStream_t st) {
+  DPD_REQUIRE(n % 4 == 0, DPD_E_INVALID, "add_inplace: n %% 4 != 0");
+  DPD_LAUNCH("bwd_merge_hi_lo", st, add_inplace_kernel<<<(unsigned)ceil_div<size_t>(n / 4, 256), 256, 0, st>>>(a, b, n / 4));
+  DPD_CUDA_CHECK_LAUNCH("add_inplace_kernel");
+  return 0;
+}
+
+int launch_transpose(const float* w, int K, int N, float* wt, cudaStream_t st) {
+  DPD_LAUNCH("pack_transpose", st, transpose_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), dim3(32, 8), 0, st>>>(w, K, N, wt));
+  DPD_CUDA_CHECK_LAUNCH("transpose_kernel");
+  return 0;
+}
+
+}  // namespace dpd

@@ -1,0 +1,41 @@
+// Backward of the implicit distance head w.r.t. its 8 variables (fp32 SIMT kernels).
+// Replaces what tf.gradients builds for optimizer.compute_gradients(total_loss_samples, vars in
+// scope 'pc_compare') in the reference trainer (train_multi_gpu_pc_compare_dist.py:274-277).
+#pragma once
+#include "head_simt.cuh"
+
+namespace dpd {
+
+constexpr int BWD_SLICES = 8;   // split of the row (reduction) axis of the weight-gradient GEMMs
+
+// active[b] = 1 if any of grad_out[128*b .. 128*b+127, 0..2] is non-zero.  Row blocks whose upstream
+// gradient is identically zero (the whole B->A half in DPDist training, :967) are skipped everywhere.
+int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st);
+
+// dZ3[r,:] = (sum_j dz4[r,j] W4[:,j]) * (H3[r,:] > 0),   dz4 = grad_out * mask * relu6'(z4) / 3
+// partial4[cta][H*3 + 3] accumulates H3^T dz4 and sum_r dz4 per CTA (reduced in fixed order later).
+int launch_out_backward(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
+                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st);
+int launch_reduce_out_partials(const float* partial4, int n_cta, int H, float* gw4, float* gb4, cudaStream_t st);
+
+struct TnParams {
+  const float* A;      // dense [M, lda] (ignored when gathering)
+  int lda;
+  const float* B;      // upstream gradient dZ [M, N]
+  int M, N, Kp;        // Kp = columns of A (multiple of 128 after padding for the launch grid)
+  const int* active;   // per 128-row block
+  float* partial;      // [BWD_SLICES][Kp][N]
+  float* partial_bias; // [BWD_SLICES][N] column sums of B (written by the blockIdx.y == 0 CTAs)
+  GatherDesc g;
+};
+int launch_simt_gemm_tn(const TnParams& p, bool gather, cudaStream_t st);
+
+// grad[row_map(k)][n] = sum_s partial[s][k][n]; unpermute != 0 maps packed layer-1 rows (patch | offset | pad)
+// back to the reference's (offset | patch) order and drops the padding rows.
+int launch_reduce_partials(const float* partial, const float* partial_bias, int Kp, int K_valid, int N, int E, int unpermute,
+                           float* gw, float* gb, cudaStream_t st);
+
+int launch_add_inplace(float* a, const float* b, size_t n, cudaStream_t st);
+int launch_transpose(const float* w, int K, int N, float* wt, cudaStream_t st);
+
+}  // namespace dpd

@@ -5,42 +5,6 @@ namespace dpd {
 namespace {
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
 
-struct RowInfo {
-  long long base;  // element offset of the row's cloud in fv, or -1 for a row past M
-  int i0, i1, i2;
-  float off[3];
-};
-
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-
-// one element of the virtual layer-1 operand
-__device__ __forceinline__ float gather_elem(const GatherDesc& g, const RowInfo& r, int kk) {
-  if (r.base < 0) return 0.f;
-  if (kk >= g.E) return (kk < g.E + 3) ? r.off[kk - g.E] : 0.f;
-  const int j = kk / g.C, ch = kk - j * g.C;
-  const int pb = (g.k - 1) >> 1;
-  const int a2 = j % g.k, a1 = (j / g.k) % g.k, a0 = j / (g.k * g.k);
-  const int n0 = r.i0 + a0 - pb, n1 = r.i1 + a1 - pb, n2 = r.i2 + a2 - pb;
-  if ((unsigned)n0 >= (unsigned)g.G || (unsigned)n1 >= (unsigned)g.G || (unsigned)n2 >= (unsigned)g.G) return 0.f;
-  return g.fv[r.base + (long long)((n0 * g.G + n1) * g.G + n2) * g.C + ch];
-}
-
-__device__ __forceinline__ float4 gather_chunk(const GatherDesc& g, const RowInfo& r, int kk, bool vec) {
-  if (vec) {  // C % 4 == 0: a 4-float chunk never straddles a voxel record
-    if (r.base < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kk >= g.E) return (kk == g.E) ? make_float4(r.off[0], r.off[1], r.off[2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int j = kk / g.C, ch = kk - j * g.C;
-    const int pb = (g.k - 1) >> 1;
-    const int a2 = j % g.k, a1 = (j / g.k) % g.k, a0 = j / (g.k * g.k);
-    const int n0 = r.i0 + a0 - pb, n1 = r.i1 + a1 - pb, n2 = r.i2 + a2 - pb;
-    if ((unsigned)n0 >= (unsigned)g.G || (unsigned)n1 >= (unsigned)g.G || (unsigned)n2 >= (unsigned)g.G)
-      return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ld4(g.fv + r.base + (long long)((n0 * g.G + n1) * g.G + n2) * g.C + ch);
-  }
-  return make_float4(gather_elem(g, r, kk), gather_elem(g, r, kk + 1), gather_elem(g, r, kk + 2),
-                     gather_elem(g, r, kk + 3));
-}
-
 template <bool GATHER>
 __global__ void __launch_bounds__(NT) simt_gemm_kernel(const SimtGemmParams p) {
   __shared__ __align__(16) float As[2][BK][BM];
@@ -49,6 +13,7 @@ __global__ void __launch_bounds__(NT) simt_gemm_kernel(const SimtGemmParams p) {
 
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (p.active && !p.active[blockIdx.y]) return;   // upstream gradient of this row block is identically zero
   const bool vec = GATHER ? ((p.g.C & 3) == 0) : true;
 
   if (GATHER) {
@@ -148,10 +113,16 @@ __global__ void __launch_bounds__(NT) simt_gemm_kernel(const SimtGemmParams p) {
       const int n = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
       if (n >= p.N) continue;
       float4 v;
-      const float4 bb = ld4(p.bias + n);
-      v.x = acc[i][h * 4 + 0] + bb.x; v.y = acc[i][h * 4 + 1] + bb.y;
-      v.z = acc[i][h * 4 + 2] + bb.z; v.w = acc[i][h * 4 + 3] + bb.w;
-      if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (p.gate) {   // backward: dX = (dZ . W^T) gated by the forward activation's ReLU
+        const float4 gg = ld4(p.gate + (size_t)m * p.N + n);
+        v.x = gg.x > 0.f ? acc[i][h * 4 + 0] : 0.f; v.y = gg.y > 0.f ? acc[i][h * 4 + 1] : 0.f;
+        v.z = gg.z > 0.f ? acc[i][h * 4 + 2] : 0.f; v.w = gg.w > 0.f ? acc[i][h * 4 + 3] : 0.f;
+      } else {
+        const float4 bb = ld4(p.bias + n);
+        v.x = acc[i][h * 4 + 0] + bb.x; v.y = acc[i][h * 4 + 1] + bb.y;
+        v.z = acc[i][h * 4 + 2] + bb.z; v.w = acc[i][h * 4 + 3] + bb.w;
+        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      }
       *reinterpret_cast<float4*>(p.Cout + (size_t)m * p.N + n) = v;
     }
   }

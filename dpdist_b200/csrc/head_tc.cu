@@ -18,6 +18,7 @@
 //                tensor of the reference (utils/dpdist_util.py:922-930) never exists.
 #include <cuda.h>
 
+#include "head_bwd.cuh"
 #include "head_tc.cuh"
 
 namespace dpd {
@@ -307,6 +308,14 @@ TcWs tc_ws_layout(const dpd_head_config& c, size_t rows) {
 size_t tc_packed_bytes(const dpd_head_config& c, int Kp1) { return tc_blob_layout(c, Kp1).total; }
 size_t tc_workspace_bytes(const dpd_head_config& c, size_t rows) { return tc_ws_layout(c, rows).total; }
 
+// backward support: where the (hi, lo) halves of the layer-2 activations live
+void tc_h2_buffers(const dpd_head_config& c, void* tc_ws, size_t ws_rows, float** hi, float** lo) {
+  const TcWs w = tc_ws_layout(c, ws_rows);
+  char* ws = (char*)tc_ws;
+  *hi = (float*)(ws + w.xh);
+  *lo = (float*)(ws + w.xl);
+}
+
 int tc_pack_weights(const dpd_head_config& c, int Kp1, const float* w1p, const float* w2, const float* w3, void* tc_blob,
                     cudaStream_t st) {
   const TcBlob b = tc_blob_layout(c, Kp1);
@@ -334,8 +343,8 @@ int tc_prepare_fv(const dpd_head_config& c, const float* fv, void* tc_ws, size_t
 }
 
 int tc_head_layers(const dpd_head_config& c, int Kp1, const GatherDesc& g, int rows, size_t ws_rows, const void* tc_blob,
-                   const float* b1, const float* b2, const float* b3, float* ha, float* hb, void* tc_ws,
-                   const float** h3, cudaStream_t st) {
+                   const float* b1, const float* b2, const float* b3, float* ha, float* hb, float* h3_out,
+                   void* tc_ws, const float** h3, cudaStream_t st) {
   const TcBlob b = tc_blob_layout(c, Kp1);
   const TcWs w = tc_ws_layout(c, ws_rows);
   const char* blob = (const char*)tc_blob;
@@ -357,9 +366,9 @@ int tc_head_layers(const dpd_head_config& c, int Kp1, const GatherDesc& g, int r
   rc = tc::launch(false, ha, hb, rows, H, (const float*)(blob + b.w2h), (const float*)(blob + b.w2l), H, b2, xh, xl, 1, nullptr, st);
   if (rc) return rc;
   // layer 3: (xh, xl) -> ha (plain fp32 for the fp32 output layer)
-  rc = tc::launch(false, xh, xl, rows, H, (const float*)(blob + b.w3h), (const float*)(blob + b.w3l), H, b3, ha, nullptr, 0, nullptr, st);
+  rc = tc::launch(false, xh, xl, rows, H, (const float*)(blob + b.w3h), (const float*)(blob + b.w3l), H, b3, h3_out ? h3_out : ha, nullptr, 0, nullptr, st);
   if (rc) return rc;
-  *h3 = ha;
+  *h3 = h3_out ? h3_out : ha;
   return 0;
 }
 

@@ -223,28 +223,19 @@ _PACKED = {}
 HEAD_IMPL = _lib.HEAD_AUTO   # module-level switch: _lib.HEAD_AUTO / HEAD_SIMT / HEAD_TC
 
 
-def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
-    """out[c,q,:] = mask * relu6(MLP([query - centre | patch_k(fv[c], voxel(query))])) / 3.
-    fv [n_clouds,V,Cc], query [n_clouds,NP,3], weights = [w1,b1,w2,b2,w3,b3,w4,b4] in the
-    reference's HWIO layouts."""
+def _head_call(fv, query, tables, weights, k, flags, idx=None):
+    """One dpd_head_forward call; returns (out, cfg, cache) so a backward can find the activations."""
     lib = _lib.load()
-    fv = _check_cuda(fv, "fv")
-    query = _check_cuda(query, "query")
     n_clouds, V, Cc = fv.shape
-    if query.shape[0] != n_clouds:
-        raise ValueError("fv and query disagree on the number of clouds")
     NP = query.shape[1]
-    G, l, lo, hi = _assign_tables(C)
-    if G ** 3 != V:
-        raise ValueError("C and fv disagree on the grid")
+    G, l, lo, hi = tables
     ws_list = [_check_cuda(w.detach(), "variable") for w in weights]
     w1 = ws_list[0]
     H = w1.shape[-1]
     if w1.numel() != (3 + k ** 3 * Cc) * H:
         raise ValueError("mapper_conv1/weights has %d elements, expected (3+k^3*C)*H = %d" % (w1.numel(), (3 + k ** 3 * Cc) * H))
-    cfg = _lib.HeadConfig(n_clouds, NP, G, Cc, int(k), H, HEAD_IMPL if impl is None else impl)
+    cfg = _lib.HeadConfig(n_clouds, NP, G, Cc, int(k), H, flags)
     out = torch.empty((n_clouds, NP, 3), device=fv.device, dtype=torch.float32)
-    idx = torch.empty((n_clouds, NP), device=fv.device, dtype=torch.int32) if return_idx else None
     with torch.cuda.device(fv.device):
         cache = _PACKED.setdefault((fv.device, cfg.flags), _PackedHead())
         blob = cache.get(lib, cfg, list(weights), ws_list)
@@ -253,6 +244,66 @@ def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
                                   _lib.fptr(hi), _ptr(blob), _ptr(out),
                                   _ptr(idx) if idx is not None else None, _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "dpd_head_forward")
+    cache.generation = getattr(cache, "generation", 0) + 1
+    return out, cfg, cache
+
+
+# called as hook(layer_index 4..1, [weight_grad, bias_grad]) as soon as a layer's gradients are complete,
+# so a data-parallel trainer can start that layer's all-reduce while the next layer is computed
+GRAD_READY_HOOK = None
+
+
+class _HeadFunction(torch.autograd.Function):
+    """Autograd node of the head: gradients w.r.t. the 8 variables (train_multi_gpu_pc_compare_dist.py:274-277).
+    Gradients w.r.t. fv / query (needed when DPDist is used as a loss for another network)
+    are not implemented yet and raise."""
+
+    @staticmethod
+    def forward(ctx, fv, query, tables, k, impl, *weights):
+        out, cfg, cache = _head_call(fv, query, tables, weights, k, impl | _lib.HEAD_TRAIN)
+        ctx.fv, ctx.cfg, ctx.cache, ctx.generation = fv, cfg, cache, cache.generation
+        ctx.shapes = [tuple(w.shape) for w in weights]
+        ctx.input_needs_grad = fv.requires_grad or query.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.input_needs_grad:
+            raise NotImplementedError("gradients w.r.t. the point clouds (DPDist as a loss for another network) are not implemented yet")
+        cache, cfg, fv = ctx.cache, ctx.cfg, ctx.fv
+        if cache.generation != ctx.generation:
+            raise RuntimeError("the activations of this forward were overwritten by a later DPDist call; call backward() first")
+        lib = _lib.load()
+        grad_out = grad_out.contiguous().float()
+        grads = [torch.empty(s, device=fv.device, dtype=torch.float32) for s in ctx.shapes]
+        ptrs = [_ptr(g) for g in grads]
+        with torch.cuda.device(fv.device):
+            for stage, layer in ((_lib.BWD_L4, 4), (_lib.BWD_L3, 3), (_lib.BWD_L2, 2), (_lib.BWD_L1, 1)):
+                rc = lib.dpd_head_backward(ctypes.byref(cfg), _ptr(fv), _ptr(cache.blob), _ptr(grad_out), stage, *ptrs,
+                                           _ptr(cache.ws), cache.ws.numel(), _stream())
+                _lib.check(rc, "dpd_head_backward")
+                if GRAD_READY_HOOK is not None:
+                    GRAD_READY_HOOK(layer, grads[2 * (layer - 1):2 * layer])
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
+    """out[c,q,:] = mask * relu6(MLP([query - centre | patch_k(fv[c], voxel(query))])) / 3.
+    fv [n_clouds,V,Cc], query [n_clouds,NP,3], weights = [w1,b1,w2,b2,w3,b3,w4,b4] in the
+    reference's HWIO layouts.  Differentiable w.r.t. the weights."""
+    fv = _check_cuda(fv, "fv")
+    query = _check_cuda(query, "query")
+    if query.shape[0] != fv.shape[0]:
+        raise ValueError("fv and query disagree on the number of clouds")
+    tables = _assign_tables(C)
+    if tables[0] ** 3 != fv.shape[1]:
+        raise ValueError("C and fv disagree on the grid")
+    impl = HEAD_IMPL if impl is None else impl
+    needs_grad = torch.is_grad_enabled() and any(getattr(w, "requires_grad", False) for w in weights)
+    if needs_grad and not return_idx:
+        return _HeadFunction.apply(fv, query, tables, k, impl, *weights)
+    idx = torch.empty(query.shape[:2], device=fv.device, dtype=torch.int32) if return_idx else None
+    out, _, _ = _head_call(fv, query, tables, weights, k, impl, idx)
     return (out, idx) if return_idx else out
 
 
@@ -306,7 +357,11 @@ def DPDist(point_cloud, point_cloudB, embedding,
         w4, b4 = tf_util.conv2d_variables(mlp[2], NUM_DIMS, [1, 1], 'mapper_conv4', reuse=reuse)  # :541-545
     fv_all = torch.cat([fvA, fvB], 0)             # rows [A-field | B-field]  (:511)
     query = torch.cat([pcB, pcA], 0)              # A's field is queried at B's points and vice versa (:494,498)
-    out = head_forward(fv_all, query, C, [w1, b1, w2, b2, w3, b3, w4, b4], k)
+    # is_training only switches batch norm in the reference (off here); a literal False/0 additionally
+    # selects the inference path (no activations kept for a backward pass)
+    grad_ok = torch.is_grad_enabled() and (bool(is_training) if isinstance(is_training, (bool, int)) else True)
+    with torch.set_grad_enabled(grad_ok):
+        out = head_forward(fv_all, query, C, [w1, b1, w2, b2, w3, b3, w4, b4], k)
     out = out.view(2, B, NP, 1, 3)
     return [out[0], out[1]]                                                    # :695
 

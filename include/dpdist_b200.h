@@ -45,6 +45,15 @@ extern "C" {
 #define DPD_HEAD_AUTO 0
 #define DPD_HEAD_SIMT 1 /* fp32 FFMA GEMMs (sanity path) */
 #define DPD_HEAD_TC 2   /* tcgen05 tensor-core GEMMs, split-precision */
+#define DPD_HEAD_TRAIN 0x10 /* OR-ed into flags: keep the activations for dpd_head_backward (one row chunk only) */
+
+/* stages of dpd_head_backward: ALL, or one layer at a time (4 -> 1) so that the caller can start the
+ * gradient all-reduce of a layer while the next one is still being computed */
+#define DPD_BWD_ALL 0
+#define DPD_BWD_L4 1
+#define DPD_BWD_L3 2
+#define DPD_BWD_L2 3
+#define DPD_BWD_L1 4
 
 int dpd_version(void);
 const char* dpd_last_error(void);
@@ -108,6 +117,23 @@ int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, const float*
                      const float* h_centers, const float* h_lo, const float* h_hi,
                      const void* d_packed, float* d_out, int32_t* d_idx, void* d_workspace,
                      size_t workspace_bytes, void* stream);
+
+/* Gradients of the head's 8 variables: replaces what optimizer.compute_gradients(total_loss_samples,
+ * vars in scope 'pc_compare') builds in the reference trainer (train_multi_gpu_pc_compare_dist.py:274-277)
+ * over utils/dpdist_util.py:494-544,688-698.  Must follow a dpd_head_forward with the SAME cfg (flags
+ * including DPD_HEAD_TRAIN), packed weights and workspace; uses the activations left there.
+ *   d_grad_out [n_clouds, n_query, 3]  dLoss/d(out); row blocks that are identically zero are skipped
+ *   d_gw1 [3+k^3*C, H] (reference row order, offset rows first), d_gw2/3 [H,H], d_gw4 [H,3], d_gb* biases
+ * stage = DPD_BWD_ALL, or DPD_BWD_L4, L3, L2, L1 in that order (each writes only its layer's gradients). */
+int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, const void* d_packed,
+                      const float* d_grad_out, int stage, float* d_gw1, float* d_gb1, float* d_gw2,
+                      float* d_gb2, float* d_gw3, float* d_gb3, float* d_gw4, float* d_gb4,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Adam with tf.train.AdamOptimizer semantics (train_multi_gpu_pc_compare_dist.py:216, 301):
+ * lr_t = lr*sqrt(1-beta2^step)/(1-beta1^step); var -= lr_t * m / (sqrt(v) + eps).  step is 1-based. */
+int dpd_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, size_t n, float lr,
+                  float beta1, float beta2, float eps, int step, void* stream);
 
 /* Test hook for the tensor-core GEMM used by layers 2-3 of the head:
  *   d_out[M,N] = relu(d_a[M,K] . d_w[K,N] + d_bias[N]),  K % 32 == 0, N % 256 == 0,
