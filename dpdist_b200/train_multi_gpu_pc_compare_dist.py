@@ -1,0 +1,98 @@
+"""DPDist training driver on synthetic ModelNet-shaped data (the `--train_comp dpdist` branch of the
+reference's train_multi_gpu_pc_compare_dist.py, :186-357, with the same flag names).
+
+    python -m dpdist_b200.train_multi_gpu_pc_compare_dist --batch_size 16 --num_point 64 --steps 100
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
+        -m dpdist_b200.train_multi_gpu_pc_compare_dist --num_gpus N --batch_size 16
+
+One process per GPU: rank i takes the slice [i*DEVICE_BATCH_SIZE, (i+1)*DEVICE_BATCH_SIZE) of every global
+batch (:241-251), gradients are averaged with NCCL (:936-974), Adam runs on every rank.  The reference's
+dataset files do not ship with it, so batches come from dpdist_b200.synthetic.dataset_batch (same shapes as
+ModelNetDataset.next_batch, modelnet_dataset.py:170-187); the AUE / PCRNet consumers are out of scope.
+"""
+import argparse
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import synthetic, train
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument('--num_gpus', type=int, default=1)
+    p.add_argument('--num_point', type=int, default=64)
+    p.add_argument('--batch_size', type=int, default=16)
+    p.add_argument('--learning_rate_dpdist', type=float, default=0.0001)
+    p.add_argument('--decay_step', type=int, default=300 * 512)
+    p.add_argument('--decay_rate', type=float, default=0.5)
+    p.add_argument('--embedding_size', type=int, default=8 ** 3)
+    p.add_argument('--K', default='5')
+    p.add_argument('--sigma3dmfv', type=float, default=2.0)
+    p.add_argument('--add_noise', type=float, default=0.0)
+    p.add_argument('--steps', type=int, default=50, help='training steps to run (synthetic data has no epochs)')
+    p.add_argument('--warmup', type=int, default=5)
+    p.add_argument('--distinct_batches', type=int, default=4)
+    p.add_argument('--log_every', type=int, default=10)
+    FLAGS = p.parse_args(argv)
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert FLAGS.batch_size % world == 0                                    # :125
+    sigma = FLAGS.sigma3dmfv * 0.0625                                       # :103
+    tr = train.DPDistTrainer(dev, base_lr=FLAGS.learning_rate_dpdist, decay_step=FLAGS.decay_step,
+                             decay_rate=FLAGS.decay_rate, Embedding_Size=FLAGS.embedding_size, k=int(FLAGS.K),
+                             sigma3dmfv=sigma, seed=1)
+    batches = []
+    for i in range(FLAGS.distinct_batches):
+        if FLAGS.batch_size <= 64:
+            pts, lab = synthetic.dataset_batch(100 + i, FLAGS.batch_size, FLAGS.num_point)
+            pcA, pcB, lab_ab = train.assemble_batch(pts, lab, FLAGS.num_point)   # :749-766
+        else:   # large synthetic batches: the chair sampler is a python loop, use the vectorised generator
+            pcA, pcB, lab_ab = synthetic.uniform_batch(100 + i, FLAGS.batch_size, FLAGS.num_point)
+        mine = [torch.from_numpy(np.ascontiguousarray(train.shard(x, rank, world))).to(dev) for x in (pcA, pcB, lab_ab)]
+        batches.append(mine)
+
+    def one(i):
+        a, b, l = batches[i % len(batches)]
+        noise = torch.randn_like(a) * FLAGS.add_noise if FLAGS.add_noise > 0 else 0      # :768-771
+        return tr.step(a, b, l, add_noise=noise)
+
+    for i in range(FLAGS.warmup):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    losses = []
+    e0.record()
+    for i in range(FLAGS.steps):
+        losses.append(one(FLAGS.warmup + i))
+        if rank == 0 and FLAGS.log_every and (i + 1) % FLAGS.log_every == 0:
+            print(' ---- batch: %03d ---- mean loss: %f' % (i + 1, float(torch.stack(losses[-FLAGS.log_every:]).mean())), flush=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"mode": "train", "n_gpus": world, "global_batch": FLAGS.batch_size, "num_point": FLAGS.num_point,
+                          "steps": FLAGS.steps, "ms_per_step": ms / FLAGS.steps,
+                          "pairs_per_s": FLAGS.batch_size * FLAGS.steps / (ms * 1e-3),
+                          "first_loss": float(losses[0]), "last_loss": float(losses[-1])}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
