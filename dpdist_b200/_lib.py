@@ -23,7 +23,7 @@ class HeadConfig(ctypes.Structure):
                 ("C", ctypes.c_int), ("k", ctypes.c_int), ("H", ctypes.c_int), ("flags", ctypes.c_int)]
 
 
-HEAD_AUTO, HEAD_SIMT, HEAD_TC = 0, 1, 2
+HEAD_AUTO, HEAD_SIMT, HEAD_TC, HEAD_TC_TF32 = 0, 1, 2, 3
 HEAD_TRAIN = 0x10
 BWD_ALL, BWD_L4, BWD_L3, BWD_L2, BWD_L1 = 0, 1, 2, 3, 4
 
@@ -62,7 +62,7 @@ SIGNATURES.update({
                                      ctypes.c_void_p]),
     "dpd_debug_tc_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
-                                         ctypes.c_void_p]),
+                                         ctypes.c_int, ctypes.c_void_p]),
     "dpd_launch_count": (ctypes.c_longlong, []),
     "dpd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dpd_profile_read": (ctypes.c_int, [ctypes.POINTER(ProfileEntry), ctypes.c_int, ctypes.c_int]),

@@ -29,8 +29,11 @@ bool train_bit(const dpd_head_config& c) { return (c.flags & DPD_HEAD_TRAIN) != 
 int resolve_impl(const dpd_head_config& c) {
   if (impl_bits(c) == DPD_HEAD_SIMT) return DPD_HEAD_SIMT;
   if (impl_bits(c) == DPD_HEAD_TC) return DPD_HEAD_TC;
+  if (impl_bits(c) == DPD_HEAD_TC_TF32) return DPD_HEAD_TC_TF32;
   return tc_supported(c) ? DPD_HEAD_TC : DPD_HEAD_SIMT;
 }
+bool is_tc(int impl) { return impl == DPD_HEAD_TC || impl == DPD_HEAD_TC_TF32; }
+bool is_f16(int impl) { return impl == DPD_HEAD_TC; }
 
 int check_cfg(const dpd_head_config* c, const char* who) {
   DPD_REQUIRE(c != nullptr, DPD_E_INVALID, "%s: null config", who);
@@ -38,8 +41,8 @@ int check_cfg(const dpd_head_config* c, const char* who) {
   DPD_REQUIRE(c->G >= 2 && c->G <= DPD_MAX_GRID, DPD_E_UNSUPPORTED, "%s: G=%d outside [2,%d]", who, c->G, DPD_MAX_GRID);
   DPD_REQUIRE(c->C > 0 && c->k > 0 && c->k <= 2 * DPD_MAX_GRID, DPD_E_INVALID, "%s: bad C/k", who);
   DPD_REQUIRE(c->H > 0 && c->H % 16 == 0, DPD_E_UNSUPPORTED, "%s: H=%d must be a positive multiple of 16", who, c->H);
-  DPD_REQUIRE((c->flags & ~(0xF | DPD_HEAD_TRAIN)) == 0 && impl_bits(*c) <= DPD_HEAD_TC, DPD_E_INVALID, "%s: bad flags", who);
-  if (impl_bits(*c) == DPD_HEAD_TC)
+  DPD_REQUIRE((c->flags & ~(0xF | DPD_HEAD_TRAIN)) == 0 && impl_bits(*c) <= DPD_HEAD_TC_TF32, DPD_E_INVALID, "%s: bad flags", who);
+  if (impl_bits(*c) == DPD_HEAD_TC || impl_bits(*c) == DPD_HEAD_TC_TF32)
     DPD_REQUIRE(tc_supported(*c), DPD_E_UNSUPPORTED, "%s: tensor-core head needs H %% 256 == 0 and C %% 4 == 0", who);
   if (train_bit(*c))
     DPD_REQUIRE(c->H % 128 == 0 && c->H <= 1024, DPD_E_UNSUPPORTED, "%s: training needs H %% 128 == 0 and H <= 1024", who);
@@ -66,7 +69,7 @@ HeadLayout make_layout(const dpd_head_config& c) {
   L.w2t = o; if (L.train) o += up(H * H * 4);
   L.w3t = o; if (L.train) o += up(H * H * 4);
   L.tc = o;
-  if (L.impl == DPD_HEAD_TC) o += up(tc_packed_bytes(c, L.Kp1));
+  if (is_tc(L.impl)) o += up(tc_packed_bytes(c, is_f16(L.impl)));
   L.total = o;
   return L;
 }
@@ -95,7 +98,7 @@ WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
     W.part4 = o; o += up((size_t)OUT_BWD_CTAS * (H * 3 + 3) * 4);
   }
   W.tc = o;
-  if (L.impl == DPD_HEAD_TC) o += up(tc_workspace_bytes(c, rows));
+  if (is_tc(L.impl)) o += up(tc_workspace_bytes(c, is_f16(L.impl), rows));
   W.total = o;
   return W;
 }
@@ -131,9 +134,9 @@ int forward_chunk(const dpd_head_config* cfg, const HeadLayout& L, const WsLayou
   GatherDesc& g = cx->g;
   g.fv = d_fv; g.idx = cx->idx; g.offset = cx->off; g.row0 = (long long)r0;
   g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
-  if (L.impl == DPD_HEAD_TC) {
-    return tc_head_layers(*cfg, L.Kp1, g, rows, chunk, pk + L.tc, (const float*)(pk + L.b1), (const float*)(pk + L.b2),
-                          (const float*)(pk + L.b3), cx->ha, cx->hb, cx->hc, ws + W.tc, h3, st);
+  if (is_tc(L.impl)) {
+    return tc_head_layers(*cfg, is_f16(L.impl), g, cx->mask, rows, chunk, pk + L.tc, (const float*)(pk + L.b1),
+                          (const float*)(pk + L.b2), (const float*)(pk + L.b3), cx->ha, cx->hb, cx->hc, ws + W.tc, h3, st);
   }
   SimtGemmParams p;
   p.g = g; p.M = rows; p.N = cfg->H; p.relu = 1;
@@ -194,9 +197,9 @@ extern "C" int dpd_head_pack_weights(const dpd_head_config* cfg, const float* d_
     if ((rc = launch_transpose(d_w2, cfg->H, cfg->H, (float*)(base + L.w2t), st))) return rc;
     if ((rc = launch_transpose(d_w3, cfg->H, cfg->H, (float*)(base + L.w3t), st))) return rc;
   }
-  if (L.impl == DPD_HEAD_TC) {
-    rc = tc_pack_weights(*cfg, L.Kp1, (const float*)(base + L.w1p), (const float*)(base + L.w2),
-                         (const float*)(base + L.w3), base + L.tc, st);
+  if (is_tc(L.impl)) {
+    rc = tc_pack_weights(*cfg, is_f16(L.impl), L.Kp1, (const float*)(base + L.w1p), (const float*)(base + L.w2),
+                         (const float*)(base + L.w3), (const float*)(base + L.b1), (const float*)(base + L.b2), base + L.tc, st);
     if (rc) return rc;
   }
   return 0;
@@ -226,8 +229,8 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
   char* ws = (char*)d_workspace;
   const char* pk = (const char*)d_packed;
 
-  if (L.impl == DPD_HEAD_TC) {
-    rc = tc_prepare_fv(*cfg, d_fv, ws + W.tc, chunk, st);
+  if (is_tc(L.impl)) {
+    rc = tc_prepare_fv(*cfg, is_f16(L.impl), d_fv, pk + L.tc, ws + W.tc, chunk, st);
     if (rc) return rc;
   }
   for (size_t r0 = 0; r0 < M; r0 += chunk) {
@@ -269,18 +272,13 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
   float* part = (float*)(ws + W.part); float* part_bias = (float*)(ws + W.part_bias); float* part4 = (float*)(ws + W.part4);
   const bool all = stage == DPD_BWD_ALL;
   // fp32 views of the forward activations (valid after dpd_head_forward with the same cfg and workspace).
-  // SIMT forward: H1 = ha, H2 = hb.  Tensor-core forward: H1 = (ha, hb), H2 = (xh, xl) as (hi, lo) pairs,
-  // merged in place into the hi buffers by the first stage.
+  // SIMT forward leaves H1 in ha and H2 in hb; the tensor-core forwards leave (hi, lo) pairs, merged into
+  // ha / hb by the first stage.
   float* H1 = ha;
   float* H2 = hb;
-  float* H2lo = nullptr;
-  if (L.impl == DPD_HEAD_TC) tc_h2_buffers(*cfg, ws + W.tc, chunk, &H2, &H2lo);
 
   if (all || stage == DPD_BWD_L4) {
-    if (L.impl == DPD_HEAD_TC) {
-      if ((rc = launch_add_inplace(H1, hb, (size_t)rows * H, st))) return rc;
-      if ((rc = launch_add_inplace(H2, H2lo, (size_t)rows * H, st))) return rc;
-    }
+    if (is_tc(L.impl) && (rc = tc_merge_activations(*cfg, is_f16(L.impl), ws + W.tc, chunk, rows, ha, hb, st))) return rc;
     if ((rc = launch_row_active(d_grad_out, rows, active, st))) return rc;
     if ((rc = launch_out_backward(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
                                   d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st))) return rc;
@@ -316,8 +314,8 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
 }
 
 extern "C" int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
-                                 float* d_out, void* d_scratch, size_t scratch_bytes, void* stream) {
+                                 float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream) {
   using namespace dpd;
   DPD_REQUIRE(d_a && d_w && d_bias && d_out && d_scratch, DPD_E_INVALID, "dpd_debug_tc_gemm: null pointer");
-  return tc_debug_gemm(d_a, M, K, d_w, N, d_bias, d_out, d_scratch, scratch_bytes, (cudaStream_t)stream);
+  return tc_debug_gemm(d_a, M, K, d_w, N, d_bias, d_out, d_scratch, scratch_bytes, f16, (cudaStream_t)stream);
 }

@@ -1,164 +1,24 @@
-// tcgen05 tensor-core path of the implicit distance head (layers 1-3), sm_100a.
+// tcgen05 tensor-core path of the implicit distance head (layers 1-3), sm_100a: host side.
 //
 // Precision: the reference computes these convolutions in fp32 (tf.nn.conv2d on fp32 tensors,
-// utils/tf_util.py:213) and parity is 1e-4, which a single TF32 or BF16 pass cannot hold at
-// K = 2503.  Every operand is therefore split x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and
-// each K-step issues three tcgen05.mma.kind::tf32 into the same fp32 TMEM accumulator:
-//   D += Ah*Bh + Al*Bh + Ah*Bl          (dropped term Al*Bl ~ 2^-22 relative)
-//
-// Kernel (head_tc_kernel.cuh): persistent, warp-specialised, one CTA per SM, tile 128(M) x 256(N),
-// K-block 32 fp32 (= one 128-byte swizzle row), 2 smem stages of {Ah, Al, Bh, Bl}, two 256-column
-// TMEM segment accumulators promoted into fp32 register sums by the epilogue warps.
-//   warp 0       TMA producer: weight tiles (and activation tiles in the dense layers)
-//   warp 1       MMA issuer (one thread)
-//   warp 2       TMEM allocator
-//   warps 4-11   epilogue: tcgen05.ld -> RN add into register sums -> +bias -> ReLU -> hi/lo split -> global
-//   warps 12-15  (layer 1 only) patch-gather producers: assemble the A tile straight from the FV
-//                tensor with 16-byte cp.async into the 128B-swizzled layout; the [B,V,k^3*20] patch
-//                tensor of the reference (utils/dpdist_util.py:922-930) never exists.
-#include <cuda.h>
-
+// utils/tf_util.py:213) and parity is 1e-4, which a single TF32/BF16/FP16 pass cannot hold at K = 2503.
+// Every operand is therefore split x = hi + lo and each K-step issues three MMAs, Al*Bh + Ah*Bl + Ah*Bh
+// (the dropped Al*Bl is 2^-22 relative), into segment accumulators that are promoted in fp32 registers
+// (head_tc_kernel.cuh).  Two operand formats:
+//   DPD_HEAD_TC      fp16x3: hi = fp16(s*x), lo = fp16(s*x - hi) with s a power of two chosen from a
+//                    rigorous bound of the tensor (|fv| measured; activations bounded by column L1 norms of
+//                    the weights), so nothing can overflow; 11+11 mantissa bits like TF32, but the fp16 pipe
+//                    runs at twice the TF32 rate and the operands are half the bytes.
+//   DPD_HEAD_TC_TF32 3xTF32: hi = tf32(x), lo = tf32(x - hi); no scaling needed (fp32 exponent range).
 #include "head_bwd.cuh"
 #include "head_tc.cuh"
-
-namespace dpd {
-namespace tc {
-
-constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int STAGES = 2;
-constexpr int A_TILE = BM * BK * 4;   // 16 KB
-constexpr int B_TILE = BN * BK * 4;   // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-constexpr int TMEM_COLS = 512;
-constexpr int NUM_GATHER_THREADS = 128;
-constexpr uint32_t LUT_ZERO = 0xFFFFFFFFu, LUT_OFFS = 0xFFFFFFFEu;
-constexpr int MAX_LUT = 4096;  // chunks of 4 floats: Kp1 <= 16384
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-// 16 TMEM lanes x 64 columns; register 4j+u: row lane/4 + 8*(u>>1), column 8j + 2*(lane%4) + (u&1)
-__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major: 1) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
-// A,B K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-}  // namespace tc
-}  // namespace dpd
-
 #include "head_tc_kernel.cuh"
 
 namespace dpd {
 namespace tc {
 
 // ---------------------------------------------------------------------------------------------
-// helper kernels
+// helper kernels: TF32 format
 // ---------------------------------------------------------------------------------------------
 // Wt_hi/lo[n][k] from W[k][n] (row-major [K,N]); 32x32 smem transpose
 __global__ void transpose_split_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ t_hi,
@@ -202,7 +62,127 @@ __global__ void split_off4_kernel(const float* __restrict__ off, int rows, float
 }
 
 // ---------------------------------------------------------------------------------------------
-// host side
+// helper kernels: scaled FP16 format
+// ---------------------------------------------------------------------------------------------
+// scale slots (floats): per-forward values live in the workspace, per-pack values in the blob
+enum { S_A1 = 0, S_A2, S_A3, S_ACC1, S_ACC2, S_ACC3, S_FVMAX_BITS, S_COUNT = 8 };          // workspace
+enum { P_W1 = 0, P_W2, P_W3, P_W1MAX_BITS, P_W2MAX_BITS, P_W3MAX_BITS, P_C1_BITS, P_C2_BITS, P_B1MAX_BITS, P_B2MAX_BITS, P_COUNT = 12 };  // blob
+
+__device__ __forceinline__ float pow2_floor_scale(float bound) {
+  // largest power of two s with s*bound <= 32768 (half of the fp16 maximum), clamped for degenerate bounds
+  const float b = fmaxf(bound, 1e-30f);
+  float e = floorf(log2f(32768.0f / b));
+  e = fminf(fmaxf(e, -60.f), 60.f);
+  return exp2f(e);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ out_bits) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+// max over columns n of sum_k |w[k][n]|   (w row-major [K, N])
+__global__ void col_l1_max_kernel(const float* __restrict__ w, int K, int N, unsigned* __restrict__ out_bits) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f;
+  if (n < N)
+    for (int k = 0; k < K; ++k) s += fabsf(w[(size_t)k * N + n]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(s));
+}
+
+__global__ void weight_scales_kernel(float* __restrict__ ps) {   // one thread
+  unsigned* pb = reinterpret_cast<unsigned*>(ps);
+  ps[P_W1] = pow2_floor_scale(__uint_as_float(pb[P_W1MAX_BITS]));
+  ps[P_W2] = pow2_floor_scale(__uint_as_float(pb[P_W2MAX_BITS]));
+  ps[P_W3] = pow2_floor_scale(__uint_as_float(pb[P_W3MAX_BITS]));
+}
+
+// per forward: activation scales from |fv|max and the weight column norms (rigorous bounds, no overflow possible):
+//   |A1| <= in1 = max(|fv|max, 1)            (offsets are < 1: query - centre of its own voxel, masked rows zeroed)
+//   |H1| <= B1 = in1*c1 + max|b1|,  |H2| <= B2 = B1*c2 + max|b2|     (c_l = max column L1 norm of W_l)
+__global__ void activation_scales_kernel(float* __restrict__ ws, const float* __restrict__ ps) {   // one thread
+  const unsigned* wb = reinterpret_cast<const unsigned*>(ws);
+  const unsigned* pb = reinterpret_cast<const unsigned*>(ps);
+  const float in1 = fmaxf(__uint_as_float(wb[S_FVMAX_BITS]), 1.0f);
+  const float B1 = in1 * __uint_as_float(pb[P_C1_BITS]) + __uint_as_float(pb[P_B1MAX_BITS]);
+  const float B2 = B1 * __uint_as_float(pb[P_C2_BITS]) + __uint_as_float(pb[P_B2MAX_BITS]);
+  const float a1 = pow2_floor_scale(in1), a2 = pow2_floor_scale(B1), a3 = pow2_floor_scale(B2);
+  ws[S_A1] = a1; ws[S_A2] = a2; ws[S_A3] = a3;
+  ws[S_ACC1] = 1.0f / (a1 * ps[P_W1]); ws[S_ACC2] = 1.0f / (a2 * ps[P_W2]); ws[S_ACC3] = 1.0f / (a3 * ps[P_W3]);
+}
+
+__global__ void debug_scales_kernel(float* __restrict__ sc) {   // one thread (tc_debug_gemm)
+  const unsigned* b = reinterpret_cast<const unsigned*>(sc);
+  sc[0] = pow2_floor_scale(__uint_as_float(b[4]));
+  sc[1] = pow2_floor_scale(__uint_as_float(b[5]));
+  sc[2] = 1.0f / (sc[0] * sc[1]);
+}
+
+__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+// Wt_hi/lo[n][k] (fp16, [N, Kp], zero beyond K) from W[k][n] times *scale
+__global__ void transpose_split_f16_kernel(const float* __restrict__ w, int K, int Kp, int N, const float* __restrict__ scale,
+                                           __half* __restrict__ t_hi, __half* __restrict__ t_lo) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const float s = *scale;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? w[(size_t)k * N + n] * s : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < Kp) {
+      __half hi, lo;
+      split_half(tile[threadIdx.x][i], hi, lo);
+      t_hi[(size_t)n * Kp + k] = hi;
+      t_lo[(size_t)n * Kp + k] = lo;
+    }
+  }
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ x, size_t n, const float* __restrict__ scale, __half* __restrict__ hi,
+                                 __half* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  split_half(x[i] * *scale, hi[i], lo[i]);
+}
+
+// offsets of rows outside the unit cube are zeroed: their output is masked to 0 anyway (:697-698) and an
+// arbitrary far-away query must not be able to overflow fp16
+__global__ void split_off4_f16_kernel(const float* __restrict__ off, const float* __restrict__ mask, int rows,
+                                      const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float s = mask[i] != 0.f ? *scale : 0.f;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    __half h = __float2half_rn(0.f), l = h;
+    if (d < 3 && s != 0.f) split_half(off[(size_t)i * 3 + d] * s, h, l);
+    hi[(size_t)i * 4 + d] = h;
+    lo[(size_t)i * 4 + d] = l;
+  }
+}
+
+// fp32 activations for the backward pass: (hi + lo) / scale
+__global__ void merge_f16_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, const float* __restrict__ scale,
+                                 float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (__half2float(hi[i]) + __half2float(lo[i])) / *scale;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -220,58 +200,66 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, cols] fp32 row-major (pitch = cols), box = {32 cols, box_rows}, 128-byte swizzle
-static int make_tmap(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// [rows, cols] row-major (pitch = cols) of fp32 or fp16, box = {128 bytes of columns, box_rows}, 128-byte swizzle
+static int make_tmap(CUtensorMap* m, const void* base, bool f16, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   DPD_REQUIRE(fn != nullptr, DPD_E_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not found");
+  const int elem = f16 ? 2 : 4;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint64_t gstr[1] = {cols * (cuuint64_t)elem};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DPD_REQUIRE(r == CUDA_SUCCESS, DPD_E_INVALID, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
               (unsigned long long)rows, (unsigned long long)cols);
   return 0;
 }
 
-static size_t smem_bytes(int num_kb) {
-  return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SharedCtl) + (size_t)num_kb * (BK / 4) * sizeof(uint32_t);
+template <bool GATHER, bool F16>
+static int launch_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                    const KernelArgs& ka, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel<GATHER, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    attr_done = true;
+  }
+  const char* name = GATHER ? (F16 ? "tc_gemm_gather_l1_f16" : "tc_gemm_gather_l1_tf32") : (F16 ? "tc_gemm_dense_f16" : "tc_gemm_dense_tf32");
+  DPD_LAUNCH(name, st, tc_gemm_kernel<GATHER, F16><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
+  DPD_CUDA_CHECK_LAUNCH("tc_gemm_kernel");
+  return 0;
 }
 
-// D[M,N] = relu(A[M,K] * B[N,K]^T + bias), operands pre-split (hi, lo); K % 32 == 0, N % 256 == 0
-static int launch(bool gather, const float* a_hi, const float* a_lo, int M, int K, const float* bt_hi, const float* bt_lo,
-                  int N, const float* bias, float* out0, float* out1, int split, const GatherArgs* g, cudaStream_t st) {
-  DPD_REQUIRE(K % BK == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm: need K %% 32 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
+// D[M,N] = relu(acc_scale * A[M,K] * B[N,K]^T + bias), operands pre-split (hi, lo); K % kb == 0, N % 256 == 0
+static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo,
+                  int N, const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
+                  const GatherArgs* g, cudaStream_t st) {
+  const int kb = f16 ? 64 : 32;
+  DPD_REQUIRE(K % kb == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm: need K %% %d == 0, N %% 256 == 0 (K=%d N=%d)", kb, K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_tmap(&tb_hi, bt_hi, N, K, BN))) return rc;
-  if ((rc = make_tmap(&tb_lo, bt_lo, N, K, BN))) return rc;
+  if ((rc = make_tmap(&tb_hi, bt_hi, f16, N, K, BN))) return rc;
+  if ((rc = make_tmap(&tb_lo, bt_lo, f16, N, K, BN))) return rc;
   if (!gather) {
-    if ((rc = make_tmap(&ta_hi, a_hi, M, K, BM))) return rc;
-    if ((rc = make_tmap(&ta_lo, a_lo, M, K, BM))) return rc;
+    if ((rc = make_tmap(&ta_hi, a_hi, f16, M, K, BM))) return rc;
+    if ((rc = make_tmap(&ta_lo, a_lo, f16, M, K, BM))) return rc;
   } else {
     ta_hi = tb_hi; ta_lo = tb_lo;   // unused
   }
   KernelArgs ka;
   memset(&ka, 0, sizeof(ka));
-  ka.M = M; ka.N = N; ka.num_kb = K / BK; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
+  ka.M = M; ka.N = N; ka.num_kb = K / kb; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
+  ka.acc_scale = acc_scale; ka.out_scale = out_scale;
   if (g) ka.g = *g;
   const int tiles = ceil_div(M, BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  const size_t smem = smem_bytes(ka.num_kb);
-  if (gather) {
-    static bool attr_done = false;
-    if (!attr_done) { DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024)); attr_done = true; }
-    DPD_LAUNCH("tc_gemm_gather_l1", st, tc_gemm_kernel<true><<<grid, 512, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
-  } else {
-    static bool attr_done = false;
-    if (!attr_done) { DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024)); attr_done = true; }
-    DPD_LAUNCH("tc_gemm_dense", st, tc_gemm_kernel<false><<<grid, 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
-  }
-  DPD_CUDA_CHECK_LAUNCH("tc_gemm_kernel");
-  return 0;
+  const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SharedCtl) + (size_t)(K / 4) * sizeof(uint32_t);
+  if (gather) return f16 ? launch_t<true, true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st)
+                         : launch_t<true, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
+  return f16 ? launch_t<false, true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st)
+             : launch_t<false, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
 }
 
 }  // namespace tc
@@ -286,103 +274,180 @@ bool tc_supported(const dpd_head_config& c) {
 
 namespace {
 size_t up256(size_t x) { return round_up<size_t>(x, 256); }
-struct TcBlob { size_t w1h, w1l, w2h, w2l, w3h, w3l, total; };
-TcBlob tc_blob_layout(const dpd_head_config& c, int Kp1) {
-  TcBlob b; size_t o = 0; const size_t H = c.H;
-  b.w1h = o; o += up256(H * Kp1 * 4); b.w1l = o; o += up256(H * Kp1 * 4);
-  b.w2h = o; o += up256(H * H * 4);   b.w2l = o; o += up256(H * H * 4);
-  b.w3h = o; o += up256(H * H * 4);   b.w3l = o; o += up256(H * H * 4);
+int kp1_of(const dpd_head_config& c, bool f16) { return round_up(c.k * c.k * c.k * c.C + 3, f16 ? 64 : 32); }
+
+struct TcBlob { size_t w1h, w1l, w2h, w2l, w3h, w3l, scales, total; };
+TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
+  TcBlob b; size_t o = 0; const size_t H = c.H, e = f16 ? 2 : 4, Kp1 = kp1_of(c, f16);
+  b.w1h = o; o += up256(H * Kp1 * e); b.w1l = o; o += up256(H * Kp1 * e);
+  b.w2h = o; o += up256(H * H * e);   b.w2l = o; o += up256(H * H * e);
+  b.w3h = o; o += up256(H * H * e);   b.w3l = o; o += up256(H * H * e);
+  b.scales = o; o += up256(tc::P_COUNT * 4);
   b.total = o; return b;
 }
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, total; };
-TcWs tc_ws_layout(const dpd_head_config& c, size_t rows) {
-  TcWs w; size_t o = 0;
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, scales, total; };
+TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
+  TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
-  w.fvh = o; o += up256(nfv * 4); w.fvl = o; o += up256(nfv * 4);
-  w.o4h = o; o += up256(rows * 16); w.o4l = o; o += up256(rows * 16);
-  w.xh = o; o += up256(rows * (size_t)c.H * 4); w.xl = o; o += up256(rows * (size_t)c.H * 4);
+  w.fvh = o; o += up256(nfv * e); w.fvl = o; o += up256(nfv * e);
+  w.o4h = o; o += up256(rows * 4 * e); w.o4l = o; o += up256(rows * 4 * e);
+  w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
+  w.yh = w.yl = o;
+  if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
+  w.scales = o; o += up256(tc::S_COUNT * 4);
   w.total = o; return w;
 }
 }  // namespace
 
-size_t tc_packed_bytes(const dpd_head_config& c, int Kp1) { return tc_blob_layout(c, Kp1).total; }
-size_t tc_workspace_bytes(const dpd_head_config& c, size_t rows) { return tc_ws_layout(c, rows).total; }
+size_t tc_packed_bytes(const dpd_head_config& c, bool f16) { return tc_blob_layout(c, f16).total; }
+size_t tc_workspace_bytes(const dpd_head_config& c, bool f16, size_t rows) { return tc_ws_layout(c, f16, rows).total; }
 
-// backward support: where the (hi, lo) halves of the layer-2 activations live
-void tc_h2_buffers(const dpd_head_config& c, void* tc_ws, size_t ws_rows, float** hi, float** lo) {
-  const TcWs w = tc_ws_layout(c, ws_rows);
-  char* ws = (char*)tc_ws;
-  *hi = (float*)(ws + w.xh);
-  *lo = (float*)(ws + w.xl);
-}
-
-int tc_pack_weights(const dpd_head_config& c, int Kp1, const float* w1p, const float* w2, const float* w3, void* tc_blob,
-                    cudaStream_t st) {
-  const TcBlob b = tc_blob_layout(c, Kp1);
+int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float* w1p, const float* w2, const float* w3,
+                    const float* b1, const float* b2, void* tc_blob, cudaStream_t st) {
+  const TcBlob b = tc_blob_layout(c, f16);
   char* base = (char*)tc_blob;
   const int H = c.H;
   dim3 blk(32, 8);
-  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(H, 32), ceil_div(Kp1, 32)), blk, 0, st>>>(
-      w1p, Kp1, H, (float*)(base + b.w1h), (float*)(base + b.w1l)));
-  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
-      w2, H, H, (float*)(base + b.w2h), (float*)(base + b.w2l)));
-  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
-      w3, H, H, (float*)(base + b.w3h), (float*)(base + b.w3l)));
-  DPD_CUDA_CHECK_LAUNCH("transpose_split_kernel");
+  if (!f16) {
+    DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(H, 32), ceil_div(Kp1_src, 32)), blk, 0, st>>>(
+        w1p, Kp1_src, H, (float*)(base + b.w1h), (float*)(base + b.w1l)));
+    DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
+        w2, H, H, (float*)(base + b.w2h), (float*)(base + b.w2l)));
+    DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
+        w3, H, H, (float*)(base + b.w3h), (float*)(base + b.w3l)));
+    DPD_CUDA_CHECK_LAUNCH("transpose_split_kernel");
+    return 0;
+  }
+  const int Kp1 = kp1_of(c, true);
+  float* ps = (float*)(base + b.scales);
+  unsigned* pb = (unsigned*)ps;
+  DPD_CUDA_CALL(cudaMemsetAsync(ps, 0, tc::P_COUNT * 4, st));
+  const size_t n1 = (size_t)Kp1_src * H, n2 = (size_t)H * H;
+  DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<256, 256, 0, st>>>(w1p, n1, pb + tc::P_W1MAX_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<256, 256, 0, st>>>(w2, n2, pb + tc::P_W2MAX_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<256, 256, 0, st>>>(w3, n2, pb + tc::P_W3MAX_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<4, 256, 0, st>>>(b1, (size_t)H, pb + tc::P_B1MAX_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<4, 256, 0, st>>>(b2, (size_t)H, pb + tc::P_B2MAX_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 256), 256, 0, st>>>(w1p, Kp1_src, H, pb + tc::P_C1_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 256), 256, 0, st>>>(w2, H, H, pb + tc::P_C2_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::weight_scales_kernel<<<1, 1, 0, st>>>(ps));
+  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(Kp1, 32)), blk, 0, st>>>(
+      w1p, Kp1_src, Kp1, H, ps + tc::P_W1, (__half*)(base + b.w1h), (__half*)(base + b.w1l)));
+  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
+      w2, H, H, H, ps + tc::P_W2, (__half*)(base + b.w2h), (__half*)(base + b.w2l)));
+  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
+      w3, H, H, H, ps + tc::P_W3, (__half*)(base + b.w3h), (__half*)(base + b.w3l)));
+  DPD_CUDA_CHECK_LAUNCH("tc_pack_weights f16");
   return 0;
 }
 
-int tc_prepare_fv(const dpd_head_config& c, const float* fv, void* tc_ws, size_t rows, cudaStream_t st) {
-  const TcWs w = tc_ws_layout(c, rows);
+int tc_prepare_fv(const dpd_head_config& c, bool f16, const float* fv, const void* tc_blob, void* tc_ws, size_t ws_rows,
+                  cudaStream_t st) {
+  const TcWs w = tc_ws_layout(c, f16, ws_rows);
   char* ws = (char*)tc_ws;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
-  DPD_LAUNCH("tc_split_fv", st, tc::split_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
-      fv, nfv, (float*)(ws + w.fvh), (float*)(ws + w.fvl)));
-  DPD_CUDA_CHECK_LAUNCH("split_kernel");
+  if (!f16) {
+    DPD_LAUNCH("tc_split_fv", st, tc::split_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
+        fv, nfv, (float*)(ws + w.fvh), (float*)(ws + w.fvl)));
+    DPD_CUDA_CHECK_LAUNCH("split_kernel");
+    return 0;
+  }
+  const TcBlob b = tc_blob_layout(c, true);
+  float* sc = (float*)(ws + w.scales);
+  DPD_CUDA_CALL(cudaMemsetAsync(sc, 0, tc::S_COUNT * 4, st));
+  DPD_LAUNCH("tc_fv_absmax", st, tc::absmax_kernel<<<num_sms() * 4, 256, 0, st>>>(fv, nfv, (unsigned*)sc + tc::S_FVMAX_BITS));
+  DPD_LAUNCH("tc_scales", st, tc::activation_scales_kernel<<<1, 1, 0, st>>>(sc, (const float*)((const char*)tc_blob + b.scales)));
+  DPD_LAUNCH("tc_split_fv", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
+      fv, nfv, sc + tc::S_A1, (__half*)(ws + w.fvh), (__half*)(ws + w.fvl)));
+  DPD_CUDA_CHECK_LAUNCH("tc_prepare_fv f16");
   return 0;
 }
 
-int tc_head_layers(const dpd_head_config& c, int Kp1, const GatherDesc& g, int rows, size_t ws_rows, const void* tc_blob,
-                   const float* b1, const float* b2, const float* b3, float* ha, float* hb, float* h3_out,
-                   void* tc_ws, const float** h3, cudaStream_t st) {
-  const TcBlob b = tc_blob_layout(c, Kp1);
-  const TcWs w = tc_ws_layout(c, ws_rows);
+int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, const float* mask, int rows, size_t ws_rows,
+                   const void* tc_blob, const float* b1, const float* b2, const float* b3, float* ha, float* hb,
+                   float* h3_out, void* tc_ws, const float** h3, cudaStream_t st) {
+  const TcBlob b = tc_blob_layout(c, f16);
+  const TcWs w = tc_ws_layout(c, f16, ws_rows);
   const char* blob = (const char*)tc_blob;
   char* ws = (char*)tc_ws;
-  const int H = c.H;
-  float* o4h = (float*)(ws + w.o4h); float* o4l = (float*)(ws + w.o4l);
-  float* xh = (float*)(ws + w.xh);   float* xl = (float*)(ws + w.xl);
-  DPD_LAUNCH("tc_split_off", st, tc::split_off4_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(g.offset, rows, o4h, o4l));
-  DPD_CUDA_CHECK_LAUNCH("split_off4_kernel");
+  const int H = c.H, Kp1 = kp1_of(c, f16);
+  const float* sc = (const float*)(ws + w.scales);
   tc::GatherArgs ga;
-  ga.fv_hi = (const float*)(ws + w.fvh); ga.fv_lo = (const float*)(ws + w.fvl);
-  ga.idx = g.idx; ga.off4_hi = o4h; ga.off4_lo = o4l; ga.row0 = g.row0;
+  ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g.idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g.row0;
   ga.n_query = g.n_query; ga.G = g.G; ga.C = g.C; ga.k = g.k; ga.E = g.E;
+  float* out3 = h3_out ? h3_out : ha;
   int rc;
-  // layer 1: gathered A -> (ha = hi, hb = lo)
-  rc = tc::launch(true, nullptr, nullptr, rows, Kp1, (const float*)(blob + b.w1h), (const float*)(blob + b.w1l), H, b1, ha, hb, 1, &ga, st);
-  if (rc) return rc;
-  // layer 2: (ha, hb) -> (xh, xl)
-  rc = tc::launch(false, ha, hb, rows, H, (const float*)(blob + b.w2h), (const float*)(blob + b.w2l), H, b2, xh, xl, 1, nullptr, st);
-  if (rc) return rc;
-  // layer 3: (xh, xl) -> ha (plain fp32 for the fp32 output layer)
-  rc = tc::launch(false, xh, xl, rows, H, (const float*)(blob + b.w3h), (const float*)(blob + b.w3l), H, b3, h3_out ? h3_out : ha, nullptr, 0, nullptr, st);
-  if (rc) return rc;
-  *h3 = h3_out ? h3_out : ha;
+  if (!f16) {
+    DPD_LAUNCH("tc_split_off", st, tc::split_off4_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(g.offset, rows, (float*)(ws + w.o4h), (float*)(ws + w.o4l)));
+    DPD_CUDA_CHECK_LAUNCH("split_off4_kernel");
+    // layer 1: gathered A -> (ha = hi, hb = lo); layer 2 -> (xh, xl); layer 3 -> fp32
+    if ((rc = tc::launch(true, false, nullptr, nullptr, rows, Kp1, blob + b.w1h, blob + b.w1l, H, b1, ha, hb, 1, nullptr, nullptr, &ga, st))) return rc;
+    if ((rc = tc::launch(false, false, ha, hb, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.xh, ws + w.xl, 1, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = tc::launch(false, false, ws + w.xh, ws + w.xl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, out3, nullptr, 0, nullptr, nullptr, nullptr, st))) return rc;
+  } else {
+    DPD_LAUNCH("tc_split_off", st, tc::split_off4_f16_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
+        g.offset, mask, rows, sc + tc::S_A1, (__half*)(ws + w.o4h), (__half*)(ws + w.o4l)));
+    DPD_CUDA_CHECK_LAUNCH("split_off4_f16_kernel");
+    // layer 1: gathered A -> (xh, xl) scaled by sA2; layer 2 -> (yh, yl) scaled by sA3; layer 3 -> fp32
+    if ((rc = tc::launch(true, true, nullptr, nullptr, rows, Kp1, blob + b.w1h, blob + b.w1l, H, b1, ws + w.xh, ws + w.xl, 1,
+                         sc + tc::S_ACC1, sc + tc::S_A2, &ga, st))) return rc;
+    if ((rc = tc::launch(false, true, ws + w.xh, ws + w.xl, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.yh, ws + w.yl, 1,
+                         sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st))) return rc;
+    if ((rc = tc::launch(false, true, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, out3, nullptr, 0,
+                         sc + tc::S_ACC3, nullptr, nullptr, st))) return rc;
+  }
+  (void)hb;
+  *h3 = out3;
+  return 0;
+}
+
+// backward support: fp32 H1 -> ha, H2 -> hb from the (hi, lo) pairs the forward left behind
+int tc_merge_activations(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, int rows, float* ha, float* hb,
+                         cudaStream_t st) {
+  const TcWs w = tc_ws_layout(c, f16, ws_rows);
+  char* ws = (char*)tc_ws;
+  const size_t n = (size_t)rows * c.H;
+  int rc;
+  if (!f16) {   // H1 = (ha, hb), H2 = (xh, xl): H1 into ha, then H2 into hb
+    if ((rc = launch_add_inplace(ha, hb, n, st))) return rc;
+    DPD_CUDA_CALL(cudaMemcpyAsync(hb, ws + w.xh, n * 4, cudaMemcpyDeviceToDevice, st));
+    return launch_add_inplace(hb, (const float*)(ws + w.xl), n, st);
+  }
+  const float* sc = (const float*)(ws + w.scales);
+  DPD_LAUNCH("bwd_merge_hi_lo", st, tc::merge_f16_kernel<<<(unsigned)ceil_div<size_t>(n, 256), 256, 0, st>>>(
+      (const __half*)(ws + w.xh), (const __half*)(ws + w.xl), sc + tc::S_A2, ha, n));
+  DPD_LAUNCH("bwd_merge_hi_lo", st, tc::merge_f16_kernel<<<(unsigned)ceil_div<size_t>(n, 256), 256, 0, st>>>(
+      (const __half*)(ws + w.yh), (const __half*)(ws + w.yl), sc + tc::S_A3, hb, n));
+  DPD_CUDA_CHECK_LAUNCH("merge_f16_kernel");
   return 0;
 }
 
 // test hook: dense split-precision GEMM on caller-provided fp32 operands (see include/dpdist_b200.h)
 int tc_debug_gemm(const float* a, int M, int K, const float* w, int N, const float* bias, float* out, void* scratch,
-                  size_t scratch_bytes, cudaStream_t st) {
-  const size_t need = ((size_t)M * K * 2 + (size_t)N * K * 2) * 4;
+                  size_t scratch_bytes, int f16, cudaStream_t st) {
+  const size_t need = ((size_t)M * K * 2 + (size_t)N * K * 2) * 4 + 256;
   DPD_REQUIRE(scratch_bytes >= need, DPD_E_WORKSPACE, "tc_debug_gemm: scratch %zu < %zu", scratch_bytes, need);
-  float* ah = (float*)scratch; float* al = ah + (size_t)M * K;
-  float* bh = al + (size_t)M * K; float* bl = bh + (size_t)N * K;
-  DPD_LAUNCH("tc_split_fv", st, tc::split_kernel<<<(unsigned)ceil_div<size_t>((size_t)M * K, 256), 256, 0, st>>>(a, (size_t)M * K, ah, al));
-  DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), dim3(32, 8), 0, st>>>(w, K, N, bh, bl));
-  DPD_CUDA_CHECK_LAUNCH("tc_debug_gemm prep");
-  return tc::launch(false, ah, al, M, K, bh, bl, N, bias, out, nullptr, 0, nullptr, st);
+  char* s = (char*)scratch;
+  if (!f16) {
+    float* ah = (float*)s; float* al = ah + (size_t)M * K;
+    float* bh = al + (size_t)M * K; float* bl = bh + (size_t)N * K;
+    DPD_LAUNCH("tc_split_fv", st, tc::split_kernel<<<(unsigned)ceil_div<size_t>((size_t)M * K, 256), 256, 0, st>>>(a, (size_t)M * K, ah, al));
+    DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), dim3(32, 8), 0, st>>>(w, K, N, bh, bl));
+    DPD_CUDA_CHECK_LAUNCH("tc_debug_gemm prep");
+    return tc::launch(false, false, ah, al, M, K, bh, bl, N, bias, out, nullptr, 0, nullptr, nullptr, nullptr, st);
+  }
+  // fp16x3 with scales from the measured maxima of both operands
+  float* sc = (float*)s;                      // [0] sA  [1] sW  [2] 1/(sA*sW)  [4] |a|max bits  [5] |w|max bits
+  __half* ah = (__half*)(s + 256); __half* al = ah + (size_t)M * K;
+  __half* bh = al + (size_t)M * K; __half* bl = bh + (size_t)N * K;
+  DPD_CUDA_CALL(cudaMemsetAsync(sc, 0, 64, st));
+  tc::absmax_kernel<<<256, 256, 0, st>>>(a, (size_t)M * K, (unsigned*)sc + 4);
+  tc::absmax_kernel<<<256, 256, 0, st>>>(w, (size_t)N * K, (unsigned*)sc + 5);
+  tc::debug_scales_kernel<<<1, 1, 0, st>>>(sc);
+  tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>((size_t)M * K, 256), 256, 0, st>>>(a, (size_t)M * K, sc + 0, ah, al);
+  tc::transpose_split_f16_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), dim3(32, 8), 0, st>>>(w, K, K, N, sc + 1, bh, bl);
+  DPD_CUDA_CHECK_LAUNCH("tc_debug_gemm f16 prep");
+  return tc::launch(false, true, ah, al, M, K, bh, bl, N, bias, out, nullptr, 0, sc + 2, nullptr, nullptr, st);
 }
 
 }  // namespace dpd

@@ -1,4 +1,8 @@
 // The persistent tcgen05 GEMM kernel of the head (included by head_tc.cu only).
+//   D[M,N] = relu(acc_scale * (A[M,K] . B[N,K]^T) + bias), operands pre-split into (hi, lo)
+//   F16 = false: hi/lo are TF32-rounded fp32 (3xTF32), K-block = 32
+//   F16 = true : hi/lo are fp16 of the operand times a power-of-two scale (fp16x3), K-block = 64
+// Either way a K-step issues three MMAs into the same fp32 TMEM accumulator: Al*Bh + Ah*Bl + Ah*Bh.
 //
 // Accuracy note (measured on B200): tcgen05.mma adds into the fp32 TMEM accumulator with
 // truncation, so a long K loop drifts by ~0.5 ulp per MMA (3.5e-5 absolute at K=1024 with three
@@ -7,30 +11,32 @@
 // starting from zero, and the epilogue warps promote finished segments into per-thread fp32
 // register sums with round-to-nearest adds while the next segment runs.
 #pragma once
+#include "tc_ptx.cuh"
 
 namespace dpd {
 namespace tc {
 
-constexpr int SEG_KB = 4;            // K-blocks (of 32) per TMEM accumulation segment
 constexpr int NUM_EPI_WARPS = 8;     // 2 per TMEM lane quarter, 128 columns each
 constexpr int EPI_COLS = BN / 2;
 
 struct GatherArgs {
-  const float* fv_hi;
-  const float* fv_lo;
+  const void* fv_hi;       // [n_clouds, V, C] fp32 (tf32-rounded) or fp16 (scaled)
+  const void* fv_lo;
   const int32_t* idx;      // [rows] chunk-local voxel index
-  const float* off4_hi;    // [rows,4]
-  const float* off4_lo;
+  const void* off4_hi;     // [rows,4]
+  const void* off4_lo;
   long long row0;          // global row of chunk-local row 0
   int n_query, G, C, k, E;
 };
 
 struct KernelArgs {
-  int M, N, num_kb;        // rows, output features, K / 32
+  int M, N, num_kb;        // rows, output features, K-blocks
   const float* bias;       // [N]
-  float* out0;             // split ? hi : value
-  float* out1;             // split ? lo : unused
+  void* out0;              // split ? hi (fp32 | fp16) : fp32 value
+  void* out1;              // split ? lo : unused
   int split;
+  const float* acc_scale;  // device scalar multiplied into the accumulator (1/(sA*sW)); nullptr = 1
+  const float* out_scale;  // device scalar applied before the fp16 split of the output; nullptr = 1
   GatherArgs g;
 };
 
@@ -52,11 +58,15 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 }
 
 // warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-11 epilogue | 12-15 gather (layer 1)
-template <bool GATHER>
+template <bool GATHER, bool F16>
 __global__ void __launch_bounds__(GATHER ? 512 : 384, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const KernelArgs args) {
+  constexpr int KB_ELEMS = F16 ? 64 : 32;          // elements per K-block (128 bytes)
+  constexpr int ELEM = F16 ? 2 : 4;
+  constexpr int CHUNKS = KB_ELEMS / 4;             // 4-element gather chunks per row per K-block
+  constexpr int SEG = F16 ? 2 : 4;                 // K-blocks per promotion segment (K = 128 either way)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   SharedCtl* ctl = (SharedCtl*)(smem + STAGES * STAGE_BYTES);
@@ -89,8 +99,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
   if (warp == 2) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
   if (GATHER) {
-    // chunk LUT: 4-float chunk q of the virtual row -> (a0,a1,a2,part) | OFFS | ZERO
-    const int nchunks = args.num_kb * (BK / 4);
+    // chunk LUT: 4-element chunk q of the virtual row -> (a0,a1,a2,part) | OFFS | ZERO
+    const int nchunks = args.num_kb * CHUNKS;
     const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4;
     for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
       uint32_t code;
@@ -119,11 +129,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         for (int kb = 0; kb < args.num_kb; ++kb) {
           mbar_wait(&ctl->empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&ctl->full[s], GATHER ? 2 * B_TILE : STAGE_BYTES);
-          tma_load_2d(stage_ptr(s, 2), &tm_b_hi, &ctl->full[s], kb * BK, nt * BN);
-          tma_load_2d(stage_ptr(s, 3), &tm_b_lo, &ctl->full[s], kb * BK, nt * BN);
+          tma_load_2d(stage_ptr(s, 2), &tm_b_hi, &ctl->full[s], kb * KB_ELEMS, nt * BN);
+          tma_load_2d(stage_ptr(s, 3), &tm_b_lo, &ctl->full[s], kb * KB_ELEMS, nt * BN);
           if (!GATHER) {
-            tma_load_2d(stage_ptr(s, 0), &tm_a_hi, &ctl->full[s], kb * BK, mt * BM);
-            tma_load_2d(stage_ptr(s, 1), &tm_a_lo, &ctl->full[s], kb * BK, mt * BM);
+            tma_load_2d(stage_ptr(s, 0), &tm_a_hi, &ctl->full[s], kb * KB_ELEMS, mt * BM);
+            tma_load_2d(stage_ptr(s, 1), &tm_a_lo, &ctl->full[s], kb * KB_ELEMS, mt * BM);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -133,12 +143,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       int s = 0; uint32_t ph = 0;
       int sb = 0; uint32_t sb_ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG_KB) {
+        for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG) {
           mbar_wait(&ctl->seg_empty[sb], sb_ph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
           uint32_t accumulate = 0;        // every segment starts from zero
-          const int kb1 = min(kb0 + SEG_KB, args.num_kb);
+          const int kb1 = min(kb0 + SEG, args.num_kb);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&ctl->full[s], ph);
             tc_fence_after();
@@ -147,11 +157,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint64_t bh = make_desc_sw128(smem_u32(stage_ptr(s, 2)));
             const uint64_t bl = make_desc_sw128(smem_u32(stage_ptr(s, 3)));
 #pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-              const uint64_t o = (uint64_t)(ks * 2);   // +32 bytes per K-step of 8 tf32, in 16-byte units
-              umma_tf32(d_tmem, al + o, bh + o, IDESC, accumulate);   // small correction terms first
-              umma_tf32(d_tmem, ah + o, bl + o, IDESC, 1);
-              umma_tf32(d_tmem, ah + o, bh + o, IDESC, 1);
+            for (int ks = 0; ks < 4; ++ks) {           // 32 bytes of K per MMA: 8 tf32 or 16 fp16
+              const uint64_t o = (uint64_t)(ks * 2);   // in 16-byte units
+              if (F16) {
+                umma_f16(d_tmem, al + o, bh + o, IDESC_F16, accumulate);    // small correction terms first
+                umma_f16(d_tmem, ah + o, bl + o, IDESC_F16, 1);
+                umma_f16(d_tmem, ah + o, bh + o, IDESC_F16, 1);
+              } else {
+                umma_tf32(d_tmem, al + o, bh + o, IDESC_TF32, accumulate);
+                umma_tf32(d_tmem, ah + o, bl + o, IDESC_TF32, 1);
+                umma_tf32(d_tmem, ah + o, bh + o, IDESC_TF32, 1);
+              }
               accumulate = 1;
             }
             umma_commit(&ctl->empty[s]);     // frees the smem slot when these MMAs retire
@@ -168,16 +184,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int e = warp - 4;
     const int q = e & 3;                    // TMEM lane quarter (== warp % 4)
     const int half = e >> 2;                // which 128 of the 256 columns
+    const float acc_scale = args.acc_scale ? __ldg(args.acc_scale) : 1.0f;
+    const float out_scale = args.out_scale ? __ldg(args.out_scale) : 1.0f;
     int sb = 0; uint32_t sb_ph = 0;
     // Register sums in the tcgen05.ld 16x256b fragment layout: load (rh, cg) covers TMEM lanes
     // 32q+16rh..+16 and columns 64cg..+64; register i = 4j+u of that load holds
     //   row 16rh + lane/4 + 8*(u>>1),  column 64cg + 8j + 2*(lane%4) + (u&1)
-    // so a quad of lanes owns 8 consecutive columns of a row and every store is a full 32-byte sector.
+    // so a quad of lanes owns 8 consecutive columns of a row.
     float sum[EPI_COLS];
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
       bool first = true;
-      for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG_KB) {
+      for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG) {
         mbar_wait(&ctl->seg_full[sb], sb_ph);
         tc_fence_after();
 #pragma unroll
@@ -219,16 +237,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               const int row = mt * BM + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
               if (row < args.M) {
                 const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
-                const float x0 = fmaxf(sp[0] + bb.x, 0.f), x1 = fmaxf(sp[1] + bb.y, 0.f);
+                const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
                 const size_t o = (size_t)row * args.N + col;
-                if (args.split) {
+                if (!args.split) {
+                  *reinterpret_cast<float2*>((float*)args.out0 + o) = make_float2(x0, x1);
+                } else if (F16) {
+                  const float s0 = x0 * out_scale, s1 = x1 * out_scale;
+                  const __half2 hi = __floats2half2_rn(s0, s1);
+                  const float2 hf = __half22float2(hi);
+                  const __half2 lo = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                  *reinterpret_cast<__half2*>((__half*)args.out0 + o) = hi;
+                  *reinterpret_cast<__half2*>((__half*)args.out1 + o) = lo;
+                } else {
                   float2 hi, lo;
                   hi.x = tf32_rna(x0); hi.y = tf32_rna(x1);
                   lo.x = tf32_rna(x0 - hi.x); lo.y = tf32_rna(x1 - hi.y);
-                  *reinterpret_cast<float2*>(args.out0 + o) = hi;
-                  *reinterpret_cast<float2*>(args.out1 + o) = lo;
-                } else {
-                  *reinterpret_cast<float2*>(args.out0 + o) = make_float2(x0, x1);
+                  *reinterpret_cast<float2*>((float*)args.out0 + o) = hi;
+                  *reinterpret_cast<float2*>((float*)args.out1 + o) = lo;
                 }
               }
             }
@@ -240,10 +265,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ===================== patch-gather producers (layer 1) =====================
     reg_dec<96>();
     const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;   // 0..127
-    const int sub = p >> 3, chunk = p & 7;                  // 8 consecutive lanes fill one 128-byte row
+    // CHUNKS consecutive lanes fill one 128-byte row: 8 x 16-byte chunks (tf32) or 16 x 8-byte chunks (fp16)
+    constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / CHUNKS;
+    const int sub = p / CHUNKS, chunk = p % CHUNKS;
     const GatherArgs& g = args.g;
     const int G = g.G, Cc = g.C, pb = (g.k - 1) >> 1;
     const int V = G * G * G;
+    const uint8_t* fv_hi = (const uint8_t*)g.fv_hi; const uint8_t* fv_lo = (const uint8_t*)g.fv_lo;
+    const uint8_t* o4_hi = (const uint8_t*)g.off4_hi; const uint8_t* o4_lo = (const uint8_t*)g.off4_lo;
     int s = 0; uint32_t ph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / num_n_tiles;
@@ -265,19 +294,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int kb = 0; kb < args.num_kb; ++kb) {
         mbar_wait(&ctl->empty[s], ph ^ 1);
         const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-        const uint32_t code = lut[kb * 8 + chunk];
+        const uint32_t code = lut[kb * CHUNKS + chunk];
 #pragma unroll
-        for (int it = 0; it < BM / 16; ++it) {
-          const int r = it * 16 + sub;
-          const uint32_t dst = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+        for (int it = 0; it < BM / ROWS_PER_IT; ++it) {
+          const int r = it * ROWS_PER_IT + sub;
+          const uint32_t dst = F16 ? (uint32_t)(r * 128 + (((chunk >> 1) ^ (r & 7)) << 4) + (chunk & 1) * 8)
+                                   : (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
           const int32_t base = ctl->row_base[r];
-          const float* src_hi = g.fv_hi;
-          const float* src_lo = g.fv_lo;
+          const uint8_t* src_hi = fv_hi;
+          const uint8_t* src_lo = fv_lo;
           uint32_t nbytes = 0;
           if (base >= 0 && code != LUT_ZERO) {
             if (code == LUT_OFFS) {
               const size_t m = (size_t)mt * BM + r;
-              src_hi = g.off4_hi + m * 4; src_lo = g.off4_lo + m * 4; nbytes = 16;
+              src_hi = o4_hi + m * 4 * ELEM; src_lo = o4_lo + m * 4 * ELEM; nbytes = 4 * ELEM;
             } else {
               const uint32_t vox = ctl->row_vox[r];
               const int n0 = (int)(vox & 255) + (int)((code >> 8) & 255) - pb;
@@ -285,12 +315,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               const int n2 = (int)((vox >> 16) & 255) + (int)(code >> 24) - pb;
               if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
                 const size_t el = (size_t)base + (size_t)(((n0 * G + n1) * G + n2) * Cc) + (code & 255);
-                src_hi = g.fv_hi + el; src_lo = g.fv_lo + el; nbytes = 16;
+                src_hi = fv_hi + el * ELEM; src_lo = fv_lo + el * ELEM; nbytes = 4 * ELEM;
               }
             }
           }
-          cp_async16(a_hi + dst, src_hi, nbytes);
-          cp_async16(a_lo + dst, src_lo, nbytes);
+          if (F16) { cp_async8(a_hi + dst, src_hi, nbytes); cp_async8(a_lo + dst, src_lo, nbytes); }
+          else     { cp_async16(a_hi + dst, src_hi, nbytes); cp_async16(a_lo + dst, src_lo, nbytes); }
         }
         // arrive on full[s] when this thread's copies have landed (same protocol as CUTLASS's
         // sm100 cp.async mainloop: cp.async.mbarrier.arrive, then the UMMA consumer waits on the mbarrier)

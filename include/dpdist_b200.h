@@ -44,7 +44,8 @@ extern "C" {
 /* head implementation selector (flags argument of dpd_head_forward) */
 #define DPD_HEAD_AUTO 0
 #define DPD_HEAD_SIMT 1 /* fp32 FFMA GEMMs (sanity path) */
-#define DPD_HEAD_TC 2   /* tcgen05 tensor-core GEMMs, split-precision */
+#define DPD_HEAD_TC 2      /* tcgen05 tensor-core GEMMs, fp16x3 split precision with power-of-two scaling */
+#define DPD_HEAD_TC_TF32 3 /* tcgen05 tensor-core GEMMs, 3xTF32 split precision */
 #define DPD_HEAD_TRAIN 0x10 /* OR-ed into flags: keep the activations for dpd_head_backward (one row chunk only) */
 
 /* stages of dpd_head_backward: ALL, or one layer at a time (4 -> 1) so that the caller can start the
@@ -136,10 +137,11 @@ int dpd_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, s
                   float beta1, float beta2, float eps, int step, void* stream);
 
 /* Test hook for the tensor-core GEMM used by layers 2-3 of the head:
- *   d_out[M,N] = relu(d_a[M,K] . d_w[K,N] + d_bias[N]),  K % 32 == 0, N % 256 == 0,
- * computed with the split-precision tcgen05 kernel.  d_scratch >= 8*(M*K + N*K) bytes.        */
+ *   d_out[M,N] = relu(d_a[M,K] . d_w[K,N] + d_bias[N]),  K % 64 == 0, N % 256 == 0,
+ * computed with the split-precision tcgen05 kernel (f16 != 0: fp16x3, else 3xTF32).
+ * d_scratch >= 8*(M*K + N*K) + 256 bytes.                                                      */
 int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
-                      float* d_out, void* d_scratch, size_t scratch_bytes, void* stream);
+                      float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream);
 
 /* Measurement hooks (used by bench.py; no effect on results).
  * dpd_launch_count : kernels this library has launched in this process (cumulative).

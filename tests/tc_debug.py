@@ -11,7 +11,7 @@ lib = _lib.load()
 dev = "cuda:0"
 
 
-def gemm_case(M, K, N, seed=0):
+def gemm_case(M, K, N, seed=0, f16=1):
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(M, K, generator=g)
     w = torch.randn(K, N, generator=g) / np.sqrt(K)
@@ -21,13 +21,13 @@ def gemm_case(M, K, N, seed=0):
     out = torch.full((M, N), float("nan"), device=dev)
     scratch = torch.empty(8 * (M * K + N * K) + 1024, dtype=torch.uint8, device=dev)
     rc = lib.dpd_debug_tc_gemm(ad.data_ptr(), M, K, wd.data_ptr(), N, bd.data_ptr(), out.data_ptr(), scratch.data_ptr(),
-                               scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                               scratch.numel(), f16, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "dpd_debug_tc_gemm")
     torch.cuda.synchronize()
     o = out.cpu().double()
     err = (o - ref).abs()
     fp32 = torch.relu(ad @ wd + bd).cpu().double()
-    print("gemm M=%d K=%d N=%d: max|err| %.3e (torch fp32 matmul: %.3e) nan=%d ref_max %.3f" % (
+    print(("f16 " if f16 else "tf32") + " gemm M=%d K=%d N=%d: max|err| %.3e (torch fp32 matmul: %.3e) nan=%d ref_max %.3f" % (
         M, K, N, float(err.max()), float((fp32 - ref).abs().max()), int(torch.isnan(o).sum()), float(ref.max())), flush=True)
     if float(err.max()) > 1e-4:
         bad = (err > 1e-4).nonzero()
@@ -40,18 +40,18 @@ def gemm_case(M, K, N, seed=0):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
     if which == "gemm":
-        gemm_case(128, 32, 256)
-        gemm_case(128, 64, 256)
-        gemm_case(256, 128, 512)
-        gemm_case(300, 1024, 1024)
-        gemm_case(128 * 150, 1024, 1024)
+        for f16 in (0, 1):
+            gemm_case(128, 64, 256, f16=f16)
+            gemm_case(256, 128, 512, f16=f16)
+            gemm_case(300, 1024, 1024, f16=f16)
+            gemm_case(128 * 150, 1024, 1024, f16=f16)
     elif which == "model":
         from dpdist_b200 import dpdist_and_aue as MODEL, dpdist_util, synthetic, tf_util
         from oracle import dpdist_oracle as O
         pcA, pcB, _ = synthetic.uniform_batch(7, 4, 64, outside_frac=0.05)
         var = O.unit_scale_variables(7)
         outs = {}
-        for impl in (_lib.HEAD_SIMT, _lib.HEAD_TC):
+        for impl in (_lib.HEAD_SIMT, _lib.HEAD_TC, _lib.HEAD_TC_TF32):
             dpdist_util.HEAD_IMPL = impl
             store = tf_util.VariableStore(device=dev)
             store.load_state_dict(var, strict=False)
@@ -65,4 +65,4 @@ if __name__ == "__main__":
         ref = torch.cat([po["pred_listAB"], po["pred_listBA"]])
         for impl, o in outs.items():
             print("impl %d vs fp64 oracle: max|err| %.3e" % (impl, float((o - ref).abs().max())), flush=True)
-        print("tc vs simt: max|diff| %.3e" % float((outs[1] - outs[2]).abs().max()), flush=True)
+        print("tc f16 vs simt: max|diff| %.3e; tc tf32 vs simt: %.3e" % (float((outs[1] - outs[2]).abs().max()), float((outs[1] - outs[3]).abs().max())), flush=True)
