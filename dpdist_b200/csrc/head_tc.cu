@@ -255,7 +255,7 @@ static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int
   if (g) ka.g = *g;
   const int tiles = ceil_div(M, BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SharedCtl) + (size_t)(K / 4) * sizeof(uint32_t);
+  const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SharedCtl) + 2 * (size_t)(K / 4) * sizeof(uint32_t);
   if (gather) return f16 ? launch_t<true, true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st)
                          : launch_t<true, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
   return f16 ? launch_t<false, true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st)
@@ -268,7 +268,7 @@ static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int
 // interface used by head.cu
 // ---------------------------------------------------------------------------------------------
 bool tc_supported(const dpd_head_config& c) {
-  return c.H % tc::BN == 0 && c.C % 4 == 0 && c.G <= 255 && c.k <= 255 &&
+  return c.H % tc::BN == 0 && c.C % 4 == 0 && c.G <= 255 && c.k <= 8 &&
          (long long)c.n_clouds * c.G * c.G * c.G * c.C < (1ll << 31);
 }
 

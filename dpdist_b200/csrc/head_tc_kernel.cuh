@@ -44,8 +44,6 @@ struct __align__(8) SharedCtl {
   uint64_t full[STAGES], empty[STAGES], seg_full[2], seg_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  int32_t row_base[BM];    // element offset of the row's cloud in fv (-1: row past M)
-  uint32_t row_vox[BM];    // i0 | i1<<8 | i2<<16
 };
 
 template <int N>
@@ -99,19 +97,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
   if (warp == 2) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
   if (GATHER) {
-    // chunk LUT: 4-element chunk q of the virtual row -> (a0,a1,a2,part) | OFFS | ZERO
+    // chunk LUTs: 4-element chunk q of the virtual row -> lut[q] = (a0 | a1<<8 | a2<<16) | OFFS | ZERO and
+    // lutd[q] = element offset of that chunk relative to the row's own voxel record
     const int nchunks = args.num_kb * CHUNKS;
-    const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4;
+    const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4, Gg = args.g.G, pbb = (args.g.k - 1) >> 1;
+    int32_t* lutd = (int32_t*)(lut + nchunks);
     for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
       uint32_t code;
+      int32_t delta = 0;
       if (q < ech) {
         const int e = q * 4, j = e / Cc, part = e - j * Cc;
         const int a2 = j % kk, a1 = (j / kk) % kk, a0 = j / (kk * kk);
-        code = (uint32_t)part | ((uint32_t)a0 << 8) | ((uint32_t)a1 << 16) | ((uint32_t)a2 << 24);
+        code = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16);
+        delta = (((a0 - pbb) * Gg + (a1 - pbb)) * Gg + (a2 - pbb)) * Cc + part;
       } else {
         code = (q == ech) ? LUT_OFFS : LUT_ZERO;
       }
       lut[q] = code;
+      lutd[q] = delta;
     }
   }
   tc_fence_before();
@@ -273,54 +276,65 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int V = G * G * G;
     const uint8_t* fv_hi = (const uint8_t*)g.fv_hi; const uint8_t* fv_lo = (const uint8_t*)g.fv_lo;
     const uint8_t* o4_hi = (const uint8_t*)g.off4_hi; const uint8_t* o4_lo = (const uint8_t*)g.off4_lo;
+    const uint32_t lut_s = smem_u32(lut), lutd_s = lut_s + (uint32_t)(args.num_kb * CHUNKS) * 4u;
+    constexpr int NIT = BM / ROWS_PER_IT;
     int s = 0; uint32_t ph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mt = t / num_n_tiles;
-      // per-tile row table (the previous tile's cp.asyncs have all been issued before the barrier)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      {
-        const int m = mt * BM + p;
-        int32_t base = -1; uint32_t vox = 0;
+      // this thread's rows of the tile, fixed for all K-blocks, in registers:
+      //   rel[it]  element offset of the row's own voxel record in fv (-1: row past M)
+      //   rmsk[it] per-axis validity bits: bit a (+8, +16 for axes 1, 2) set if tap a of the k^3 patch is inside the grid
+      int32_t rel[NIT];
+      uint32_t rmsk[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int m = mt * BM + it * ROWS_PER_IT + sub;
+        rel[it] = -1; rmsk[it] = 0;
         if (m < args.M) {
           const long long cloud = (g.row0 + m) / g.n_query;
-          base = (int32_t)(cloud * V * Cc);
-          const int v = g.idx[m];
-          vox = (uint32_t)(v / (G * G)) | ((uint32_t)((v / G) % G) << 8) | ((uint32_t)(v % G) << 16);
+          const int v = __ldg(g.idx + m);
+          rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
+          const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
+          uint32_t mk = 0;
+          for (int a = 0; a < g.k; ++a) {
+            mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
+            mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
+            mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
+          }
+          rmsk[it] = mk;
         }
-        ctl->row_base[p] = base;
-        ctl->row_vox[p] = vox;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int kb = 0; kb < args.num_kb; ++kb) {
         mbar_wait(&ctl->empty[s], ph ^ 1);
         const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-        const uint32_t code = lut[kb * CHUNKS + chunk];
+        uint32_t code; int32_t delta;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+        const uint32_t dst0 = F16 ? (uint32_t)(sub * 128 + (chunk & 1) * 8) : (uint32_t)(sub * 128);
+        const uint32_t c16 = F16 ? (uint32_t)(chunk >> 1) : (uint32_t)chunk;
+        if (code < LUT_OFFS) {          // a patch chunk (the common case): 3 shifts + 2 ands + 1 add per row
+          const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
 #pragma unroll
-        for (int it = 0; it < BM / ROWS_PER_IT; ++it) {
-          const int r = it * ROWS_PER_IT + sub;
-          const uint32_t dst = F16 ? (uint32_t)(r * 128 + (((chunk >> 1) ^ (r & 7)) << 4) + (chunk & 1) * 8)
-                                   : (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
-          const int32_t base = ctl->row_base[r];
-          const uint8_t* src_hi = fv_hi;
-          const uint8_t* src_lo = fv_lo;
-          uint32_t nbytes = 0;
-          if (base >= 0 && code != LUT_ZERO) {
-            if (code == LUT_OFFS) {
-              const size_t m = (size_t)mt * BM + r;
-              src_hi = o4_hi + m * 4 * ELEM; src_lo = o4_lo + m * 4 * ELEM; nbytes = 4 * ELEM;
-            } else {
-              const uint32_t vox = ctl->row_vox[r];
-              const int n0 = (int)(vox & 255) + (int)((code >> 8) & 255) - pb;
-              const int n1 = (int)((vox >> 8) & 255) + (int)((code >> 16) & 255) - pb;
-              const int n2 = (int)((vox >> 16) & 255) + (int)(code >> 24) - pb;
-              if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
-                const size_t el = (size_t)base + (size_t)(((n0 * G + n1) * G + n2) * Cc) + (code & 255);
-                src_hi = fv_hi + el * ELEM; src_lo = fv_lo + el * ELEM; nbytes = 4 * ELEM;
-              }
-            }
+          for (int it = 0; it < NIT; ++it) {
+            const int r = it * ROWS_PER_IT + sub;
+            const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            const uint32_t ok = (rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u;
+            const size_t el = ok ? (size_t)(rel[it] + delta) : 0;
+            const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+            if (F16) { cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes); cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes); }
+            else     { cp_async16(a_hi + dst, fv_hi + el * ELEM, nbytes); cp_async16(a_lo + dst, fv_lo + el * ELEM, nbytes); }
           }
-          if (F16) { cp_async8(a_hi + dst, src_hi, nbytes); cp_async8(a_lo + dst, src_lo, nbytes); }
-          else     { cp_async16(a_hi + dst, src_hi, nbytes); cp_async16(a_lo + dst, src_lo, nbytes); }
+        } else {                        // the offset chunk and the zero padding (last K-block only)
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int r = it * ROWS_PER_IT + sub;
+            const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            const bool ok = (code == LUT_OFFS) && rel[it] >= 0;
+            const size_t m = ok ? (size_t)mt * BM + r : 0;
+            const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+            if (F16) { cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes); cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes); }
+            else     { cp_async16(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes); cp_async16(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes); }
+          }
         }
         // arrive on full[s] when this thread's copies have landed (same protocol as CUTLASS's
         // sm100 cp.async mainloop: cp.async.mbarrier.arrive, then the UMMA consumer waits on the mbarrier)
