@@ -13,6 +13,8 @@
 #include "head_bwd.cuh"
 #include "head_tc.cuh"
 #include "head_tc_kernel.cuh"
+#include "head_tc_kernel2.cuh"
+#include <stdlib.h>
 
 namespace dpd {
 namespace tc {
@@ -231,10 +233,60 @@ static int launch_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CU
   return 0;
 }
 
+template <bool GATHER>
+static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                     const KernelArgs& ka, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    attr_done = true;
+  }
+  DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : "tc_gemm2_dense_f16", st,
+             tc_gemm2_kernel<GATHER><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
+  DPD_CUDA_CHECK_LAUNCH("tc_gemm2_kernel");
+  return 0;
+}
+
+// 2-CTA (cta_group::2) fp16x3 kernel: 256x256 tiles on CTA pairs.  DPD_TC_2CTA=0 selects the single-CTA kernel.
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DPD_TC_2CTA"); v = e ? (atoi(e) != 0) : 1; }
+  return v != 0;
+}
+
+static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo, int N,
+                   const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
+                   const GatherArgs* g, cudaStream_t st) {
+  DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
+  DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_tmap(&tb_hi, bt_hi, true, N, K, BN / 2))) return rc;
+  if ((rc = make_tmap(&tb_lo, bt_lo, true, N, K, BN / 2))) return rc;
+  if (!gather) {
+    if ((rc = make_tmap(&ta_hi, a_hi, true, M, K, BM))) return rc;
+    if ((rc = make_tmap(&ta_lo, a_lo, true, M, K, BM))) return rc;
+  } else {
+    ta_hi = tb_hi; ta_lo = tb_lo;
+  }
+  KernelArgs ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
+  ka.acc_scale = acc_scale; ka.out_scale = out_scale;
+  if (g) ka.g = *g;
+  const int tiles = ceil_div(M, 2 * BM) * (N / BN);
+  const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + 2 * (size_t)(K / 4) * sizeof(uint32_t);
+  return gather ? launch2_t<true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st)
+                : launch2_t<false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st);
+}
+
 // D[M,N] = relu(acc_scale * A[M,K] * B[N,K]^T + bias), operands pre-split (hi, lo); K % kb == 0, N % 256 == 0
 static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo,
                   int N, const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
                   const GatherArgs* g, cudaStream_t st) {
+  if (f16 && use_2cta())
+    return launch2(gather, a_hi, a_lo, M, K, bt_hi, bt_lo, N, bias, out0, out1, split, acc_scale, out_scale, g, st);
   const int kb = f16 ? 64 : 32;
   DPD_REQUIRE(K % kb == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm: need K %% %d == 0, N %% 256 == 0 (K=%d N=%d)", kb, K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm: K=%d too large", K);

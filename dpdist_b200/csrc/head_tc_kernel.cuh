@@ -64,7 +64,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   constexpr int KB_ELEMS = F16 ? 64 : 32;          // elements per K-block (128 bytes)
   constexpr int ELEM = F16 ? 2 : 4;
   constexpr int CHUNKS = KB_ELEMS / 4;             // 4-element gather chunks per row per K-block
-  constexpr int SEG = F16 ? 2 : 4;                 // K-blocks per promotion segment (K = 128 either way)
+  constexpr int SEG = 4;                            // K-blocks per promotion segment (48 MMAs)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   SharedCtl* ctl = (SharedCtl*)(smem + STAGES * STAGE_BYTES);

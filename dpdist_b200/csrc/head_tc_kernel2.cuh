@@ -1,0 +1,380 @@
+// 2-CTA (cta_group::2) variant of the fp16x3 head GEMM: a cluster of two CTAs on one TPC computes a
+// 256(M) x 256(N) tile.  Each CTA owns 128 rows of A and of the accumulator (its own TMEM) and loads only
+// HALF of the B tile (128 of the 256 weight rows); tcgen05.mma.cta_group::2, issued by the leader CTA,
+// reads both halves.  Per CTA a K-block is 64 KB instead of 96 KB, so three stages fit and the L2->SM
+// traffic per MMA drops by a third - the single-CTA kernel is bound by exactly that traffic
+// (10-11 TB/s of L2->SM reads at 54 % tensor-pipe utilisation, profiles/ncu_r1_summary.md).
+//
+// Synchronisation (leader = cluster rank 0, peer = rank 1):
+//   full[s]      leader only.  Completed by: leader TMA thread (arrive.expect_tx for BOTH CTAs' bytes),
+//                the TMA loads of both CTAs (cta_group::2 loads signal the leader's barrier), and for layer 1
+//                the leader's gather threads (cp.async arrive) + one relay arrive from the peer.
+//   gfull[s]     peer only (layer 1): the peer's gather threads; a relay thread forwards it to full[s].
+//   empty[s], seg_full[b]   both CTAs, completed by tcgen05.commit ... multicast::cluster from the leader.
+//   seg_empty[b] leader only: 8 local + 8 remote epilogue-warp arrivals.
+#pragma once
+#include "head_tc_kernel.cuh"
+
+namespace dpd {
+namespace tc {
+
+constexpr int STAGES2 = 3;
+constexpr int B_HALF = (BN / 2) * ROW_BYTES;                 // 16 KB
+constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF;        // 64 KB
+constexpr uint32_t IDESC_F16_M256 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct __align__(8) SharedCtl2 {
+  uint64_t full[STAGES2], empty[STAGES2], gfull[STAGES2], seg_full[2], seg_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mcast(uint64_t* bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// warps: 0 TMA producer | 1 MMA issuer (leader) | 2 TMEM allocator | 3 gather relay (peer, layer 1) |
+//        4-11 epilogue | 12-15 gather (layer 1)
+template <bool GATHER>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GATHER ? 512 : 384, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                const KernelArgs args) {
+  constexpr int KB_ELEMS = 64, ELEM = 2, CHUNKS = 16, SEG = 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  SharedCtl2* ctl = (SharedCtl2*)(smem + STAGES2 * STAGE2_BYTES);
+  uint32_t* lut = (uint32_t*)(ctl + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_m_tiles = (args.M + 2 * BM - 1) / (2 * BM);
+  const int num_n_tiles = args.N / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 Ah, 1 Al, 2 Bh (half), 3 Bl (half)
+    uint8_t* b = smem + s * STAGE2_BYTES;
+    return which == 0 ? b : which == 1 ? b + A_TILE : which == 2 ? b + 2 * A_TILE : b + 2 * A_TILE + B_HALF;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
+    if (!GATHER) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&ctl->full[s], GATHER ? (2 + NUM_GATHER_THREADS) : 1);
+      mbar_init(&ctl->empty[s], 1);
+      mbar_init(&ctl->gfull[s], NUM_GATHER_THREADS);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ctl->seg_full[a], 1);
+      mbar_init(&ctl->seg_empty[a], 2 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_cg2(&ctl->tmem_base, TMEM_COLS);
+  if (GATHER) {
+    const int nchunks = args.num_kb * CHUNKS;
+    const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4, Gg = args.g.G, pbb = (args.g.k - 1) >> 1;
+    int32_t* lutd = (int32_t*)(lut + nchunks);
+    for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
+      uint32_t code;
+      int32_t delta = 0;
+      if (q < ech) {
+        const int e = q * 4, j = e / Cc, part = e - j * Cc;
+        const int a2 = j % kk, a1 = (j / kk) % kk, a0 = j / (kk * kk);
+        code = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16);
+        delta = (((a0 - pbb) * Gg + (a1 - pbb)) * Gg + (a2 - pbb)) * Cc + part;
+      } else {
+        code = (q == ech) ? LUT_OFFS : LUT_ZERO;
+      }
+      lut[q] = code;
+      lutd[q] = delta;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < 4) {
+    reg_dec<56>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int s = 0; uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+        const int row0 = mt * 2 * BM + (int)rank * BM;
+        const int brow0 = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
+          if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
+          tma_load_2d_cg2(stage_ptr(s, 2), &tm_b_hi, lbar, kb * KB_ELEMS, brow0);
+          tma_load_2d_cg2(stage_ptr(s, 3), &tm_b_lo, lbar, kb * KB_ELEMS, brow0);
+          if (!GATHER) {
+            tma_load_2d_cg2(stage_ptr(s, 0), &tm_a_hi, lbar, kb * KB_ELEMS, row0);
+            tma_load_2d_cg2(stage_ptr(s, 1), &tm_a_lo, lbar, kb * KB_ELEMS, row0);
+          }
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0 && leader) {
+      // ===================== MMA issuer (leader only) =====================
+      int s = 0; uint32_t ph = 0;
+      int sb = 0; uint32_t sb_ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG) {
+          mbar_wait_cluster(&ctl->seg_empty[sb], sb_ph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
+          uint32_t accumulate = 0;
+          const int kb1 = min(kb0 + SEG, args.num_kb);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait_cluster(&ctl->full[s], ph);
+            tc_fence_after();
+            const uint64_t ah = make_desc_sw128(smem_u32(stage_ptr(s, 0)));
+            const uint64_t al = make_desc_sw128(smem_u32(stage_ptr(s, 1)));
+            const uint64_t bh = make_desc_sw128(smem_u32(stage_ptr(s, 2)));
+            const uint64_t bl = make_desc_sw128(smem_u32(stage_ptr(s, 3)));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t o = (uint64_t)(ks * 2);
+              umma_f16_cg2(d_tmem, al + o, bh + o, IDESC_F16_M256, accumulate);
+              umma_f16_cg2(d_tmem, ah + o, bl + o, IDESC_F16_M256, 1);
+              umma_f16_cg2(d_tmem, ah + o, bh + o, IDESC_F16_M256, 1);
+              accumulate = 1;
+            }
+            umma_commit_cg2_mcast(&ctl->empty[s]);
+            if (++s == STAGES2) { s = 0; ph ^= 1; }
+          }
+          umma_commit_cg2_mcast(&ctl->seg_full[sb]);
+          if (++sb == 2) { sb = 0; sb_ph ^= 1; }
+        }
+      }
+    } else if (GATHER && warp == 3 && lane == 0 && !leader) {
+      // ===================== gather relay (peer only): local gfull[s] -> leader's full[s] =====================
+      int s = 0; uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&ctl->gfull[s], ph);
+          fence_proxy_async();
+          mbar_arrive_remote(map_to_rank(smem_u32(&ctl->full[s]), 0));
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 4 + NUM_EPI_WARPS) {
+    // ===================== epilogue (both CTAs): segment promotion + bias/ReLU/split/store =====================
+    if (GATHER) reg_inc<176>(); else reg_inc<216>();
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int half = e >> 2;
+    const float acc_scale = args.acc_scale ? __ldg(args.acc_scale) : 1.0f;
+    const float out_scale = args.out_scale ? __ldg(args.out_scale) : 1.0f;
+    int sb = 0; uint32_t sb_ph = 0;
+    float sum[EPI_COLS];
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+      const int row_base = mt * 2 * BM + (int)rank * BM;
+      bool first = true;
+      for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG) {
+        mbar_wait(&ctl->seg_full[sb], sb_ph);
+        tc_fence_after();
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+          for (int cg = 0; cg < 2; ++cg) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32 + rh * 16) << 16) +
+                                   (uint32_t)(sb * BN + half * EPI_COLS + cg * 64);
+            uint32_t v[32];
+            tmem_ld_16x256b_x8(taddr, v);
+            tmem_ld_wait();
+            float* sp = sum + (rh * 2 + cg) * 32;
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sp[j] = __uint_as_float(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sp[j] += __uint_as_float(v[j]);
+            }
+          }
+        }
+        first = false;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&ctl->seg_empty[sb]);
+          else mbar_arrive_remote(map_to_rank(smem_u32(&ctl->seg_empty[sb]), 0));
+        }
+        if (++sb == 2) { sb = 0; sb_ph ^= 1; }
+      }
+      const int col0 = nt * BN + half * EPI_COLS + 2 * (lane & 3);
+#pragma unroll
+      for (int cg = 0; cg < 2; ++cg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = col0 + cg * 64 + j * 8;
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+            for (int u2 = 0; u2 < 2; ++u2) {
+              const int row = row_base + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
+              if (row < args.M) {
+                const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
+                const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
+                const size_t o = (size_t)row * args.N + col;
+                if (!args.split) {
+                  *reinterpret_cast<float2*>((float*)args.out0 + o) = make_float2(x0, x1);
+                } else {
+                  const float s0 = x0 * out_scale, s1 = x1 * out_scale;
+                  const __half2 hi = __floats2half2_rn(s0, s1);
+                  const float2 hf = __half22float2(hi);
+                  const __half2 lo = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                  *reinterpret_cast<__half2*>((__half*)args.out0 + o) = hi;
+                  *reinterpret_cast<__half2*>((__half*)args.out1 + o) = lo;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (GATHER) {
+    // ===================== patch-gather producers (both CTAs, own 128 rows) =====================
+    reg_dec<96>();
+    const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
+    constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / CHUNKS;
+    constexpr int NIT = BM / ROWS_PER_IT;
+    const int sub = p / CHUNKS, chunk = p % CHUNKS;
+    const GatherArgs& g = args.g;
+    const int G = g.G, Cc = g.C, pb = (g.k - 1) >> 1;
+    const int V = G * G * G;
+    const uint8_t* fv_hi = (const uint8_t*)g.fv_hi; const uint8_t* fv_lo = (const uint8_t*)g.fv_lo;
+    const uint8_t* o4_hi = (const uint8_t*)g.off4_hi; const uint8_t* o4_lo = (const uint8_t*)g.off4_lo;
+    const uint32_t lut_s = smem_u32(lut), lutd_s = lut_s + (uint32_t)(args.num_kb * CHUNKS) * 4u;
+    int s = 0; uint32_t ph = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int mt = t / num_n_tiles;
+      const int row_base = mt * 2 * BM + (int)rank * BM;
+      int32_t rel[NIT];
+      uint32_t rmsk[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int m = row_base + it * ROWS_PER_IT + sub;
+        rel[it] = -1; rmsk[it] = 0;
+        if (m < args.M) {
+          const long long cloud = (g.row0 + m) / g.n_query;
+          const int v = __ldg(g.idx + m);
+          rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
+          const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
+          uint32_t mk = 0;
+          for (int a = 0; a < g.k; ++a) {
+            mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
+            mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
+            mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
+          }
+          rmsk[it] = mk;
+        }
+      }
+      for (int kb = 0; kb < args.num_kb; ++kb) {
+        mbar_wait(&ctl->empty[s], ph ^ 1);
+        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+        uint32_t code; int32_t delta;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+        const uint32_t dst0 = (uint32_t)(sub * 128 + (chunk & 1) * 8);
+        const uint32_t c16 = (uint32_t)(chunk >> 1);
+        if (code < LUT_OFFS) {
+          const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int r = it * ROWS_PER_IT + sub;
+            const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            const uint32_t ok = (rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u;
+            const size_t el = ok ? (size_t)(rel[it] + delta) : 0;
+            const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+            cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
+            cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < NIT; ++it) {
+            const int r = it * ROWS_PER_IT + sub;
+            const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            const bool ok = (code == LUT_OFFS) && rel[it] >= 0;
+            const size_t m = ok ? (size_t)row_base + r : 0;
+            const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+            cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
+            cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
+          }
+        }
+        cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
+        if (++s == STAGES2) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's smem / TMEM must stay alive until the leader's last MMA has retired
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace dpd

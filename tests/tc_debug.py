@@ -65,4 +65,5 @@ if __name__ == "__main__":
         ref = torch.cat([po["pred_listAB"], po["pred_listBA"]])
         for impl, o in outs.items():
             print("impl %d vs fp64 oracle: max|err| %.3e" % (impl, float((o - ref).abs().max())), flush=True)
+        print("tc f16 vs tc tf32: max|diff| %.3e (0 would mean the same code path)" % float((outs[2] - outs[3]).abs().max()), flush=True)
         print("tc f16 vs simt: max|diff| %.3e; tc tf32 vs simt: %.3e" % (float((outs[1] - outs[2]).abs().max()), float((outs[1] - outs[3]).abs().max())), flush=True)
