@@ -63,6 +63,9 @@ SIGNATURES.update({
     "dpd_debug_tc_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                          ctypes.c_int, ctypes.c_void_p]),
+    "dpd_model_forward": (ctypes.c_int, [ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_float, c_float_p,
+                                         ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dpd_launch_count": (ctypes.c_longlong, []),
     "dpd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dpd_profile_read": (ctypes.c_int, [ctypes.POINTER(ProfileEntry), ctypes.c_int, ctypes.c_int]),

@@ -151,6 +151,19 @@ __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p
   }
 }
 
+int fv_forward_dispatch(const FvParams& p, cudaStream_t st, bool* split_done) {
+  if (split_done) *split_done = false;
+  int r = fv_forward_optimized(p, st);
+  if (r <= 0) {
+    if (r == 0 && split_done) *split_done = p.fv_hi != nullptr && !p.flatten;
+    return r;
+  }
+  size_t smem = (size_t)(9 * FV_PCHUNK * p.G + DPD_FV_CHANNELS_FULL * (1 + FV_THREADS / 32)) * sizeof(float);
+  DPD_LAUNCH("fv_generic", st, fv_generic_kernel<<<p.n_clouds, FV_THREADS, smem, st>>>(p));
+  DPD_CUDA_CHECK_LAUNCH("fv_generic_kernel");
+  return 0;
+}
+
 }  // namespace dpd
 
 extern "C" int dpd_fv_forward(const float* d_points, int n_clouds, int n_points, int G,
@@ -164,16 +177,6 @@ extern "C" int dpd_fv_forward(const float* d_points, int n_clouds, int n_points,
   DPD_REQUIRE(aligned16(d_fv), DPD_E_INVALID, "dpd_fv_forward: d_fv must be 16-byte aligned");
   if (n_clouds == 0) return 0;
   FvParams p;
-  p.points = d_points; p.fv = d_fv; p.n_clouds = n_clouds; p.N = n_points; p.G = G; p.V = G * G * G;
-  p.full_fv = full_fv ? 1 : 0; p.flatten = flatten ? 1 : 0;
-  p.C = full_fv ? DPD_FV_CHANNELS_FULL : DPD_FV_CHANNELS_SMALL;
-  p.sigma = sigma;
-  for (int i = 0; i < DPD_MAX_GRID; ++i) p.c[i] = i < G ? h_centers[i] : 0.f;
-  cudaStream_t st = (cudaStream_t)stream;
-  int r = fv_forward_optimized(p, st);
-  if (r <= 0) return r;
-  size_t smem = (size_t)(9 * FV_PCHUNK * G + DPD_FV_CHANNELS_FULL * (1 + FV_THREADS / 32)) * sizeof(float);
-  DPD_LAUNCH("fv_generic", st, fv_generic_kernel<<<n_clouds, FV_THREADS, smem, st>>>(p));
-  DPD_CUDA_CHECK_LAUNCH("fv_generic_kernel");
-  return 0;
+  fill_fv_params(p, d_points, n_clouds, n_points, G, h_centers, sigma, full_fv, flatten, d_fv);
+  return fv_forward_dispatch(p, (cudaStream_t)stream, nullptr);
 }

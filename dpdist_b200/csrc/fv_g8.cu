@@ -12,6 +12,7 @@
 //            Gaussians (fixed-order reductions, deterministic), coalesced float4 copy-out.
 // Algorithmic HBM traffic: 4*(3N + 20*512) bytes per cloud (read points once, write the FV once).
 #include "fv.cuh"
+#include <cuda_fp16.h>
 
 namespace dpd {
 namespace {
@@ -289,6 +290,19 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
         float4 v;
         v.x = s0[g] * n0; v.y = s0[PITCH + g] * n1; v.z = s0[2 * PITCH + g] * n2; v.w = s0[3 * PITCH + g] * n3;
         reinterpret_cast<float4*>(out)[g * 5 + c4] = v;
+        if (p.fv_hi != nullptr) {   // scaled fp16 (hi, lo) copy for the tensor-core head
+          const float sc = p.split_scale;
+          const float a0 = v.x * sc, a1 = v.y * sc, a2 = v.z * sc, a3 = v.w * sc;
+          const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+          const size_t e4 = (size_t)cloud * (V8 * C20 / 4) + g * 5 + c4;
+          uint2 uh, ul;
+          uh.x = *reinterpret_cast<const unsigned*>(&h01); uh.y = *reinterpret_cast<const unsigned*>(&h23);
+          ul.x = *reinterpret_cast<const unsigned*>(&l01); ul.y = *reinterpret_cast<const unsigned*>(&l23);
+          reinterpret_cast<uint2*>(p.fv_hi)[e4] = uh;
+          reinterpret_cast<uint2*>(p.fv_lo)[e4] = ul;
+        }
       }
     }
   }

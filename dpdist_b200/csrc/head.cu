@@ -4,6 +4,7 @@
 #include "head_bwd.cuh"
 #include "head_simt.cuh"
 #include "head_tc.cuh"
+#include "fv.cuh"
 
 namespace dpd {
 
@@ -124,7 +125,7 @@ struct ChunkCtx {
 // forward layers 1..3 (+ voxel assignment) for rows [r0, r0+rows); *h3 = the fp32 layer-3 activations
 int forward_chunk(const dpd_head_config* cfg, const HeadLayout& L, const WsLayout& W, size_t chunk, const float* d_fv,
                   const float* d_query, const float* h_centers, const float* h_lo, const float* h_hi, const char* pk, char* ws,
-                  size_t r0, int rows, int32_t* d_idx, ChunkCtx* cx, const float** h3, cudaStream_t st) {
+                  size_t r0, int rows, int32_t* d_idx, ChunkCtx* cx, const float** h3, cudaStream_t st, float* fused_out) {
   cx->idx = (int32_t*)(ws + W.idx); cx->mask = (float*)(ws + W.mask); cx->off = (float*)(ws + W.off);
   cx->ha = (float*)(ws + W.ha); cx->hb = (float*)(ws + W.hb); cx->hc = L.train ? (float*)(ws + W.hc) : nullptr;
   // rows are independent: assign this chunk's queries as a flat list of `rows` points
@@ -136,7 +137,8 @@ int forward_chunk(const dpd_head_config* cfg, const HeadLayout& L, const WsLayou
   g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
   if (is_tc(L.impl)) {
     return tc_head_layers(*cfg, is_f16(L.impl), g, cx->mask, rows, chunk, pk + L.tc, (const float*)(pk + L.b1),
-                          (const float*)(pk + L.b2), (const float*)(pk + L.b3), cx->ha, cx->hb, cx->hc, ws + W.tc, h3, st);
+                          (const float*)(pk + L.b2), (const float*)(pk + L.b3), cx->ha, cx->hb, cx->hc, ws + W.tc, h3, st,
+                          (const float*)(pk + L.w4), (const float*)(pk + L.b4), fused_out);
   }
   SimtGemmParams p;
   p.g = g; p.M = rows; p.N = cfg->H; p.relu = 1;
@@ -205,6 +207,46 @@ extern "C" int dpd_head_pack_weights(const dpd_head_config* cfg, const float* d_
   return 0;
 }
 
+namespace dpd {
+namespace {
+
+// chunk size (rows, multiple of 128) that fits the caller's workspace; 0 if even 128 rows do not fit
+size_t pick_chunk(const dpd_head_config& c, const HeadLayout& L, size_t M, size_t workspace_bytes) {
+  size_t chunk = round_up<size_t>(M < (size_t)MAX_CHUNK_ROWS ? M : (size_t)MAX_CHUNK_ROWS, 128);
+  while (chunk > 128 && make_ws(c, L, chunk).total > workspace_bytes) chunk = round_up<size_t>(chunk / 2, 128);
+  return make_ws(c, L, chunk).total <= workspace_bytes ? chunk : 0;
+}
+
+// fv_mode: see tc_prepare_fv
+int head_forward_impl(const dpd_head_config* cfg, const HeadLayout& L, size_t chunk, const float* d_fv, const float* d_query,
+                      const float* h_centers, const float* h_lo, const float* h_hi, const void* d_packed, float* d_out,
+                      int32_t* d_idx, void* d_workspace, cudaStream_t st, int fv_mode) {
+  const size_t M = total_rows(*cfg);
+  const WsLayout W = make_ws(*cfg, L, chunk);
+  char* ws = (char*)d_workspace;
+  const char* pk = (const char*)d_packed;
+  int rc;
+  if (is_tc(L.impl)) {
+    rc = tc_prepare_fv(*cfg, is_f16(L.impl), d_fv, pk + L.tc, ws + W.tc, chunk, st, is_f16(L.impl) ? fv_mode : 0);
+    if (rc) return rc;
+  }
+  for (size_t r0 = 0; r0 < M; r0 += chunk) {
+    const int rows = (int)((M - r0 < chunk) ? (M - r0) : chunk);
+    ChunkCtx cx;
+    const float* h3 = nullptr;
+    rc = forward_chunk(cfg, L, W, chunk, d_fv, d_query, h_centers, h_lo, h_hi, pk, ws, r0, rows, d_idx, &cx, &h3, st,
+                       d_out + r0 * 3);
+    if (rc) return rc;
+    if (h3 == nullptr) continue;   // the output layer was fused into layer 3
+    rc = launch_head_out(h3, cfg->H, (const float*)(pk + L.w4), (const float*)(pk + L.b4), cx.mask, d_out + r0 * 3, rows, cfg->H, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace dpd
+
 extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, const float* d_query,
                                 const float* h_centers, const float* h_lo, const float* h_hi,
                                 const void* d_packed, float* d_out, int32_t* d_idx,
@@ -217,32 +259,49 @@ extern "C" int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, c
   const size_t M = total_rows(*cfg);
   if (M == 0) return 0;
   const HeadLayout L = make_layout(*cfg);
-  // largest chunk (multiple of 128 rows) that fits the caller's workspace
-  size_t chunk = round_up<size_t>(M < (size_t)MAX_CHUNK_ROWS ? M : (size_t)MAX_CHUNK_ROWS, 128);
-  while (chunk > 128 && make_ws(*cfg, L, chunk).total > workspace_bytes) chunk = round_up<size_t>(chunk / 2, 128);
-  DPD_REQUIRE(make_ws(*cfg, L, chunk).total <= workspace_bytes, DPD_E_WORKSPACE,
+  const size_t chunk = pick_chunk(*cfg, L, M, workspace_bytes);
+  DPD_REQUIRE(chunk != 0, DPD_E_WORKSPACE,
               "dpd_head_forward: workspace %zu B too small (need >= %zu B)", workspace_bytes, make_ws(*cfg, L, 128).total);
   DPD_REQUIRE(!L.train || chunk >= M, DPD_E_UNSUPPORTED,
               "dpd_head_forward: training mode keeps all activations: %zu rows exceed one chunk (%zu)", M, chunk);
+  return head_forward_impl(cfg, L, chunk, d_fv, d_query, h_centers, h_lo, h_hi, d_packed, d_out, d_idx, d_workspace,
+                           (cudaStream_t)stream, 0);
+}
+
+extern "C" int dpd_model_forward(const dpd_head_config* cfg, const float* d_points, int n_points, float sigma,
+                                 const float* h_fv_centers, const float* d_query, const float* h_centers,
+                                 const float* h_lo, const float* h_hi, const void* d_packed, float* d_fv,
+                                 float* d_out, int32_t* d_idx, void* d_workspace, size_t workspace_bytes,
+                                 void* stream) {
+  using namespace dpd;
+  int rc = check_cfg(cfg, "dpd_model_forward");
+  if (rc) return rc;
+  DPD_REQUIRE(d_points && h_fv_centers && d_query && h_centers && h_lo && h_hi && d_packed && d_fv && d_out && d_workspace,
+              DPD_E_INVALID, "dpd_model_forward: null pointer");
+  DPD_REQUIRE(aligned16(d_fv) && aligned16(d_packed) && aligned16(d_workspace), DPD_E_INVALID, "dpd_model_forward: pointers must be 16-byte aligned");
+  DPD_REQUIRE(n_points > 0 && sigma > 0.f, DPD_E_INVALID, "dpd_model_forward: bad n_points / sigma");
+  DPD_REQUIRE(cfg->C == DPD_FV_CHANNELS_FULL || cfg->C == DPD_FV_CHANNELS_SMALL, DPD_E_INVALID, "dpd_model_forward: C must be 20 or 7");
+  if (cfg->n_clouds == 0) return 0;
+  const size_t M = total_rows(*cfg);
+  const HeadLayout L = make_layout(*cfg);
+  const size_t chunk = pick_chunk(*cfg, L, M, workspace_bytes);
+  DPD_REQUIRE(chunk != 0, DPD_E_WORKSPACE,
+              "dpd_model_forward: workspace %zu B too small (need >= %zu B)", workspace_bytes, make_ws(*cfg, L, 128).total);
+  DPD_REQUIRE(!L.train || chunk >= M, DPD_E_UNSUPPORTED,
+              "dpd_model_forward: training mode keeps all activations: %zu rows exceed one chunk (%zu)", M, chunk);
   const WsLayout W = make_ws(*cfg, L, chunk);
   cudaStream_t st = (cudaStream_t)stream;
-  char* ws = (char*)d_workspace;
-  const char* pk = (const char*)d_packed;
-
-  if (is_tc(L.impl)) {
-    rc = tc_prepare_fv(*cfg, is_f16(L.impl), d_fv, pk + L.tc, ws + W.tc, chunk, st);
-    if (rc) return rc;
+  FvParams p;
+  fill_fv_params(p, d_points, cfg->n_clouds, n_points, cfg->G, h_fv_centers, sigma, cfg->C == DPD_FV_CHANNELS_FULL, 0, d_fv);
+  int fv_mode = 1;   // a 3DmFV tensor is L2-normalised per channel: |fv| <= 1
+  if (is_f16(L.impl)) {
+    tc_fv_split_ptrs(*cfg, true, (char*)d_workspace + W.tc, chunk, &p.fv_hi, &p.fv_lo);
+    p.split_scale = TC_FV_UNIT_SCALE;
   }
-  for (size_t r0 = 0; r0 < M; r0 += chunk) {
-    const int rows = (int)((M - r0 < chunk) ? (M - r0) : chunk);
-    ChunkCtx cx;
-    const float* h3 = nullptr;
-    rc = forward_chunk(cfg, L, W, chunk, d_fv, d_query, h_centers, h_lo, h_hi, pk, ws, r0, rows, d_idx, &cx, &h3, st);
-    if (rc) return rc;
-    rc = launch_head_out(h3, cfg->H, (const float*)(pk + L.w4), (const float*)(pk + L.b4), cx.mask, d_out + r0 * 3, rows, cfg->H, st);
-    if (rc) return rc;
-  }
-  return 0;
+  bool split_done = false;
+  if ((rc = fv_forward_dispatch(p, st, &split_done))) return rc;
+  if (split_done) fv_mode = 2;
+  return head_forward_impl(cfg, L, chunk, d_fv, d_query, h_centers, h_lo, h_hi, d_packed, d_out, d_idx, d_workspace, st, fv_mode);
 }
 
 extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, const void* d_packed,

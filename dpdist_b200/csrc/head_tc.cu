@@ -107,10 +107,10 @@ __global__ void weight_scales_kernel(float* __restrict__ ps) {   // one thread
 // per forward: activation scales from |fv|max and the weight column norms (rigorous bounds, no overflow possible):
 //   |A1| <= in1 = max(|fv|max, 1)            (offsets are < 1: query - centre of its own voxel, masked rows zeroed)
 //   |H1| <= B1 = in1*c1 + max|b1|,  |H2| <= B2 = B1*c2 + max|b2|     (c_l = max column L1 norm of W_l)
-__global__ void activation_scales_kernel(float* __restrict__ ws, const float* __restrict__ ps) {   // one thread
+__global__ void activation_scales_kernel(float* __restrict__ ws, const float* __restrict__ ps, bool unit_bound) {   // one thread
   const unsigned* wb = reinterpret_cast<const unsigned*>(ws);
   const unsigned* pb = reinterpret_cast<const unsigned*>(ps);
-  const float in1 = fmaxf(__uint_as_float(wb[S_FVMAX_BITS]), 1.0f);
+  const float in1 = unit_bound ? 1.0f : fmaxf(__uint_as_float(wb[S_FVMAX_BITS]), 1.0f);
   const float B1 = in1 * __uint_as_float(pb[P_C1_BITS]) + __uint_as_float(pb[P_B1MAX_BITS]);
   const float B2 = B1 * __uint_as_float(pb[P_C2_BITS]) + __uint_as_float(pb[P_B2MAX_BITS]);
   const float a1 = pow2_floor_scale(in1), a2 = pow2_floor_scale(B1), a3 = pow2_floor_scale(B2);
@@ -183,6 +183,23 @@ __global__ void merge_f16_kernel(const __half* __restrict__ hi, const __half* __
   out[i] = (__half2float(hi[i]) + __half2float(lo[i])) / *scale;
 }
 
+// output layer finish for the fused layer-3/4 kernel: sums the per-(N-tile, half) partial dot products in
+// fixed order, adds b4, relu6(x)/3 and the in-cube mask (utils/dpdist_util.py:690-691, 697-698)
+__global__ void head_out_finish_kernel(const float4* __restrict__ part4, int nslots, const float* __restrict__ b4,
+                                       const float* __restrict__ mask, float* __restrict__ out, int M) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < nslots; ++i) {
+    const float4 v = part4[(size_t)row * nslots + i];
+    s0 += v.x; s1 += v.y; s2 += v.z;
+  }
+  const float m = mask[row];
+  out[(size_t)row * 3 + 0] = fminf(fmaxf(s0 + b4[0], 0.f), 6.f) / 3.0f * m;
+  out[(size_t)row * 3 + 1] = fminf(fmaxf(s1 + b4[1], 0.f), 6.f) / 3.0f * m;
+  out[(size_t)row * 3 + 2] = fminf(fmaxf(s2 + b4[2], 0.f), 6.f) / 3.0f * m;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
@@ -241,7 +258,7 @@ static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const C
     DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
     attr_done = true;
   }
-  DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : "tc_gemm2_dense_f16", st,
+  DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : "tc_gemm2_dense_f16"), st,
              tc_gemm2_kernel<GATHER><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
   DPD_CUDA_CHECK_LAUNCH("tc_gemm2_kernel");
   return 0;
@@ -254,9 +271,16 @@ static bool use_2cta() {
   return v != 0;
 }
 
+// DPD_TC_FUSE_L4=0 keeps the separate output-layer kernel (A/B measurements)
+static bool fuse_l4() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DPD_TC_FUSE_L4"); v = e ? (atoi(e) != 0) : 1; }
+  return v != 0;
+}
+
 static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo, int N,
                    const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
-                   const GatherArgs* g, cudaStream_t st) {
+                   const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr) {
   DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -272,7 +296,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   KernelArgs ka;
   memset(&ka, 0, sizeof(ka));
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
-  ka.acc_scale = acc_scale; ka.out_scale = out_scale;
+  ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4;
   if (g) ka.g = *g;
   const int tiles = ceil_div(M, 2 * BM) * (N / BN);
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
@@ -393,8 +417,10 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
   return 0;
 }
 
+// mode 0: foreign fv (measure |fv|max, split)   1: |fv| <= 1 known (3DmFV output), split here
+//      2: |fv| <= 1 and the FV kernel already wrote the (hi, lo) pair at tc_fv_split_ptrs with TC_FV_UNIT_SCALE
 int tc_prepare_fv(const dpd_head_config& c, bool f16, const float* fv, const void* tc_blob, void* tc_ws, size_t ws_rows,
-                  cudaStream_t st) {
+                  cudaStream_t st, int mode) {
   const TcWs w = tc_ws_layout(c, f16, ws_rows);
   char* ws = (char*)tc_ws;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -406,18 +432,29 @@ int tc_prepare_fv(const dpd_head_config& c, bool f16, const float* fv, const voi
   }
   const TcBlob b = tc_blob_layout(c, true);
   float* sc = (float*)(ws + w.scales);
-  DPD_CUDA_CALL(cudaMemsetAsync(sc, 0, tc::S_COUNT * 4, st));
-  DPD_LAUNCH("tc_fv_absmax", st, tc::absmax_kernel<<<num_sms() * 4, 256, 0, st>>>(fv, nfv, (unsigned*)sc + tc::S_FVMAX_BITS));
-  DPD_LAUNCH("tc_scales", st, tc::activation_scales_kernel<<<1, 1, 0, st>>>(sc, (const float*)((const char*)tc_blob + b.scales)));
-  DPD_LAUNCH("tc_split_fv", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
-      fv, nfv, sc + tc::S_A1, (__half*)(ws + w.fvh), (__half*)(ws + w.fvl)));
+  if (mode == 0) {
+    DPD_CUDA_CALL(cudaMemsetAsync(sc, 0, tc::S_COUNT * 4, st));
+    DPD_LAUNCH("tc_fv_absmax", st, tc::absmax_kernel<<<num_sms() * 4, 256, 0, st>>>(fv, nfv, (unsigned*)sc + tc::S_FVMAX_BITS));
+  }
+  // with the unit bound in1 = max(|fv|max, 1) = 1 exactly as the measured path would find for a 3DmFV tensor
+  DPD_LAUNCH("tc_scales", st, tc::activation_scales_kernel<<<1, 1, 0, st>>>(sc, (const float*)((const char*)tc_blob + b.scales), mode != 0));
+  if (mode != 2)
+    DPD_LAUNCH("tc_split_fv", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
+        fv, nfv, sc + tc::S_A1, (__half*)(ws + w.fvh), (__half*)(ws + w.fvl)));
   DPD_CUDA_CHECK_LAUNCH("tc_prepare_fv f16");
   return 0;
 }
 
+void tc_fv_split_ptrs(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, void** hi, void** lo) {
+  const TcWs w = tc_ws_layout(c, f16, ws_rows);
+  *hi = (char*)tc_ws + w.fvh;
+  *lo = (char*)tc_ws + w.fvl;
+}
+
 int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, const float* mask, int rows, size_t ws_rows,
                    const void* tc_blob, const float* b1, const float* b2, const float* b3, float* ha, float* hb,
-                   float* h3_out, void* tc_ws, const float** h3, cudaStream_t st) {
+                   float* h3_out, void* tc_ws, const float** h3, cudaStream_t st, const float* w4, const float* b4,
+                   float* fused_out) {
   const TcBlob b = tc_blob_layout(c, f16);
   const TcWs w = tc_ws_layout(c, f16, ws_rows);
   const char* blob = (const char*)tc_blob;
@@ -445,6 +482,19 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
                          sc + tc::S_ACC1, sc + tc::S_A2, &ga, st))) return rc;
     if ((rc = tc::launch(false, true, ws + w.xh, ws + w.xl, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.yh, ws + w.yl, 1,
                          sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st))) return rc;
+    if (fused_out != nullptr && tc::use_2cta() && tc::fuse_l4() && h3_out == nullptr) {
+      // layer 3 with the output layer fused into its epilogue: H3 never reaches HBM.  `ha` (unused by this path)
+      // holds the [rows, 2*H/256] float4 partials.
+      const int nslots = 2 * (H / tc::BN);
+      float* part4 = ha;
+      if ((rc = tc::launch2(false, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, nullptr, nullptr, 0,
+                            sc + tc::S_ACC3, nullptr, nullptr, st, w4, part4))) return rc;
+      DPD_LAUNCH("head_out_finish", st, tc::head_out_finish_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
+          (const float4*)part4, nslots, b4, mask, fused_out, rows));
+      DPD_CUDA_CHECK_LAUNCH("head_out_finish_kernel");
+      *h3 = nullptr;
+      return 0;
+    }
     if ((rc = tc::launch(false, true, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, out3, nullptr, 0,
                          sc + tc::S_ACC3, nullptr, nullptr, st))) return rc;
   }

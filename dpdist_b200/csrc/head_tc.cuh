@@ -13,14 +13,21 @@ size_t tc_workspace_bytes(const dpd_head_config& c, bool f16, size_t rows);
 int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float* w1p, const float* w2, const float* w3,
                     const float* b1, const float* b2, void* tc_blob, cudaStream_t st);
 
-// once per head call: hi/lo split of the whole FV tensor (and, for fp16, the activation scales) into the tc workspace
+// once per head call: hi/lo split of the whole FV tensor (and, for fp16, the activation scales) into the tc workspace.
+// mode 0: foreign fv (|fv|max is measured on the device)   1: |fv| <= 1 guaranteed (output of the 3DmFV kernels)
+//      2: as 1, and the (hi, lo) pair was already written to tc_fv_split_ptrs() scaled by TC_FV_UNIT_SCALE
+constexpr float TC_FV_UNIT_SCALE = 32768.0f;   // pow2_floor_scale(1): largest power of two s with s*1 <= 32768
 int tc_prepare_fv(const dpd_head_config& c, bool f16, const float* fv, const void* tc_blob, void* tc_ws, size_t ws_rows,
-                  cudaStream_t st);
+                  cudaStream_t st, int mode = 0);
+void tc_fv_split_ptrs(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, void** hi, void** lo);
 
-// runs layers 1..3 for `rows` chunk-local rows; *h3 points at the fp32 [rows,H] layer-3 activations
+// runs layers 1..3 for `rows` chunk-local rows; *h3 points at the fp32 [rows,H] layer-3 activations.
+// If fused_out != nullptr and the configuration allows it (fp16x3, 2-CTA kernel, inference) the output layer is
+// fused into layer 3: fused_out [rows,3] receives the final masked distances and *h3 is set to nullptr.
 int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, const float* mask, int rows, size_t ws_rows,
                    const void* tc_blob, const float* b1, const float* b2, const float* b3, float* ha, float* hb,
-                   float* h3_out, void* tc_ws, const float** h3, cudaStream_t st);
+                   float* h3_out, void* tc_ws, const float** h3, cudaStream_t st, const float* w4 = nullptr,
+                   const float* b4 = nullptr, float* fused_out = nullptr);
 
 // backward support: fp32 layer-1 / layer-2 activations into ha / hb from the (hi, lo) pairs of the forward
 int tc_merge_activations(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, int rows, float* ha, float* hb,

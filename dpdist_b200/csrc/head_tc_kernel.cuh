@@ -37,6 +37,10 @@ struct KernelArgs {
   int split;
   const float* acc_scale;  // device scalar multiplied into the accumulator (1/(sA*sW)); nullptr = 1
   const float* out_scale;  // device scalar applied before the fp16 split of the output; nullptr = 1
+  // fused output layer (2-CTA kernel, layer 3 only): when part4 != nullptr the activations are not stored;
+  // each (N-tile, column half) instead writes its share of H3 . W4 as one float4 per row
+  const float* w4;         // [N,3] fp32 (reference layout of mapper_conv4/weights)
+  float* part4;            // [M, 2*N/BN, 4]
   GatherArgs g;
 };
 

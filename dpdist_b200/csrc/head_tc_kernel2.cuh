@@ -261,6 +261,54 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (++sb == 2) { sb = 0; sb_ph ^= 1; }
       }
       const int col0 = nt * BN + half * EPI_COLS + 2 * (lane & 3);
+      if (!GATHER && args.part4 != nullptr) {
+        // fused output layer: this warp's share of H3[row, :] . W4 for its 64 rows x 128 columns.  A thread holds
+        // 4 rows x 32 columns; the quad (lane & 3) covers 8 consecutive columns per j, so a 2-step butterfly over
+        // the quad completes the 128-column partial sums (fixed order -> deterministic).
+        float pr[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) pr[r][0] = pr[r][1] = pr[r][2] = 0.f;
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = col0 + cg * 64 + j * 8;
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+            const float2 wa = __ldg(reinterpret_cast<const float2*>(args.w4 + (size_t)col * 3));       // w[col][0], w[col][1]
+            const float2 wb = __ldg(reinterpret_cast<const float2*>(args.w4 + (size_t)col * 3 + 2));   // w[col][2], w[col+1][0]
+            const float2 wc = __ldg(reinterpret_cast<const float2*>(args.w4 + (size_t)col * 3 + 4));   // w[col+1][1], w[col+1][2]
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+              for (int u2 = 0; u2 < 2; ++u2) {
+                const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
+                const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
+                float* q3 = pr[rh * 2 + u2];
+                q3[0] = fmaf(x1, wb.y, fmaf(x0, wa.x, q3[0]));
+                q3[1] = fmaf(x1, wc.x, fmaf(x0, wa.y, q3[1]));
+                q3[2] = fmaf(x1, wc.y, fmaf(x0, wb.x, q3[2]));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            pr[r][d] += __shfl_xor_sync(0xffffffffu, pr[r][d], 1);
+            pr[r][d] += __shfl_xor_sync(0xffffffffu, pr[r][d], 2);
+          }
+        // lane (lane & 3) == r stores row r of the thread's four rows
+        const int r = lane & 3;
+        float4 o = make_float4(pr[0][0], pr[0][1], pr[0][2], 0.f);
+        if (r == 1) o = make_float4(pr[1][0], pr[1][1], pr[1][2], 0.f);
+        if (r == 2) o = make_float4(pr[2][0], pr[2][1], pr[2][2], 0.f);
+        if (r == 3) o = make_float4(pr[3][0], pr[3][1], pr[3][2], 0.f);
+        const int row = row_base + q * 32 + (r >> 1) * 16 + (lane >> 2) + 8 * (r & 1);
+        if (row < args.M)
+          reinterpret_cast<float4*>(args.part4)[(size_t)row * (2 * num_n_tiles) + nt * 2 + half] = o;
+        continue;
+      }
 #pragma unroll
       for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll

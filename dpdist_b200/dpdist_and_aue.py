@@ -10,6 +10,9 @@ from . import dpdist_util as dpdist
 from . import tf_util
 
 
+FUSED_INFERENCE = True   # module switch: False forces the staged path (get_3dmfv_tf -> local_z -> DPDist) everywhere
+
+
 def placeholder_inputs(batch_size, num_point, NUM_DIMS=2, device=None):
     """models/dpdist_and_aue.py:23-28.  TF placeholders become zero-filled device buffers with the
     graph names the consumers bind to: input1, input2, labels12, labels21."""
@@ -49,6 +52,18 @@ def get_model(pcA, pcB,
             raise NotImplementedError("k == 0 (global FV + MLP) is not the DPDist hot path")
         pcA_noise = pcA + add_noise                                                       # :45
         B = pcA.shape[0]
+        # Inference (no gradient can be asked of the result): the whole graph below is one library call,
+        # dpd_model_forward.  Same ops, same results; the training path keeps the three reference stages.
+        wants_grad = torch.is_grad_enabled() and (bool(is_training) if isinstance(is_training, (bool, int)) else True)
+        if FUSED_INFERENCE and not wants_grad and NUM_DIMS == 3 and conv_version == 1 and not bn:
+            fv, out, C = dpdist.model_forward(torch.cat([pcA_noise, pcB], 0), torch.cat([pcB, pcA], 0), n_gaussians,
+                                              sigma3dmfv, full_fv, k, localSNmlp, reuse=reuse)
+            out = out.view(2, B, pcA.shape[1], 1, 3)
+            embedding_A, embedding_B = dpdist.LocalPatches(fv[:B], k), dpdist.LocalPatches(fv[B:], k)
+            if materialize_embeddings:
+                embedding_A, embedding_B = embedding_A.materialize(), embedding_B.materialize()
+            return ({'pred_listAB': out[0], 'pred_listBA': out[1]}, {},
+                    {'embedding_A': embedding_A, 'embedding_B': embedding_B})
         # one launch encodes both clouds of every pair: rows [A | B]
         emb = dpdist.get_3dmfv_tf(torch.cat([pcA_noise, pcB], 0), n_gaussians=n_gaussians,
                                   flatten=flatten, full_fv=full_fv,

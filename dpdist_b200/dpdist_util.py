@@ -154,11 +154,24 @@ def local_z_3d(net, is_training, reuse=False, NUM_DIMS=3, k=3, overlap=True):
     grid_len = int(np.round(np.power(num_vox, 1 / 3)))                        # :916
     if grid_len ** NUM_DIMS != num_vox:
         net = net[:, :int(grid_len ** NUM_DIMS), :].contiguous()              # :918
-    X, Y, Z = get_grid_centers(num_vox, NUM_DIMS)
-    C = np.stack([X, Y, Z], -1).astype(np.float32).reshape(-1, NUM_DIMS)      # :927-929
-    Ct = torch.from_numpy(C).to(net.device)
-    Ct._dpd_tables = _assign_tables(C)      # host copy of the interval tables: no D2H sync in DPDist
-    return LocalPatches(net, k), Ct
+    return LocalPatches(net, k), _centers_tensor(num_vox, NUM_DIMS, net.device)
+
+
+_CENTERS = {}
+
+
+def _centers_tensor(num_vox, NUM_DIMS, device):
+    """C [V,3] fp32 on `device` (:925-929), built once per (grid, device); carries the host interval tables so
+    that DPDist needs no D2H copy."""
+    key = (int(num_vox), int(NUM_DIMS), str(device))
+    Ct = _CENTERS.get(key)
+    if Ct is None:
+        X, Y, Z = get_grid_centers(num_vox, NUM_DIMS)
+        C = np.stack([X, Y, Z], -1).astype(np.float32).reshape(-1, NUM_DIMS)      # :927-929
+        Ct = torch.from_numpy(C).to(device)
+        Ct._dpd_tables = _assign_tables(C)
+        _CENTERS[key] = Ct
+    return Ct
 
 
 # --------------------------------------------------------------------------------------
@@ -321,14 +334,7 @@ def _as_fv(embedding, k):
     return emb[:, :, centre * E:(centre + 1) * E].contiguous()
 
 
-def DPDist(point_cloud, point_cloudB, embedding,
-           embeddingB, C, is_training, bn_decay=None, reuse=None,
-           bn=True, wd=0.0,
-           sig=True, Embedding_Size=512,
-           NUM_DIMS=2, mlp=[32, 16, 16], k=3, conv_version=1, output_act='relu'):
-    """utils/dpdist_util.py:412-700 for k > 0, conv_version 1, NUM_DIMS 3, bn off.
-    Returns [pred_AB, pred_BA], each [B,NP,1,3]: queries point_cloudB against A's field and
-    queries point_cloud against B's field (:494-500), masked to the unit cube (:697-698)."""
+def _check_head_options(k, conv_version, NUM_DIMS, bn, output_act, mlp):
     if k <= 0:
         raise NotImplementedError("k == 0 (global embedding) is not the DPDist hot path")
     if conv_version != 1:
@@ -341,6 +347,63 @@ def DPDist(point_cloud, point_cloudB, embedding,
         raise NotImplementedError("output_act must be 'relu' (models/dpdist_and_aue.py:74)")
     if len(mlp) != 3 or not (mlp[0] == mlp[1] == mlp[2]):
         raise NotImplementedError("mlp must be three equal widths (reference default [1024,1024,1024])")
+
+
+def _head_variables(E, NUM_DIMS, mlp, reuse):
+    """The 8 variables of scope 'dpdist_local' (:514-545), created or looked up exactly as DPDist does."""
+    H = mlp[0]
+    with tf_util.variable_scope('dpdist_local', reuse=reuse):                 # :514
+        w1, b1 = tf_util.conv2d_variables(1, H, [1, E + NUM_DIMS], 'mapper_conv1', reuse=reuse)   # :516-521
+        w2, b2 = tf_util.conv2d_variables(H, mlp[1], [1, 1], 'mapper_conv2', reuse=reuse)         # :529-533
+        w3, b3 = tf_util.conv2d_variables(mlp[1], mlp[2], [1, 1], 'mapper_conv3', reuse=reuse)    # :535-539
+        w4, b4 = tf_util.conv2d_variables(mlp[2], NUM_DIMS, [1, 1], 'mapper_conv4', reuse=reuse)  # :541-545
+    return [w1, b1, w2, b2, w3, b3, w4, b4]
+
+
+def model_forward(points, query, n_gaussians, sigma, full_fv, k, mlp, reuse=None, impl=None):
+    """One dpd_model_forward call: 3DmFV of `points` [2B,N,3] (rows [A | B]) and the head evaluated at `query`
+    [2B,NP,3] (rows [pcB | pcA]) -> (fv [2B,V,C], out [2B,NP,3], C [V,3]).  Inference only (no autograd node);
+    results equal get_3dmfv_tf + local_z + DPDist, which get_model uses whenever gradients are needed."""
+    lib = _lib.load()
+    points = _check_cuda(points, "points")
+    query = _check_cuda(query, "query")
+    n_clouds, N, D = points.shape
+    if D != 3 or query.shape[0] != n_clouds or query.shape[2] != 3:
+        raise ValueError("points must be [2B,N,3] and query [2B,NP,3]")
+    _check_head_options(k, 1, 3, False, 'relu', mlp)
+    G, l = _fv_grid(n_gaussians, 3)
+    V, Cc = G ** 3, FV_CHANNELS[bool(full_fv)]
+    Ct = _centers_tensor(V, 3, points.device)
+    _, cl, lo, hi = Ct._dpd_tables
+    weights = _head_variables(Cc * k ** 3, 3, mlp, reuse)
+    ws_list = [_check_cuda(w.detach(), "variable") for w in weights]
+    H = mlp[0]
+    NP = query.shape[1]
+    flags = HEAD_IMPL if impl is None else impl
+    cfg = _lib.HeadConfig(n_clouds, NP, G, Cc, int(k), H, flags)
+    fv = torch.empty((n_clouds, V, Cc), device=points.device, dtype=torch.float32)
+    out = torch.empty((n_clouds, NP, 3), device=points.device, dtype=torch.float32)
+    with torch.cuda.device(points.device):
+        cache = _PACKED.setdefault((points.device, cfg.flags), _PackedHead())
+        blob = cache.get(lib, cfg, list(weights), ws_list)
+        ws = cache.workspace(lib, cfg, points.device)
+        rc = lib.dpd_model_forward(ctypes.byref(cfg), _ptr(points), N, float(sigma), _lib.fptr(l), _ptr(query),
+                                   _lib.fptr(cl), _lib.fptr(lo), _lib.fptr(hi), _ptr(blob), _ptr(fv), _ptr(out), None,
+                                   _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "dpd_model_forward")
+    cache.generation = getattr(cache, "generation", 0) + 1
+    return fv, out, Ct
+
+
+def DPDist(point_cloud, point_cloudB, embedding,
+           embeddingB, C, is_training, bn_decay=None, reuse=None,
+           bn=True, wd=0.0,
+           sig=True, Embedding_Size=512,
+           NUM_DIMS=2, mlp=[32, 16, 16], k=3, conv_version=1, output_act='relu'):
+    """utils/dpdist_util.py:412-700 for k > 0, conv_version 1, NUM_DIMS 3, bn off.
+    Returns [pred_AB, pred_BA], each [B,NP,1,3]: queries point_cloudB against A's field and
+    queries point_cloud against B's field (:494-500), masked to the unit cube (:697-698)."""
+    _check_head_options(k, conv_version, NUM_DIMS, bn, output_act, mlp)
     pcA = _check_cuda(point_cloud, "point_cloud")
     pcB = _check_cuda(point_cloudB, "point_cloudB")
     fvA, fvB = _as_fv(embedding, k), _as_fv(embeddingB, k)
@@ -350,18 +413,14 @@ def DPDist(point_cloud, point_cloudB, embedding,
     B, NP, _ = pcA.shape
     E = fvA.shape[2] * k ** 3
     H = mlp[0]
-    with tf_util.variable_scope('dpdist_local', reuse=reuse):                 # :514
-        w1, b1 = tf_util.conv2d_variables(1, H, [1, E + NUM_DIMS], 'mapper_conv1', reuse=reuse)   # :516-521
-        w2, b2 = tf_util.conv2d_variables(H, mlp[1], [1, 1], 'mapper_conv2', reuse=reuse)         # :529-533
-        w3, b3 = tf_util.conv2d_variables(mlp[1], mlp[2], [1, 1], 'mapper_conv3', reuse=reuse)    # :535-539
-        w4, b4 = tf_util.conv2d_variables(mlp[2], NUM_DIMS, [1, 1], 'mapper_conv4', reuse=reuse)  # :541-545
+    weights = _head_variables(E, NUM_DIMS, mlp, reuse)
     fv_all = torch.cat([fvA, fvB], 0)             # rows [A-field | B-field]  (:511)
     query = torch.cat([pcB, pcA], 0)              # A's field is queried at B's points and vice versa (:494,498)
     # is_training only switches batch norm in the reference (off here); a literal False/0 additionally
     # selects the inference path (no activations kept for a backward pass)
     grad_ok = torch.is_grad_enabled() and (bool(is_training) if isinstance(is_training, (bool, int)) else True)
     with torch.set_grad_enabled(grad_ok):
-        out = head_forward(fv_all, query, C, [w1, b1, w2, b2, w3, b3, w4, b4], k)
+        out = head_forward(fv_all, query, C, weights, k)
     out = out.view(2, B, NP, 1, 3)
     return [out[0], out[1]]                                                    # :695
 

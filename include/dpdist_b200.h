@@ -119,6 +119,22 @@ int dpd_head_forward(const dpd_head_config* cfg, const float* d_fv, const float*
                      const void* d_packed, float* d_out, int32_t* d_idx, void* d_workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Whole forward of the hot path in one call: replaces the body of get_model for k > 0, conv_version 1
+ * (models/dpdist_and_aue.py:31-86): get_3dmfv_tf of every cloud (:56-61) -> local_z (:64-65, never
+ * materialised) -> DPDist (:69-75).  Same results as dpd_fv_forward followed by dpd_head_forward; the
+ * library additionally lets the 3DmFV kernel emit the tensor-core operand copy of the FV tensor and uses
+ * the bound |fv| <= 1 (per-channel L2 normalisation, utils/dpdist_util.py:124-126) instead of measuring it.
+ *   d_points [n_clouds, n_points, 3]  clouds to encode, rows [A-clouds (+noise, :45) | B-clouds]
+ *   d_query  [n_clouds, n_query, 3]   rows [pcB | pcA]: A's field is queried at B's points (:494-500)
+ *   d_fv     [n_clouds, G^3, C]  out  the 3DmFV tensor (what embedding_set is built from), C = cfg->C in {20, 7}
+ *   d_out    [n_clouds, n_query, 3] out  rows [pred_AB | pred_BA]
+ *   h_fv_centers[G]: Gaussian axis centres (:42); h_centers / h_lo / h_hi: voxel tables (see top).     */
+int dpd_model_forward(const dpd_head_config* cfg, const float* d_points, int n_points, float sigma,
+                      const float* h_fv_centers, const float* d_query, const float* h_centers,
+                      const float* h_lo, const float* h_hi, const void* d_packed, float* d_fv,
+                      float* d_out, int32_t* d_idx, void* d_workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* Gradients of the head's 8 variables: replaces what optimizer.compute_gradients(total_loss_samples,
  * vars in scope 'pc_compare') builds in the reference trainer (train_multi_gpu_pc_compare_dist.py:274-277)
  * over utils/dpdist_util.py:494-544,688-698.  Must follow a dpd_head_forward with the SAME cfg (flags

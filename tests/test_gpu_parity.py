@@ -121,8 +121,9 @@ def test_local_patches_bit_exact(G, k, C):
 
 
 # ------------------------------------------------------------------ head + full model
-def _run_model(pcA, pcB, var, impl, k=5, V=512, sigma=0.125, H=1024):
+def _run_model(pcA, pcB, var, impl, k=5, V=512, sigma=0.125, H=1024, fused=True):
     dpdist_util.HEAD_IMPL = impl
+    MODEL.FUSED_INFERENCE = fused
     try:
         with tf_util.use_store(_store_from(var)):
             p, _, emb = MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), False, bn=0,
@@ -131,6 +132,7 @@ def _run_model(pcA, pcB, var, impl, k=5, V=512, sigma=0.125, H=1024):
         return p, emb
     finally:
         dpdist_util.HEAD_IMPL = _lib.HEAD_AUTO
+        MODEL.FUSED_INFERENCE = True
 
 
 IMPLS = [_lib.HEAD_SIMT, _lib.HEAD_AUTO]
@@ -190,6 +192,21 @@ def test_model_other_grids_simt(G, k, H):
         po, _, _ = O.get_model(torch.tensor(pcA), torch.tensor(pcB), var, Embedding_Size=G ** 3, k=k, sigma3dmfv=1.0 / G)
     assert_out_close(p["pred_listAB"], po["pred_listAB"])
     assert_out_close(p["pred_listBA"], po["pred_listBA"])
+
+
+@pytest.mark.parametrize("impl,G,k,H", [(_lib.HEAD_AUTO, 8, 5, 1024), (_lib.HEAD_SIMT, 8, 5, 1024), (_lib.HEAD_AUTO, 5, 3, 256),
+                                        (_lib.HEAD_TC_TF32, 8, 5, 1024)])
+def test_one_call_forward_equals_the_three_stages(impl, G, k, H):
+    """dpd_model_forward (3DmFV emitting the tensor-core operand copy, |fv| <= 1 bound) is bit-identical to
+    dpd_fv_forward -> dpd_head_forward (measured |fv|max, separate split)."""
+    pcA, pcB, _ = synthetic.uniform_batch(11 + G, 6, 64, outside_frac=0.05)
+    var = O.init_variables(k=k, mlp=(H, H, H), seed=3, bias_std=0.05, weight_gain=(600.0, 2.0, 2.0, 1.0), out_bias=1.0)
+    kw = dict(k=k, V=G ** 3, sigma=1.0 / G, H=H)
+    pf, ef = _run_model(pcA, pcB, var, impl, fused=True, **kw)
+    ps, es = _run_model(pcA, pcB, var, impl, fused=False, **kw)
+    assert torch.equal(ef["embedding_A"].fv, es["embedding_A"].fv) and torch.equal(ef["embedding_B"].fv, es["embedding_B"].fv)
+    assert torch.equal(pf["pred_listAB"], ps["pred_listAB"]) and torch.equal(pf["pred_listBA"], ps["pred_listBA"])
+    assert float(pf["pred_listAB"].abs().max()) > 0
 
 
 def test_dense_patch_tensor_is_accepted_like_the_reference():

@@ -101,4 +101,7 @@ def test_inference_path_unchanged_by_training_mode():
         p_train, _, _ = MODEL.get_model(a, b, True, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
         p_eval, _, _ = MODEL.get_model(a, b, False, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
     assert p_train["pred_listAB"].requires_grad and not p_eval["pred_listAB"].requires_grad
-    assert torch.equal(p_train["pred_listAB"].detach(), p_eval["pred_listAB"])
+    # identical layers 1-3; the inference path fuses the output layer into layer 3 (H3 . W4 summed per 128-column
+    # slice), training keeps H3 and uses the separate output kernel: fp32 re-association of a 1024-term dot product
+    d = (p_train["pred_listAB"].detach() - p_eval["pred_listAB"]).abs()
+    assert float(d.max()) <= 4e-6, float(d.max())
