@@ -25,6 +25,7 @@ class HeadConfig(ctypes.Structure):
 
 HEAD_AUTO, HEAD_SIMT, HEAD_TC, HEAD_TC_TF32 = 0, 1, 2, 3
 HEAD_TRAIN = 0x10
+HEAD_INPUT_GRAD = 0x20
 BWD_ALL, BWD_L4, BWD_L3, BWD_L2, BWD_L1 = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); must list every symbol include/dpdist_b200.h declares
@@ -66,6 +67,10 @@ SIGNATURES.update({
     "dpd_model_forward": (ctypes.c_int, [ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_float, c_float_p,
                                          ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "dpd_fv_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_float,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "dpd_head_backward_inputs": (ctypes.c_int, [ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dpd_launch_count": (ctypes.c_longlong, []),
     "dpd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dpd_profile_read": (ctypes.c_int, [ctypes.POINTER(ProfileEntry), ctypes.c_int, ctypes.c_int]),

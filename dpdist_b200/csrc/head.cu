@@ -19,13 +19,15 @@ struct HeadLayout {
   bool train;
   int E, K1, Kp1;
   // packed blob (byte offsets)
-  size_t w1p, w2, w3, w4, b1, b2, b3, b4, w2t, w3t, tc, total;
+  bool input_grad;
+  size_t w1p, w2, w3, w4, b1, b2, b3, b4, w2t, w3t, w1pt, tc, total;
 };
 
 size_t up(size_t x) { return round_up<size_t>(x, ALIGN); }
 
 int impl_bits(const dpd_head_config& c) { return c.flags & 0xF; }
 bool train_bit(const dpd_head_config& c) { return (c.flags & DPD_HEAD_TRAIN) != 0; }
+bool input_grad_bit(const dpd_head_config& c) { return (c.flags & DPD_HEAD_INPUT_GRAD) != 0; }
 
 int resolve_impl(const dpd_head_config& c) {
   if (impl_bits(c) == DPD_HEAD_SIMT) return DPD_HEAD_SIMT;
@@ -42,7 +44,8 @@ int check_cfg(const dpd_head_config* c, const char* who) {
   DPD_REQUIRE(c->G >= 2 && c->G <= DPD_MAX_GRID, DPD_E_UNSUPPORTED, "%s: G=%d outside [2,%d]", who, c->G, DPD_MAX_GRID);
   DPD_REQUIRE(c->C > 0 && c->k > 0 && c->k <= 2 * DPD_MAX_GRID, DPD_E_INVALID, "%s: bad C/k", who);
   DPD_REQUIRE(c->H > 0 && c->H % 16 == 0, DPD_E_UNSUPPORTED, "%s: H=%d must be a positive multiple of 16", who, c->H);
-  DPD_REQUIRE((c->flags & ~(0xF | DPD_HEAD_TRAIN)) == 0 && impl_bits(*c) <= DPD_HEAD_TC_TF32, DPD_E_INVALID, "%s: bad flags", who);
+  DPD_REQUIRE((c->flags & ~(0xF | DPD_HEAD_TRAIN | DPD_HEAD_INPUT_GRAD)) == 0 && impl_bits(*c) <= DPD_HEAD_TC_TF32, DPD_E_INVALID, "%s: bad flags", who);
+  DPD_REQUIRE(!input_grad_bit(*c) || train_bit(*c), DPD_E_INVALID, "%s: DPD_HEAD_INPUT_GRAD needs DPD_HEAD_TRAIN", who);
   if (impl_bits(*c) == DPD_HEAD_TC || impl_bits(*c) == DPD_HEAD_TC_TF32)
     DPD_REQUIRE(tc_supported(*c), DPD_E_UNSUPPORTED, "%s: tensor-core head needs H %% 256 == 0 and C %% 4 == 0", who);
   if (train_bit(*c))
@@ -54,6 +57,7 @@ HeadLayout make_layout(const dpd_head_config& c) {
   HeadLayout L;
   L.impl = resolve_impl(c);
   L.train = train_bit(c);
+  L.input_grad = input_grad_bit(c);
   L.E = c.k * c.k * c.k * c.C;
   L.K1 = L.E + 3;
   L.Kp1 = round_up(L.K1, 32);
@@ -69,6 +73,7 @@ HeadLayout make_layout(const dpd_head_config& c) {
   L.b4 = o;  o += up(16);
   L.w2t = o; if (L.train) o += up(H * H * 4);
   L.w3t = o; if (L.train) o += up(H * H * 4);
+  L.w1pt = o; if (L.input_grad) o += up((size_t)L.Kp1 * H * 4);
   L.tc = o;
   if (is_tc(L.impl)) o += up(tc_packed_bytes(c, is_f16(L.impl)));
   L.total = o;
@@ -76,8 +81,22 @@ HeadLayout make_layout(const dpd_head_config& c) {
 }
 
 struct WsLayout {
-  size_t idx, mask, off, ha, hb, hc, g0, g1, active, part, part_bias, part4, tc, total;
+  size_t idx, mask, off, ha, hb, hc, g0, g1, active, part, part_bias, part4, dx1, tc, total;
 };
+
+// Input gradients run over groups of whole clouds whose first row is a multiple of 128 (the granularity of the
+// `active` flags): clouds per group = a multiple of 128 / gcd(128, n_query), about 16384 rows.
+int input_grad_group_clouds(const dpd_head_config& c) {
+  int g = 128, q = c.n_query;
+  while (q) { const int t = g % q; g = q; q = t; }        // g = gcd(128, n_query)
+  const int base = 128 / g;
+  const long long rows_base = (long long)base * c.n_query;
+  long long mult = 16384 / rows_base;
+  if (mult < 1) mult = 1;
+  long long cpg = base * mult;
+  const long long need = round_up<long long>(c.n_clouds > 0 ? c.n_clouds : 1, base);
+  return (int)(cpg < need ? cpg : need);
+}
 
 WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
   WsLayout W;
@@ -88,7 +107,7 @@ WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
   W.off = o;  o += up(rows * 12);
   W.ha = o;   o += up(rows * H * 4);
   W.hb = o;   o += up(rows * H * 4);
-  W.hc = W.g0 = W.g1 = W.active = W.part = W.part_bias = W.part4 = o;
+  W.hc = W.g0 = W.g1 = W.active = W.part = W.part_bias = W.part4 = W.dx1 = o;
   if (L.train) {
     W.hc = o; o += up(rows * H * 4);    // layer-3 activations (kept for the backward pass)
     W.g0 = o; o += up(rows * H * 4);    // upstream gradients, ping-pong
@@ -97,6 +116,8 @@ WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
     W.part = o; o += up((size_t)BWD_SLICES * L.Kp1 * H * 4);
     W.part_bias = o; o += up((size_t)BWD_SLICES * H * 4);
     W.part4 = o; o += up((size_t)OUT_BWD_CTAS * (H * 3 + 3) * 4);
+    W.dx1 = o;
+    if (L.input_grad) o += up((size_t)input_grad_group_clouds(c) * c.n_query * L.Kp1 * 4);
   }
   W.tc = o;
   if (is_tc(L.impl)) o += up(tc_workspace_bytes(c, is_f16(L.impl), rows));
@@ -199,6 +220,7 @@ extern "C" int dpd_head_pack_weights(const dpd_head_config* cfg, const float* d_
     if ((rc = launch_transpose(d_w2, cfg->H, cfg->H, (float*)(base + L.w2t), st))) return rc;
     if ((rc = launch_transpose(d_w3, cfg->H, cfg->H, (float*)(base + L.w3t), st))) return rc;
   }
+  if (L.input_grad && (rc = launch_transpose((const float*)(base + L.w1p), L.Kp1, cfg->H, (float*)(base + L.w1pt), st))) return rc;
   if (is_tc(L.impl)) {
     rc = tc_pack_weights(*cfg, is_f16(L.impl), L.Kp1, (const float*)(base + L.w1p), (const float*)(base + L.w2),
                          (const float*)(base + L.w3), (const float*)(base + L.b1), (const float*)(base + L.b2), base + L.tc, st);
@@ -341,7 +363,7 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
     if ((rc = launch_row_active(d_grad_out, rows, active, st))) return rc;
     if ((rc = launch_out_backward(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
                                   d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st))) return rc;
-    if ((rc = launch_reduce_out_partials(part4, OUT_BWD_CTAS, H, d_gw4, d_gb4, st))) return rc;
+    if (d_gw4 && (rc = launch_reduce_out_partials(part4, OUT_BWD_CTAS, H, d_gw4, d_gb4, st))) return rc;
   }
   TnParams tp;
   tp.M = rows; tp.N = H; tp.active = active; tp.partial = part; tp.partial_bias = part_bias; tp.lda = H;
@@ -349,25 +371,66 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
   gp.M = rows; gp.N = H; gp.Kp = H; gp.relu = 0; gp.bias = nullptr; gp.lda = H; gp.active = active;
   if (all || stage == DPD_BWD_L3) {
     tp.A = H2; tp.B = g0; tp.Kp = H;
-    if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
-    if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw3, d_gb3, st))) return rc;
+    if (d_gw3) {
+      if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
+      if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw3, d_gb3, st))) return rc;
+    }
     gp.A = g0; gp.B = (const float*)(pk + L.w3t); gp.gate = H2; gp.Cout = g1;     // dZ2 = (dZ3 . W3^T) * (H2 > 0)
     if ((rc = launch_simt_gemm(gp, false, st))) return rc;
   }
   if (all || stage == DPD_BWD_L2) {
     tp.A = H1; tp.B = g1; tp.Kp = H;
-    if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
-    if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw2, d_gb2, st))) return rc;
+    if (d_gw2) {
+      if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
+      if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw2, d_gb2, st))) return rc;
+    }
     gp.A = g1; gp.B = (const float*)(pk + L.w2t); gp.gate = H1; gp.Cout = g0;     // dZ1 = (dZ2 . W2^T) * (H1 > 0)
     if ((rc = launch_simt_gemm(gp, false, st))) return rc;
   }
-  if (all || stage == DPD_BWD_L1) {
+  if ((all || stage == DPD_BWD_L1) && d_gw1) {
     GatherDesc g;
     g.fv = d_fv; g.idx = (const int32_t*)(ws + W.idx); g.offset = (const float*)(ws + W.off); g.row0 = 0;
     g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
     tp.A = nullptr; tp.B = g0; tp.Kp = L.Kp1; tp.g = g;
     if ((rc = launch_simt_gemm_tn(tp, true, st))) return rc;
     if ((rc = launch_reduce_partials(part, part_bias, L.Kp1, L.K1, H, L.E, 1, d_gw1, d_gb1, st))) return rc;
+  }
+  return 0;
+}
+
+extern "C" int dpd_head_backward_inputs(const dpd_head_config* cfg, const void* d_packed, float* d_grad_fv,
+                                        float* d_grad_query, void* d_workspace, size_t workspace_bytes, void* stream) {
+  using namespace dpd;
+  int rc = check_cfg(cfg, "dpd_head_backward_inputs");
+  if (rc) return rc;
+  DPD_REQUIRE(train_bit(*cfg) && input_grad_bit(*cfg), DPD_E_INVALID,
+              "dpd_head_backward_inputs: cfg.flags must carry DPD_HEAD_TRAIN | DPD_HEAD_INPUT_GRAD (pack, forward and backward alike)");
+  DPD_REQUIRE(d_packed && d_grad_fv && d_grad_query && d_workspace, DPD_E_INVALID, "dpd_head_backward_inputs: null pointer");
+  DPD_REQUIRE(aligned16(d_grad_fv), DPD_E_INVALID, "dpd_head_backward_inputs: d_grad_fv must be 16-byte aligned");
+  const size_t M = total_rows(*cfg);
+  if (M == 0) return 0;
+  const HeadLayout L = make_layout(*cfg);
+  const size_t chunk = round_up<size_t>(M, 128);
+  DPD_REQUIRE(M <= (size_t)MAX_CHUNK_ROWS && make_ws(*cfg, L, chunk).total <= workspace_bytes, DPD_E_WORKSPACE,
+              "dpd_head_backward_inputs: needs the single-chunk training workspace (%zu rows)", M);
+  const WsLayout W = make_ws(*cfg, L, chunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)d_workspace;
+  const char* pk = (const char*)d_packed;
+  const int H = cfg->H;
+  const float* dz1 = (const float*)(ws + W.g0);       // left there by stage DPD_BWD_L2
+  const int* active = (const int*)(ws + W.active);
+  float* dx1 = (float*)(ws + W.dx1);
+  const int cpg = input_grad_group_clouds(*cfg);
+  for (int c0 = 0; c0 < cfg->n_clouds; c0 += cpg) {
+    const int nc = cfg->n_clouds - c0 < cpg ? cfg->n_clouds - c0 : cpg;
+    const size_t r0 = (size_t)c0 * cfg->n_query;       // multiple of 128 by construction
+    SimtGemmParams gp;
+    gp.A = dz1 + r0 * H; gp.lda = H; gp.B = (const float*)(pk + L.w1pt); gp.bias = nullptr; gp.Cout = dx1;
+    gp.M = nc * cfg->n_query; gp.N = L.Kp1; gp.Kp = H; gp.relu = 0; gp.gate = nullptr; gp.active = active + r0 / 128;
+    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    if ((rc = launch_patch_scatter(dx1, L.Kp1, (const int32_t*)(ws + W.idx), active, c0, nc, cfg->n_query, cfg->G, cfg->C, cfg->k,
+                                   d_grad_fv, d_grad_query, st))) return rc;
   }
   return 0;
 }

@@ -255,7 +255,62 @@ __global__ void transpose_kernel(const float* __restrict__ w, int K, int N, floa
   }
 }
 
+// one CTA per cloud; see launch_patch_scatter
+template <bool VEC>
+__global__ void __launch_bounds__(256) patch_scatter_kernel(const float* __restrict__ dx1, int ldx, const int32_t* __restrict__ idx,
+                                                            const int* __restrict__ active, int cloud0, int n_query, int G, int C,
+                                                            int k, float* __restrict__ grad_fv, float* __restrict__ grad_query) {
+  extern __shared__ int qinfo[];   // [n_query] i0 | i1 << 8 | i2 << 16 | active << 24
+  const int cloud = cloud0 + blockIdx.x;
+  const long long row0 = (long long)cloud * n_query;
+  const float* dx = dx1 + (size_t)blockIdx.x * n_query * ldx;
+  const int V = G * G * G, E = k * k * k * C, pb = (k - 1) >> 1;
+  for (int q = threadIdx.x; q < n_query; q += blockDim.x) {
+    const long long r = row0 + q;
+    const int v = idx[r];
+    const int on = active[r >> 7] ? 1 : 0;
+    qinfo[q] = (v / (G * G)) | (((v / G) % G) << 8) | ((v % G) << 16) | (on << 24);
+    float* gq = grad_query + r * 3;
+    const float* src = dx + (size_t)q * ldx + E;
+    gq[0] = on ? src[0] : 0.f; gq[1] = on ? src[1] : 0.f; gq[2] = on ? src[2] : 0.f;
+  }
+  __syncthreads();
+  const int CW = VEC ? C / 4 : C;      // items per voxel
+  float* out = grad_fv + (size_t)cloud * V * C;
+  for (int item = threadIdx.x; item < V * CW; item += blockDim.x) {
+    const int v = item / CW, cw = item - v * CW;
+    const int j0 = v / (G * G) + pb, j1 = (v / G) % G + pb, j2 = v % G + pb;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < n_query; ++q) {
+      const int qi = qinfo[q];
+      const int a0 = j0 - (qi & 0xff), a1 = j1 - ((qi >> 8) & 0xff), a2 = j2 - ((qi >> 16) & 0xff);
+      if ((qi >> 24) == 0 || (unsigned)a0 >= (unsigned)k || (unsigned)a1 >= (unsigned)k || (unsigned)a2 >= (unsigned)k) continue;
+      const float* src = dx + (size_t)q * ldx + ((a0 * k + a1) * k + a2) * C;
+      if (VEC) {
+        const float4 x = ld4(src + cw * 4);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      } else {
+        acc.x += src[cw];
+      }
+    }
+    if (VEC) reinterpret_cast<float4*>(out)[item] = acc;
+    else out[item] = acc.x;
+  }
+}
+
 }  // namespace
+
+int launch_patch_scatter(const float* dx1, int ldx, const int32_t* idx, const int* active, int cloud0, int n_clouds, int n_query,
+                         int G, int C, int k, float* grad_fv, float* grad_query, cudaStream_t st) {
+  DPD_REQUIRE(n_query <= 8192, DPD_E_UNSUPPORTED, "input gradients: at most 8192 queries per cloud (got %d)", n_query);
+  const size_t smem = (size_t)n_query * sizeof(int);
+  if ((C & 3) == 0 && (ldx & 3) == 0)
+    DPD_LAUNCH("bwd_patch_scatter", st, patch_scatter_kernel<true><<<n_clouds, 256, smem, st>>>(dx1, ldx, idx, active, cloud0, n_query, G, C, k, grad_fv, grad_query));
+  else
+    DPD_LAUNCH("bwd_patch_scatter", st, patch_scatter_kernel<false><<<n_clouds, 256, smem, st>>>(dx1, ldx, idx, active, cloud0, n_query, G, C, k, grad_fv, grad_query));
+  DPD_CUDA_CHECK_LAUNCH("patch_scatter_kernel");
+  return 0;
+}
 
 int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st) {
   DPD_LAUNCH("bwd_row_active", st, row_active_kernel<<<ceil_div(M, 128), 128, 0, st>>>(grad_out, M, active));

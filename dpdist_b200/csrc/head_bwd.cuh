@@ -36,6 +36,14 @@ int launch_reduce_partials(const float* partial, const float* partial_bias, int 
                            float* gw, float* gb, cudaStream_t st);
 
 int launch_add_inplace(float* a, const float* b, size_t n, cudaStream_t st);
+
+// Input gradients of layer 1 for the clouds [cloud0, cloud0 + n_clouds): dx1 [rows, ldx] = dZ1 . W1p^T holds, per query row,
+// the gradient of its virtual operand row [patch (E) | offset (3) | pad].  grad_fv[cloud, v, :] gathers the patch
+// parts of all queries of the cloud whose k^3 neighbourhood contains v (fixed query order: deterministic, no
+// atomics); grad_query[row, :] = the offset part (offset = query - centre, utils/dpdist_util.py:491).
+// idx / active are indexed by global row; dx1 row 0 is global row cloud0 * n_query.
+int launch_patch_scatter(const float* dx1, int ldx, const int32_t* idx, const int* active, int cloud0, int n_clouds, int n_query,
+                         int G, int C, int k, float* grad_fv, float* grad_query, cudaStream_t st);
 int launch_transpose(const float* w, int K, int N, float* wt, cudaStream_t st);
 
 }  // namespace dpd

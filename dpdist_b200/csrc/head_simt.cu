@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NT) simt_gemm_kernel(const SimtGemmParams p) {
         v.x = gg.x > 0.f ? acc[i][h * 4 + 0] : 0.f; v.y = gg.y > 0.f ? acc[i][h * 4 + 1] : 0.f;
         v.z = gg.z > 0.f ? acc[i][h * 4 + 2] : 0.f; v.w = gg.w > 0.f ? acc[i][h * 4 + 3] : 0.f;
       } else {
-        const float4 bb = ld4(p.bias + n);
+        const float4 bb = p.bias ? ld4(p.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         v.x = acc[i][h * 4 + 0] + bb.x; v.y = acc[i][h * 4 + 1] + bb.y;
         v.z = acc[i][h * 4 + 2] + bb.z; v.w = acc[i][h * 4 + 3] + bb.w;
         if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }

@@ -55,6 +55,9 @@ def get_model(pcA, pcB,
         # Inference (no gradient can be asked of the result): the whole graph below is one library call,
         # dpd_model_forward.  Same ops, same results; the training path keeps the three reference stages.
         wants_grad = torch.is_grad_enabled() and (bool(is_training) if isinstance(is_training, (bool, int)) else True)
+        # ... unless the graph is differentiated through into the point clouds (DPDist as a loss, :203 consumers)
+        wants_grad = wants_grad or (torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad
+                                                                    for t in (pcA, pcB, add_noise)))
         if FUSED_INFERENCE and not wants_grad and NUM_DIMS == 3 and conv_version == 1 and not bn:
             fv, out, C = dpdist.model_forward(torch.cat([pcA_noise, pcB], 0), torch.cat([pcB, pcA], 0), n_gaussians,
                                               sigma3dmfv, full_fv, k, localSNmlp, reuse=reuse)

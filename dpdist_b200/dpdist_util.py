@@ -93,15 +93,9 @@ def _ptr(t):
 # --------------------------------------------------------------------------------------
 # 3DmFV
 # --------------------------------------------------------------------------------------
-def get_3dmfv_tf(points, n_gaussians=9, sigma=0.0625, flatten=True, normalize=True, full_fv=True):
-    """points [B,N,3] -> fv [B, n_gaussians, 20|7] (flatten=False) or [B, (20|7)*n_gaussians].
-    `normalize` is accepted and ignored: the reference hard-wires it to True (:111)."""
+def _fv_forward(points, G, l, sigma, full_fv, flatten):
     lib = _lib.load()
-    points = _check_cuda(points, "points")
-    if points.dim() != 3 or points.shape[-1] != 3:
-        raise ValueError("points must be [B,N,3]")
     B, N, _ = points.shape
-    G, l = _fv_grid(n_gaussians, 3)
     C = FV_CHANNELS[bool(full_fv)]
     V = G ** 3
     out = torch.empty((B, C * V) if flatten else (B, V, C), device=points.device, dtype=torch.float32)
@@ -110,6 +104,44 @@ def get_3dmfv_tf(points, n_gaussians=9, sigma=0.0625, flatten=True, normalize=Tr
                                 int(bool(flatten)), _ptr(out), _stream())
     _lib.check(rc, "dpd_fv_forward")
     return out
+
+
+class _FvFunction(torch.autograd.Function):
+    """get_3dmfv_tf with its gradient w.r.t. the points (dpd_fv_backward): the path PCRNet-ours and the AUE
+    task differentiate through when DPDist is their loss (iterative_PCRNet_ours.py:229-257)."""
+
+    @staticmethod
+    def forward(ctx, points, G, l, sigma, full_fv, flatten):
+        ctx.save_for_backward(points)
+        ctx.cfg = (G, l, float(sigma), bool(full_fv), bool(flatten))
+        return _fv_forward(points, G, l, sigma, full_fv, flatten)
+
+    @staticmethod
+    def backward(ctx, grad_fv):
+        (points,) = ctx.saved_tensors
+        G, l, sigma, full_fv, flatten = ctx.cfg
+        lib = _lib.load()
+        grad_fv = grad_fv.contiguous().float()
+        B, N, _ = points.shape
+        grad_points = torch.empty_like(points)
+        with torch.cuda.device(points.device):
+            rc = lib.dpd_fv_backward(_ptr(points), B, N, G, _lib.fptr(l), sigma, int(full_fv), int(flatten),
+                                     _ptr(grad_fv), _ptr(grad_points), _stream())
+        _lib.check(rc, "dpd_fv_backward")
+        return grad_points, None, None, None, None, None
+
+
+def get_3dmfv_tf(points, n_gaussians=9, sigma=0.0625, flatten=True, normalize=True, full_fv=True):
+    """points [B,N,3] -> fv [B, n_gaussians, 20|7] (flatten=False) or [B, (20|7)*n_gaussians].
+    `normalize` is accepted and ignored: the reference hard-wires it to True (:111).
+    Differentiable w.r.t. `points`."""
+    points = _check_cuda(points, "points")
+    if points.dim() != 3 or points.shape[-1] != 3:
+        raise ValueError("points must be [B,N,3]")
+    G, l = _fv_grid(n_gaussians, 3)
+    if torch.is_grad_enabled() and points.requires_grad:
+        return _FvFunction.apply(points, G, l, sigma, full_fv, flatten)
+    return _fv_forward(points, G, l, sigma, full_fv, flatten)
 
 
 # --------------------------------------------------------------------------------------
@@ -200,8 +232,8 @@ def get_pc_grid_binary_mask_from_centers(Centers, point_cloud):
 # --------------------------------------------------------------------------------------
 class _PackedHead:
     """Kernel-layout copy of the four conv layers, rebuilt when any variable changes.  The cache key is
-    the identity of the variable objects (kept alive here so ids cannot be recycled) plus their
-    in-place version counters, so optimizer steps and load_state_dict both invalidate it."""
+    the storage address of the variables (kept alive here so addresses cannot be recycled; detach() views
+    share it) plus their in-place version counters, so optimizer steps and load_state_dict both invalidate it."""
 
     def __init__(self):
         self.key = None
@@ -210,7 +242,7 @@ class _PackedHead:
         self.ws = None
 
     def get(self, lib, cfg, weights, ws_list):
-        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags) + tuple((id(w), w._version) for w in weights)
+        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags) + tuple((w.data_ptr(), w._version) for w in weights)
         if key != self.key:
             nbytes = lib.dpd_head_packed_bytes(ctypes.byref(cfg))
             if nbytes == 0:
@@ -267,43 +299,58 @@ GRAD_READY_HOOK = None
 
 
 class _HeadFunction(torch.autograd.Function):
-    """Autograd node of the head: gradients w.r.t. the 8 variables (train_multi_gpu_pc_compare_dist.py:274-277).
-    Gradients w.r.t. fv / query (needed when DPDist is used as a loss for another network)
-    are not implemented yet and raise."""
+    """Autograd node of the head.  Gradients w.r.t. the 8 variables (train_multi_gpu_pc_compare_dist.py:274-277)
+    and / or w.r.t. the inputs fv and query (DPDist as a loss for another network, iterative_PCRNet_ours.py:229-257);
+    only what the graph asks for is computed."""
 
     @staticmethod
     def forward(ctx, fv, query, tables, k, impl, *weights):
-        out, cfg, cache = _head_call(fv, query, tables, weights, k, impl | _lib.HEAD_TRAIN)
-        ctx.fv, ctx.cfg, ctx.cache, ctx.generation = fv, cfg, cache, cache.generation
+        ctx.inputs_need = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        flags = impl | _lib.HEAD_TRAIN | (_lib.HEAD_INPUT_GRAD if ctx.inputs_need else 0)
+        out, cfg, cache = _head_call(fv, query, tables, weights, k, flags)
+        ctx.fv, ctx.cfg, ctx.cache, ctx.generation = fv.detach(), cfg, cache, cache.generation
         ctx.shapes = [tuple(w.shape) for w in weights]
-        ctx.input_needs_grad = fv.requires_grad or query.requires_grad
+        ctx.query_shape = tuple(query.shape)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        if ctx.input_needs_grad:
-            raise NotImplementedError("gradients w.r.t. the point clouds (DPDist as a loss for another network) are not implemented yet")
         cache, cfg, fv = ctx.cache, ctx.cfg, ctx.fv
         if cache.generation != ctx.generation:
             raise RuntimeError("the activations of this forward were overwritten by a later DPDist call; call backward() first")
         lib = _lib.load()
         grad_out = grad_out.contiguous().float()
-        grads = [torch.empty(s, device=fv.device, dtype=torch.float32) for s in ctx.shapes]
-        ptrs = [_ptr(g) for g in grads]
+        need_w = ctx.needs_input_grad[5:]
+        # a layer's weight and bias gradients come out of one product: compute both if either is asked for
+        need_layer = [bool(need_w[2 * i] or need_w[2 * i + 1]) for i in range(4)]
+        grads = [torch.empty(s, device=fv.device, dtype=torch.float32) if need_layer[i // 2] else None
+                 for i, s in enumerate(ctx.shapes)]
+        ptrs = [_ptr(g) if g is not None else None for g in grads]
+        grad_fv = grad_query = None
         with torch.cuda.device(fv.device):
             for stage, layer in ((_lib.BWD_L4, 4), (_lib.BWD_L3, 3), (_lib.BWD_L2, 2), (_lib.BWD_L1, 1)):
+                if layer == 1 and not need_layer[0]:
+                    break
                 rc = lib.dpd_head_backward(ctypes.byref(cfg), _ptr(fv), _ptr(cache.blob), _ptr(grad_out), stage, *ptrs,
                                            _ptr(cache.ws), cache.ws.numel(), _stream())
                 _lib.check(rc, "dpd_head_backward")
-                if GRAD_READY_HOOK is not None:
+                if GRAD_READY_HOOK is not None and need_layer[layer - 1]:
                     GRAD_READY_HOOK(layer, grads[2 * (layer - 1):2 * layer])
-        return (None, None, None, None, None) + tuple(grads)
+            if ctx.inputs_need:
+                grad_fv = torch.empty_like(fv)
+                grad_query = torch.empty(ctx.query_shape, device=fv.device, dtype=torch.float32)
+                rc = lib.dpd_head_backward_inputs(ctypes.byref(cfg), _ptr(cache.blob), _ptr(grad_fv), _ptr(grad_query),
+                                                  _ptr(cache.ws), cache.ws.numel(), _stream())
+                _lib.check(rc, "dpd_head_backward_inputs")
+        wg = tuple(g if need_w[i] else None for i, g in enumerate(grads))
+        return (grad_fv if ctx.needs_input_grad[0] else None, grad_query if ctx.needs_input_grad[1] else None,
+                None, None, None) + wg
 
 
 def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
     """out[c,q,:] = mask * relu6(MLP([query - centre | patch_k(fv[c], voxel(query))])) / 3.
     fv [n_clouds,V,Cc], query [n_clouds,NP,3], weights = [w1,b1,w2,b2,w3,b3,w4,b4] in the
-    reference's HWIO layouts.  Differentiable w.r.t. the weights."""
+    reference's HWIO layouts.  Differentiable w.r.t. the weights, fv and query."""
     fv = _check_cuda(fv, "fv")
     query = _check_cuda(query, "query")
     if query.shape[0] != fv.shape[0]:
@@ -312,7 +359,8 @@ def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
     if tables[0] ** 3 != fv.shape[1]:
         raise ValueError("C and fv disagree on the grid")
     impl = HEAD_IMPL if impl is None else impl
-    needs_grad = torch.is_grad_enabled() and any(getattr(w, "requires_grad", False) for w in weights)
+    needs_grad = torch.is_grad_enabled() and (fv.requires_grad or query.requires_grad or
+                                              any(getattr(w, "requires_grad", False) for w in weights))
     if needs_grad and not return_idx:
         return _HeadFunction.apply(fv, query, tables, k, impl, *weights)
     idx = torch.empty(query.shape[:2], device=fv.device, dtype=torch.int32) if return_idx else None
@@ -417,10 +465,11 @@ def DPDist(point_cloud, point_cloudB, embedding,
     fv_all = torch.cat([fvA, fvB], 0)             # rows [A-field | B-field]  (:511)
     query = torch.cat([pcB, pcA], 0)              # A's field is queried at B's points and vice versa (:494,498)
     # is_training only switches batch norm in the reference (off here); a literal False/0 additionally
-    # selects the inference path (no activations kept for a backward pass)
-    grad_ok = torch.is_grad_enabled() and (bool(is_training) if isinstance(is_training, (bool, int)) else True)
-    with torch.set_grad_enabled(grad_ok):
-        out = head_forward(fv_all, query, C, weights, k)
+    # freezes the variables: no weight gradients, and no activations kept unless the INPUTS ask for gradients
+    # (DPDist as a loss for another network)
+    if isinstance(is_training, (bool, int)) and not is_training:
+        weights = [w.detach() for w in weights]
+    out = head_forward(fv_all, query, C, weights, k)
     out = out.view(2, B, NP, 1, 3)
     return [out[0], out[1]]                                                    # :695
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DPD_ABI_VERSION 1
+#define DPD_ABI_VERSION 2
 #define DPD_MAX_GRID 16
 #define DPD_FV_CHANNELS_FULL 20
 #define DPD_FV_CHANNELS_SMALL 7
@@ -47,6 +47,7 @@ extern "C" {
 #define DPD_HEAD_TC 2      /* tcgen05 tensor-core GEMMs, fp16x3 split precision with power-of-two scaling */
 #define DPD_HEAD_TC_TF32 3 /* tcgen05 tensor-core GEMMs, 3xTF32 split precision */
 #define DPD_HEAD_TRAIN 0x10 /* OR-ed into flags: keep the activations for dpd_head_backward (one row chunk only) */
+#define DPD_HEAD_INPUT_GRAD 0x20 /* OR-ed with DPD_HEAD_TRAIN: also keep what dpd_head_backward_inputs needs */
 
 /* stages of dpd_head_backward: ALL, or one layer at a time (4 -> 1) so that the caller can start the
  * gradient all-reduce of a layer while the next one is still being computed */
@@ -67,6 +68,17 @@ const char* dpd_last_error(void);
  *            flatten=1: [n_clouds, C*G^3]    channel-major                      (:129-132)     */
 int dpd_fv_forward(const float* d_points, int n_clouds, int n_points, int G, const float* h_centers,
                    float sigma, int full_fv, int flatten, float* d_fv, void* stream);
+
+/* Gradient of the 3DmFV encoding w.r.t. the points: replaces what tf.gradients builds over get_3dmfv_tf
+ * (utils/dpdist_util.py:54-137) when the DPDist graph is used as a loss for another network and gradients flow
+ * into input1 / input2 (pcrnet-registration/iterative_PCRNet_ours.py:229-257; train_multi_gpu_pc_compare_dist.py:433-463).
+ * TF semantics: reduce_max / reduce_min gradients are split evenly among ties; d/dx sign(x) sqrt(max(|x|,1e-12)) is 0
+ * below the clamp; l2_normalize is a constant scale below its clamp.  G <= 10 (shared-memory limit).
+ *   d_grad_fv     same layout as dpd_fv_forward's d_fv (flatten = 0 or 1)
+ *   d_grad_points [n_clouds, n_points, 3] out                                                    */
+int dpd_fv_backward(const float* d_points, int n_clouds, int n_points, int G, const float* h_centers,
+                    float sigma, int full_fv, int flatten, const float* d_grad_fv, float* d_grad_points,
+                    void* stream);
 
 /* Voxel assignment of query points: replaces DPDist.get_pc_grid_binary_mask_from_centers +
  * the mask / offset gathers of get_emb_and_concat (utils/dpdist_util.py:459-492, 434-447).
@@ -141,11 +153,24 @@ int dpd_model_forward(const dpd_head_config* cfg, const float* d_points, int n_p
  * including DPD_HEAD_TRAIN), packed weights and workspace; uses the activations left there.
  *   d_grad_out [n_clouds, n_query, 3]  dLoss/d(out); row blocks that are identically zero are skipped
  *   d_gw1 [3+k^3*C, H] (reference row order, offset rows first), d_gw2/3 [H,H], d_gw4 [H,3], d_gb* biases
- * stage = DPD_BWD_ALL, or DPD_BWD_L4, L3, L2, L1 in that order (each writes only its layer's gradients). */
+ * stage = DPD_BWD_ALL, or DPD_BWD_L4, L3, L2, L1 in that order (each writes only its layer's gradients).
+ * A NULL d_gw<i> skips that layer's weight / bias gradient (frozen DPDist used as a loss): the chain of
+ * activation gradients is still propagated for dpd_head_backward_inputs.                                  */
 int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, const void* d_packed,
                       const float* d_grad_out, int stage, float* d_gw1, float* d_gb1, float* d_gw2,
                       float* d_gb2, float* d_gw3, float* d_gb3, float* d_gw4, float* d_gb4,
                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Gradients of the head w.r.t. its INPUTS: the 3DmFV tensor and the query points (the path PCRNet-ours and the AUE
+ * task differentiate through, pcrnet-registration/iterative_PCRNet_ours.py:229-257).  Must follow
+ * dpd_head_backward stages L4, L3, L2 (or ALL) of the same forward; cfg.flags carry DPD_HEAD_TRAIN | DPD_HEAD_INPUT_GRAD.
+ *   d_grad_fv    [n_clouds, G^3, C]     out: sum over the cloud's queries of the patch part of dL/d(layer-1 input),
+ *                                       i.e. the transpose of the gather of get_emb_and_concat (:449-453) and of
+ *                                       extract_volume_patches (:922-930)
+ *   d_grad_query [n_clouds, n_query, 3] out: the offset part (offset = query - centre, :491; the voxel index and the
+ *                                       in-cube mask are piecewise constant and carry no gradient)            */
+int dpd_head_backward_inputs(const dpd_head_config* cfg, const void* d_packed, float* d_grad_fv,
+                             float* d_grad_query, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Adam with tf.train.AdamOptimizer semantics (train_multi_gpu_pc_compare_dist.py:216, 301):
  * lr_t = lr*sqrt(1-beta2^step)/(1-beta1^step); var -= lr_t * m / (sqrt(v) + eps).  step is 1-based. */

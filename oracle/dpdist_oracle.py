@@ -112,13 +112,13 @@ def get_3dmfv(points, n_gaussians=9, sigma=0.0625, flatten=True, normalize=True,
     Q_per_d = Q[..., None]                                            # :75
 
     d_pi_all = ((Q - batch_w) / (torch.sqrt(batch_w) * n_points))[..., None]   # :78
-    d_pi_max = d_pi_all.max(dim=1).values                             # :80
+    d_pi_max = d_pi_all.amax(dim=1)                             # :80
     d_pi_mean = d_pi_all.mean(dim=1)                                  # :81
     d_pi = torch.cat([d_pi_mean, d_pi_max], 2) if full_fv else d_pi_mean      # :82-85
 
     d_mu_all = Q_per_d * (batch_points - batch_mu) / batch_sig        # :87
-    d_mu_all_max = d_mu_all.max(dim=1).values                         # :89
-    d_mu_all_min = d_mu_all.min(dim=1).values                         # :90
+    d_mu_all_max = d_mu_all.amax(dim=1)                         # :89
+    d_mu_all_min = d_mu_all.amin(dim=1)                         # :90
     d_mu_all_mean = d_mu_all.mean(dim=1)                              # :91
     if full_fv:
         d_mu_all_full = torch.cat([d_mu_all_mean, d_mu_all_max, d_mu_all_min], 2)   # :94
@@ -127,8 +127,8 @@ def get_3dmfv(points, n_gaussians=9, sigma=0.0625, flatten=True, normalize=True,
     d_mu = (1 / torch.sqrt(w_per_batch_per_d)) * d_mu_all_full        # :98
 
     d_sig_all = Q_per_d * (torch.pow((batch_points - batch_mu) / batch_sig, 2) - 1)  # :100
-    d_sig_all_max = d_sig_all.max(dim=1).values
-    d_sig_all_min = d_sig_all.min(dim=1).values
+    d_sig_all_max = d_sig_all.amax(dim=1)     # amax/amin: gradient split evenly among ties, like TF reduce_max
+    d_sig_all_min = d_sig_all.amin(dim=1)
     d_sig_all_mean = d_sig_all.mean(dim=1)
     if full_fv:
         d_sig_all_full = torch.cat([d_sig_all_mean, d_sig_all_max, d_sig_all_min], 2)  # :106

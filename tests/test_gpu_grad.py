@@ -1,0 +1,175 @@
+"""GPU tests of the input-gradient path: DPDist used as a loss whose gradients flow into the
+point clouds, as PCRNet-ours and the AUE task do (pcrnet-registration/iterative_PCRNet_ours.py:229-257;
+train_multi_gpu_pc_compare_dist.py:433-463).  Reference gradients = torch autograd through the fp64 CPU oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from dpdist_b200 import _lib, dpdist_and_aue as MODEL, dpdist_util, synthetic, tf_util
+from oracle import dpdist_oracle as O
+from tolerances import assert_close, assert_grad_close, assert_out_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _oracle_fv_grad(pts, gup, V, sigma, full_fv, flatten):
+    x = torch.tensor(pts, dtype=torch.float64, requires_grad=True)
+    fv = O.get_3dmfv(x, n_gaussians=V, sigma=sigma, flatten=flatten, full_fv=full_fv)
+    (fv * torch.tensor(gup, dtype=torch.float64)).sum().backward()
+    return x.grad.numpy()
+
+
+@pytest.mark.parametrize("G,N,sigma", [(8, 64, 0.125), (8, 200, 0.125), (8, 1, 0.125), (4, 9, 0.125), (8, 64, 0.25), (2, 5, 0.5)])
+@pytest.mark.parametrize("full_fv,flatten", [(True, False), (False, False), (True, True)])
+@pytest.mark.parametrize("conditioned", [True, False])
+def test_fv_backward_matches_oracle_autograd(G, N, sigma, full_fv, flatten, conditioned):
+    rng = np.random.default_rng(100 * G + N)
+    pts = rng.uniform(-0.85, 0.85, size=(3, N, 3)).astype(np.float32)
+    if N >= 5:
+        pts[1, 3] = pts[1, 1]          # duplicated point: every max / min it attains is a two-way tie (TF splits evenly)
+    V, C = G ** 3, 20 if full_fv else 7
+    gup = rng.normal(size=(3, C * V) if flatten else (3, V, C)).astype(np.float32)
+    if conditioned:   # no upstream gradient on entries that sit near the square root's singularity (tolerances.py)
+        fv64 = O.get_3dmfv(torch.tensor(pts, dtype=torch.float64), n_gaussians=V, sigma=sigma, flatten=flatten, full_fv=full_fv)
+        gup = gup * (fv64.abs().numpy() >= 1e-2)
+    want = _oracle_fv_grad(pts, gup, V, sigma, full_fv, flatten)
+    x = torch.tensor(pts, device=DEV, requires_grad=True)
+    fv = dpdist_util.get_3dmfv_tf(x, n_gaussians=V, sigma=sigma, flatten=flatten, full_fv=full_fv)
+    (fv * torch.tensor(gup, device=DEV)).sum().backward()
+    if conditioned:
+        assert_grad_close(x.grad, want, "d fv / d points (conditioned)", rtol=1e-3, rms_tol=1e-3)
+    else:
+        assert_grad_close(x.grad, want, "d fv / d points", frac=0.95)
+    if N >= 5:   # the two copies of the duplicated point receive identical gradients
+        assert torch.equal(x.grad[1, 3], x.grad[1, 1])
+
+
+def test_fv_backward_is_deterministic_and_batch_independent():
+    rng = np.random.default_rng(5)
+    pts = torch.tensor(rng.uniform(-0.8, 0.8, size=(700, 64, 3)).astype(np.float32), device=DEV)
+    gup = torch.tensor(rng.normal(size=(700, 512, 20)).astype(np.float32), device=DEV)
+
+    def run(p, g):
+        x = p.clone().requires_grad_(True)
+        (dpdist_util.get_3dmfv_tf(x, n_gaussians=512, sigma=0.125, flatten=False) * g).sum().backward()
+        return x.grad
+    a, b = run(pts, gup), run(pts, gup)
+    assert torch.equal(a, b)
+    c = run(pts[600:], gup[600:])       # more clouds than CTAs vs. one cloud per CTA: same numbers
+    assert torch.equal(a[600:], c)
+    assert torch.isfinite(a).all()
+
+
+def test_fv_backward_rejects_what_it_cannot_do():
+    lib = _lib.load()
+    l = np.zeros(16, np.float32)
+    x = torch.zeros((1, 4, 3), device=DEV)
+    g = torch.zeros((1, 11 ** 3, 20), device=DEV)
+    rc = lib.dpd_fv_backward(x.data_ptr(), 1, 4, 11, _lib.fptr(l), 0.1, 1, 0, g.data_ptr(), x.data_ptr(), None)
+    assert rc == -2 and b"shared memory" in lib.dpd_last_error()
+    assert lib.dpd_fv_backward(None, 1, 4, 8, _lib.fptr(l), 0.1, 1, 0, g.data_ptr(), x.data_ptr(), None) == -1
+
+
+# ------------------------------------------------------------------ head inputs
+def _oracle_head_input_grads(fv, query, var, k, gout):
+    """autograd through the oracle's local_z + DPDist with fv / query as leaves.  fv [2B,V,C] rows [A | B],
+    query [2B,NP,3] rows [pcB | pcA]."""
+    B = fv.shape[0] // 2
+    f = torch.tensor(fv, dtype=torch.float64, requires_grad=True)
+    q = torch.tensor(query, dtype=torch.float64, requires_grad=True)
+    v = {n: t.double() for n, t in var.items()}
+    embA, C = O.local_z(f[:B], k=k)
+    embB, _ = O.local_z(f[B:], k=k)
+    ab, ba = O.DPDist(q[B:], q[:B], embA, embB, C.double(), v)       # DPDist(pcA, pcB, ...): queries pcB on A
+    out = torch.cat([ab, ba], 0)[:, :, 0, :]
+    (out * torch.tensor(gout, dtype=torch.float64)).sum().backward()
+    return out.detach().numpy(), f.grad.numpy(), q.grad.numpy()
+
+
+@pytest.mark.parametrize("impl", [_lib.HEAD_SIMT, _lib.HEAD_AUTO])
+@pytest.mark.parametrize("B,NP,G,k,H", [(2, 64, 8, 5, 1024), (3, 20, 4, 3, 256), (1, 200, 8, 5, 256)])
+def test_head_input_gradients_match_oracle_autograd(impl, B, NP, G, k, H):
+    rng = np.random.default_rng(B * 1000 + NP)
+    V = G ** 3
+    pts = rng.uniform(-0.8, 0.8, size=(2 * B, 64, 3)).astype(np.float32)
+    with O.tf_cpu_numerics():
+        fv = O.get_3dmfv(torch.tensor(pts), V, 0.125, flatten=False).numpy()
+    query = rng.uniform(-0.9, 0.9, size=(2 * B, NP, 3)).astype(np.float32)
+    query[0, :3] = [[1.2, 0.1, 0.1], [0.0, -1.5, 0.3], [0.99, 0.99, -0.99]]          # outside the cube / corner voxel
+    gout = rng.normal(size=(2 * B, NP, 3)).astype(np.float32)
+    var = O.unit_scale_variables(5, k=k, mlp=(H, H, H))
+    want_out, want_gfv, want_gq = _oracle_head_input_grads(fv, query, var, k, gout)
+
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    f = torch.tensor(fv, device=DEV, requires_grad=True)
+    q = torch.tensor(query, device=DEV, requires_grad=True)
+    X, Y, Z = dpdist_util.get_grid_centers(V, 3)
+    C = torch.tensor(np.stack([X, Y, Z], -1).astype(np.float32).reshape(-1, 3), device=DEV)
+    weights = [store.vars[O.VAR_PREFIX + s + sfx].detach() for s in O.MLP_SCOPES for sfx in ("/weights", "/biases")]
+    out = dpdist_util.head_forward(f, q, C, weights, k, impl=impl)
+    assert out.requires_grad
+    assert_out_close(out, want_out, "head out")
+    (out * torch.tensor(gout, device=DEV)).sum().backward()
+    assert_grad_close(f.grad, want_gfv, "d out / d fv", rtol=2e-4, rms_tol=2e-4)
+    assert_grad_close(q.grad, want_gq, "d out / d query", rtol=2e-4, rms_tol=2e-4)
+    assert float(q.grad[0, :2].abs().max()) == 0.0                                   # masked queries get no gradient
+    assert all(store.vars[n].grad is None for n in store.vars)                       # frozen variables: nothing computed
+
+
+# ------------------------------------------------------------------ whole model as a loss
+@pytest.mark.parametrize("B", [2, 5])
+def test_dpdist_as_a_loss_gradients_into_both_clouds(B):
+    """loss = (mean(out1[...,0]) + mean(out2[...,0])) / 2 as in iterative_PCRNet_ours.py:253-257, DPDist frozen."""
+    pcA, pcB, _ = synthetic.uniform_batch(31 + B, B, 64, outside_frac=0.03)
+    var = O.unit_scale_variables(3)
+    a = torch.tensor(pcA, dtype=torch.float64, requires_grad=True)
+    b = torch.tensor(pcB, dtype=torch.float64, requires_grad=True)
+    p, _, _ = O.get_model(a, b, {n: t.double() for n, t in var.items()})
+    want = (p["pred_listAB"][..., 0].mean() + p["pred_listBA"][..., 0].mean()) / 2
+    want.backward()
+
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    ga = torch.tensor(pcA, device=DEV, requires_grad=True)
+    gb = torch.tensor(pcB, device=DEV, requires_grad=True)
+    with tf_util.use_store(store):
+        pred, _, _ = MODEL.get_model(ga, gb, False, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+    loss = (pred["pred_listAB"][..., 0].mean() + pred["pred_listBA"][..., 0].mean()) / 2
+    loss.backward()
+    assert abs(float(loss) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+    assert_grad_close(ga.grad, a.grad.numpy(), "d loss / d input1", frac=0.95)
+    assert_grad_close(gb.grad, b.grad.numpy(), "d loss / d input2", frac=0.95)
+    assert all(v.grad is None for v in store.vars.values())
+    # the same call without requires_grad takes the one-call inference path and gives the same numbers
+    with tf_util.use_store(store):
+        pred2, _, _ = MODEL.get_model(ga.detach(), gb.detach(), False, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+    assert_close(pred2["pred_listAB"], pred["pred_listAB"].detach(), 0, 2e-6, "inference vs differentiable path")
+
+
+def test_training_and_input_gradients_together():
+    """weights AND inputs ask for gradients: both come out of one backward."""
+    pcA, pcB, labels = synthetic.uniform_batch(77, 2, 64)
+    var = O.unit_scale_variables(9)
+    v = {n: t.double().requires_grad_(True) for n, t in var.items()}
+    a = torch.tensor(pcA, dtype=torch.float64, requires_grad=True)
+    p, _, _ = O.get_model(a, torch.tensor(pcB, dtype=torch.float64), v)
+    O.get_loss(p, {}, torch.tensor(labels * 3.0, dtype=torch.float64))[0].backward()
+
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    ga = torch.tensor(pcA, device=DEV, requires_grad=True)
+    tf_util.clear_collections()
+    with tf_util.use_store(store):
+        pred, ep, _ = MODEL.get_model(ga, torch.tensor(pcB, device=DEV), True, bn=0, Embedding_Size=512, k=5,
+                                      sigma3dmfv=0.125, reuse=True)
+        MODEL.get_loss(pred, ep, torch.tensor(labels * 3.0, device=DEV))
+    tf_util.get_collection("loss_samples")[-1].backward()
+    assert_grad_close(ga.grad, a.grad.numpy(), "d loss / d input1 (training)", frac=0.95)
+    for n, t in v.items():
+        ref = t.grad
+        err = float((store.vars[n].grad.cpu().double() - ref).abs().max())
+        assert err <= 2e-4 * float(ref.abs().max()), n
