@@ -104,5 +104,23 @@ extern "C" int dpd_profile_read(dpd_profile_entry* h_entries, int max_entries, i
   return n;
 }
 
+// CRC32C (Castagnoli, reflected polynomial 0x82F63B78) of a HOST buffer: the checksum TensorFlow's tensor-bundle
+// checkpoints store per variable (dpdist_b200/tf_checkpoint.py verifies it when loading a reference model.ckpt).
+extern "C" uint32_t dpd_crc32c(const void* h_data, size_t n) {
+  static uint32_t table[256];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[i] = c;
+    }
+  });
+  const unsigned char* p = (const unsigned char*)h_data;
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
 extern "C" int dpd_version(void) { return DPD_ABI_VERSION; }
 extern "C" const char* dpd_last_error(void) { return dpd::last_error_buf(); }

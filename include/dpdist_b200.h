@@ -184,6 +184,11 @@ int dpd_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, s
 int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
                       float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream);
 
+/* CRC32C (Castagnoli) of a HOST buffer: the per-variable checksum of TensorFlow V2 checkpoints, used when a
+ * reference-trained model.ckpt (train_multi_gpu_pc_compare_dist.py:311; consumed by
+ * pcrnet-registration/iterative_PCRNet_ours.py:229) is loaded under its TF variable names. */
+uint32_t dpd_crc32c(const void* h_data, size_t n);
+
 /* Measurement hooks (used by bench.py; no effect on results).
  * dpd_launch_count : kernels this library has launched in this process (cumulative).
  * dpd_profile_enable(1) brackets every kernel launch with CUDA events on the launching stream;

@@ -241,3 +241,36 @@ def test_full_size_batch_properties():
     # pairs are independent: the same pair alone gives the same answer
     p1, _ = _run_model(pcA[500:501], pcB[500:501], var, _lib.HEAD_AUTO)
     assert_out_close(p1["pred_listAB"], ab[500:501])
+
+
+def test_stress_config_E_properties():
+    """BASELINE config E (4096 pairs, N = NP = 512, G = 8, k = 5: 4.19 M query rows in 16 row chunks, 336 MB of
+    3DmFV tensors) on one GPU.  The oracle cannot run this size; check size-independent properties and two pairs
+    against the oracle."""
+    rng = np.random.default_rng(3)
+    B, N = 4096, 512
+    pcA = rng.uniform(-0.8, 0.8, size=(B, N, 3)).astype(np.float32)
+    pcB = rng.uniform(-0.8, 0.8, size=(B, N, 3)).astype(np.float32)
+    pcB[:, :8, 0] = 1.25                                   # 8 queries per cloud outside the unit cube
+    var = O.unit_scale_variables(4)
+    p, emb = _run_model(pcA, pcB, var, _lib.HEAD_AUTO)
+    ab, ba = p["pred_listAB"], p["pred_listBA"]
+    assert ab.shape == (B, N, 1, 3) and ba.shape == (B, N, 1, 3)
+    assert torch.isfinite(ab).all() and torch.isfinite(ba).all()
+    assert float(ab.min()) >= 0 and float(ab.max()) <= 2.0 and float(ba.max()) <= 2.0
+    assert float(ab[:, :8].abs().max()) == 0.0             # masked queries (:697-698); pcB queries A's field
+    assert float(ab[:, 8:].max()) > 0.0
+    fv = emb["embedding_A"].fv
+    assert fv.shape == (B, 512, 20)
+    # every channel of every cloud is L2-normalised over the Gaussians (:124-126)
+    nrm = fv.double().square().sum(1).sqrt()
+    assert float((nrm - 1).abs().max()) < 1e-5
+    # pairs are independent and row chunks are invisible: pairs from the first, a middle and the last chunk alone
+    for i in (0, 2049, B - 1):
+        p1, _ = _run_model(pcA[i:i + 1], pcB[i:i + 1], var, _lib.HEAD_AUTO)
+        assert_out_close(p1["pred_listAB"], ab[i:i + 1], "pair %d alone" % i)
+        assert_out_close(p1["pred_listBA"], ba[i:i + 1], "pair %d alone" % i)
+    with O.tf_cpu_numerics():
+        oab, oba = O.forward_chunked(torch.tensor(pcA[2049:2051]), torch.tensor(pcB[2049:2051]), var, chunk=1)
+    assert_out_close(ab[2049:2051], oab, "config E vs oracle (AB)")
+    assert_out_close(ba[2049:2051], oba, "config E vs oracle (BA)")

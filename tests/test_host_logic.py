@@ -99,3 +99,29 @@ def test_synthetic_shapes_follow_the_dataset():
     assert (np.abs(b) > 1).any()
     a2, _, _ = synthetic.uniform_batch(2, 8, 64)
     assert np.array_equal(a, a2)
+
+
+def test_pcrnet_host_geometry():
+    """helper.py:539-570 / :229-262 / :309-329 restated: quaternion -> rotation, Euler poses, transform accumulation."""
+    import torch
+    from dpdist_b200 import pcrnet_ours as P
+    rng = np.random.default_rng(0)
+    ang = 0.7
+    q = torch.tensor([[np.cos(ang / 2), 0.0, 0.0, np.sin(ang / 2)]], dtype=torch.float32)     # rotation about z
+    pts = torch.tensor(rng.normal(size=(1, 5, 3)), dtype=torch.float32)
+    t = torch.tensor([[0.1, -0.2, 0.3]])
+    got = P.transformation_quat_tensor(pts, q, t)
+    Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    np.testing.assert_allclose(got[0].numpy(), pts[0].numpy() @ Rz.T + t.numpy(), atol=1e-6)
+    poses = P.generate_poses(8, rng)
+    assert np.abs(poses[:, :3]).max() <= 0.01 and np.abs(poses[:, 3:]).max() <= np.pi / 4
+    R = P.euler_to_matrix(poses)
+    np.testing.assert_allclose(np.einsum("bij,bkj->bik", R, R), np.tile(np.eye(3), (8, 1, 1)), atol=1e-12)
+    moved = P.apply_transformation(rng.normal(size=(8, 4, 3)), poses)
+    assert moved.dtype == np.float32 and moved.shape == (8, 4, 3)
+    # compose: T <- M(pose) @ T, un-normalised quaternion is normalised (transforms3d.quat2mat behaviour)
+    pose7 = torch.tensor([[0.1, 0.2, 0.3, 2 * np.cos(ang / 2), 0, 0, 2 * np.sin(ang / 2)]], dtype=torch.float32)
+    T, Rm = P.compose(torch.eye(4)[None], pose7)
+    np.testing.assert_allclose(Rm[0].numpy(), Rz, atol=1e-6)
+    np.testing.assert_allclose(T[0, :3, 3].numpy(), [0.1, 0.2, 0.3], atol=1e-7)
+    assert abs(float(P.normalize_quat(pose7[:, 3:]).norm()) - 1) < 1e-6
