@@ -71,6 +71,11 @@ SIGNATURES.update({
                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "dpd_head_backward_inputs": (ctypes.c_int, [ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "dpd_nearest_distance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "dpd_assemble_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
     "dpd_crc32c": (ctypes.c_uint32, [ctypes.c_char_p, ctypes.c_size_t]),
     "dpd_launch_count": (ctypes.c_longlong, []),
     "dpd_profile_enable": (ctypes.c_int, [ctypes.c_int]),

@@ -184,6 +184,27 @@ int dpd_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, s
 int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
                       float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream);
 
+/* Ground-truth distances of the dataset generator: replaces scipy cdist(point_set, neg_set).min(0)
+ * (dataset_sample_with_gt.py:87-91, 116-117), brute force in fp32 on d^2 = dx^2 + dy^2 + dz^2 (no |a|^2+|b|^2-2ab).
+ *   d_surface [n_clouds, n_surface, 3], d_query [n_clouds, n_query, 3]
+ *   d_dist    [n_clouds, n_query]  out: Euclidean distance to the nearest surface point
+ *   d_arg     [n_clouds, n_query]  out, optional (NULL): index of that point (first minimum)             */
+int dpd_nearest_distance(const float* d_surface, int n_clouds, int n_surface, const float* d_query, int n_query,
+                         float* d_dist, int32_t* d_arg, void* stream);
+
+/* Batch assembly of the DPDist trainer fused with the dataset augmentation: replaces train_one_epoch_3d's numpy
+ * slicing (train_multi_gpu_pc_compare_dist.py:749-766) and ModelNetDataset._augment_batch_data
+ * (modelnet_dataset.py:82-95 = provider.rotate_point_cloud :32-50 + provider.shift_point_cloud :200-211).
+ *   d_data  [bsize, 3*npoints, 3] = surface | close | far points of each item (modelnet_dataset.py:136-139)
+ *   d_label [bsize, 2*npoints]    = GT distances of close | far
+ *   d_angle [bsize] rotation about the up (y) axis in radians, d_shift [bsize, 3]; either may be NULL (no augmentation)
+ *   d_pcA [bsize, num_point, 3] = S_A[:num_point];  d_pcB [bsize, num_point, 3] = S_B[:h] | close[:q] | far[q:h];
+ *   d_labels_ab [bsize, num_point] = 0 x h | gt_close[:q] | gt_far[q:h],  h = num_point/2, q = h/2,
+ *   S_A / S_B = the two halves of the surface points.                                                        */
+int dpd_assemble_batch(const float* d_data, const float* d_label, int bsize, int npoints, int num_point,
+                       const float* d_angle, const float* d_shift, float* d_pcA, float* d_pcB,
+                       float* d_labels_ab, void* stream);
+
 /* CRC32C (Castagnoli) of a HOST buffer: the per-variable checksum of TensorFlow V2 checkpoints, used when a
  * reference-trained model.ckpt (train_multi_gpu_pc_compare_dist.py:311; consumed by
  * pcrnet-registration/iterative_PCRNet_ours.py:229) is loaded under its TF variable names. */

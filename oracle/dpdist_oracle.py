@@ -353,3 +353,42 @@ def forward_chunked(pcA, pcB, variables, chunk=8, **kw):
         outs_ab.append(p["pred_listAB"])
         outs_ba.append(p["pred_listBA"])
     return torch.cat(outs_ab), torch.cat(outs_ba)
+
+
+# --------------------------------------------------------------------------------------
+# data side (test infrastructure for dpdist_b200/data.py)
+# --------------------------------------------------------------------------------------
+def nearest_distance(point_set, neg_set):
+    """dataset_sample_with_gt.py:90-91: dist = cdist(point_set, neg_set_rand); dist_AB = dist.min(0)  (float64)."""
+    from scipy.spatial.distance import cdist
+    d = cdist(np.asarray(point_set, dtype=np.float64), np.asarray(neg_set, dtype=np.float64))
+    return d.min(0), d.argmin(0)
+
+
+def rotate_shift(batch_data, angles, shifts):
+    """provider.rotate_point_cloud (provider.py:32-50) + provider.shift_point_cloud (:200-211) with given draws."""
+    out = np.zeros(batch_data.shape, dtype=np.float32)
+    for k in range(batch_data.shape[0]):
+        cosval, sinval = np.cos(angles[k]), np.sin(angles[k])
+        rotation_matrix = np.array([[cosval, 0, sinval], [0, 1, 0], [-sinval, 0, cosval]])
+        out[k] = np.dot(batch_data[k].reshape((-1, 3)), rotation_matrix)
+        out[k] += shifts[k]
+    return out
+
+
+def assemble_batch(batch_data, batch_label, NUM_POINT):
+    """train_multi_gpu_pc_compare_dist.py:749-766, literally."""
+    H_NUM_POINT = int(NUM_POINT / 2)
+    split_off_surface = 0.5
+    batch_data = np.split(batch_data, 3, 1)
+    batch_surface = np.split(batch_data[0], 2, 1)
+    bsize = batch_data[0].shape[0]
+    pcA = batch_surface[0][:, :NUM_POINT]
+    batch_label = np.split(batch_label, 2, 1)
+    labels_AB = np.concatenate(
+        [np.zeros([bsize, H_NUM_POINT]), batch_label[0][:, :int(H_NUM_POINT * split_off_surface)],
+         batch_label[1][:, int(H_NUM_POINT * split_off_surface):H_NUM_POINT]], 1)
+    batch_off = np.concatenate([batch_data[1][:, :int(H_NUM_POINT * split_off_surface)],
+                                batch_data[2][:, int(H_NUM_POINT * split_off_surface):H_NUM_POINT]], 1)
+    pcB = np.concatenate([batch_surface[1][:, :H_NUM_POINT], batch_off], 1)
+    return pcA, pcB, labels_AB
