@@ -263,15 +263,21 @@ def run_ours(args, rank, world, local_rank):
         ach = fl / per_launch_s / 1e12
         # the kernel is timed inside a long step -> sustained peak
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
+        # very command (profiles/ncu_r1_summary.md, final kernels): layer 1 = 109 + 487 MB, layer 2 = 553 + 494 MB
+        traffic = {"tc_gemm2_gather_l1_f16": 596.1e6, "tc_gemm2_dense_f16": 1047.1e6, "tc_gemm2_dense_l3_l4_f16": 560.9e6}.get(dom)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peaks["source"] + ", dense bf16 sustained; the fp32-accurate fp16x3 split issues 3 tensor "
+                    "traffic": traffic, "traffic_source": "ncu --set full, profiles/ncu_r1_summary.md (bytes per launch)",
+                    "tensor_work_frac": 3 * ach / peak, "peak_source": peaks["source"] + ", dense bf16 sustained; the fp32-accurate fp16x3 split issues 3 tensor "
                     "passes per algorithmic flop, so frac <= 0.333 (DESIGN.md 4.2)", "tensor_passes_per_flop": 3, "share_of_step": kernels[dom]["share"]}
     fvk = [k for k in kernels if k.startswith("fv")]
     if fvk:
         s = kernels[fvk[0]]["ms_per_launch"] * 1e-3
         ach = 2 * CFG["pairs_per_gpu"] * FV_BYTES_PER_CLOUD / s / 1e9
         fv_kernel = {"kernel": fvk[0], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "clouds_per_launch": 2 * CFG["pairs_per_gpu"],
+                     "frac": ach / peaks["hbm_gbs"], "traffic": 110.0e6,
+                     "note": "nominally HBM-bound; in practice bound by fp32 issue slots and the half-rate ALU pipe (FMNMX3): "
+                             "all-pairs ceiling = 43 % of the HBM peak (DESIGN.md 4.1)", "clouds_per_launch": 2 * CFG["pairs_per_gpu"],
                      "bytes_per_cloud": FV_BYTES_PER_CLOUD, "peak_source": peaks["source"]}
 
     # steady-state 3DmFV bandwidth: 16384 clouds per launch (8 x the in-step launch) so launch and tail

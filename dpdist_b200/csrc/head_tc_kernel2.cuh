@@ -309,30 +309,74 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           reinterpret_cast<float4*>(args.part4)[(size_t)row * (2 * num_n_tiles) + nt * 2 + half] = o;
         continue;
       }
+      if (args.split) {
+        // (hi, lo) fp16 activations for the next layer.  After the 16x256b load a quad holds, per j, 8 consecutive
+        // columns (2 per lane) = 16 bytes of fp16: half a sector.  Two j groups are transposed inside the quad with
+        // shuffles so that every lane owns 4 consecutive columns and the quad writes 16 columns = one full 32-byte
+        // sector per row with 8-byte stores (half the store instructions and L2 write requests of 4-byte stores).
+        const int ql = lane & 3;
+        const int src_a = (lane & ~3) | (2 * (ql & 1)), src_b = src_a + 1;
+        const bool upper = (ql >> 1) != 0;          // lanes 2,3 of the quad take the words of group j+1
 #pragma unroll
-      for (int cg = 0; cg < 2; ++cg) {
+        for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = col0 + cg * 64 + j * 8;
-          const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+          for (int jp = 0; jp < 4; ++jp) {
+            const int colj = col0 + cg * 64 + (2 * jp) * 8;
+            const float2 b0 = __ldg(reinterpret_cast<const float2*>(args.bias + colj));
+            const float2 b1 = __ldg(reinterpret_cast<const float2*>(args.bias + colj + 8));
 #pragma unroll
-          for (int rh = 0; rh < 2; ++rh) {
+            for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
-            for (int u2 = 0; u2 < 2; ++u2) {
-              const int row = row_base + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
-              if (row < args.M) {
-                const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
-                const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
-                const size_t o = (size_t)row * args.N + col;
-                if (!args.split) {
-                  *reinterpret_cast<float2*>((float*)args.out0 + o) = make_float2(x0, x1);
-                } else {
-                  const float s0 = x0 * out_scale, s1 = x1 * out_scale;
+              for (int u2 = 0; u2 < 2; ++u2) {
+                const int row = row_base + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
+                uint32_t wh[2], wl[2];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                  const float* sp = sum + (rh * 2 + cg) * 32 + (2 * jp + jj) * 4 + u2 * 2;
+                  const float2 bb = jj ? b1 : b0;
+                  const float s0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f) * out_scale;
+                  const float s1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f) * out_scale;
                   const __half2 hi = __floats2half2_rn(s0, s1);
                   const float2 hf = __half22float2(hi);
                   const __half2 lo = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
-                  *reinterpret_cast<__half2*>((__half*)args.out0 + o) = hi;
-                  *reinterpret_cast<__half2*>((__half*)args.out1 + o) = lo;
+                  wh[jj] = *reinterpret_cast<const uint32_t*>(&hi);
+                  wl[jj] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                uint2 oh, ol;
+                {
+                  const uint32_t a0 = __shfl_sync(0xffffffffu, wh[0], src_a), a1 = __shfl_sync(0xffffffffu, wh[1], src_a);
+                  const uint32_t c0 = __shfl_sync(0xffffffffu, wh[0], src_b), c1 = __shfl_sync(0xffffffffu, wh[1], src_b);
+                  oh.x = upper ? a1 : a0; oh.y = upper ? c1 : c0;
+                  const uint32_t d0 = __shfl_sync(0xffffffffu, wl[0], src_a), d1 = __shfl_sync(0xffffffffu, wl[1], src_a);
+                  const uint32_t e0 = __shfl_sync(0xffffffffu, wl[0], src_b), e1 = __shfl_sync(0xffffffffu, wl[1], src_b);
+                  ol.x = upper ? d1 : d0; ol.y = upper ? e1 : e0;
+                }
+                if (row < args.M) {
+                  // quad base column (lane & 3 == 0) is colj - 2*ql; this lane owns columns [base + 4*ql, base + 4*ql + 4)
+                  const size_t o = (size_t)row * args.N + (size_t)(colj - 2 * ql + 4 * ql);
+                  *reinterpret_cast<uint2*>((__half*)args.out0 + o) = oh;
+                  *reinterpret_cast<uint2*>((__half*)args.out1 + o) = ol;
+                }
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = col0 + cg * 64 + j * 8;
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll
+              for (int u2 = 0; u2 < 2; ++u2) {
+                const int row = row_base + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
+                if (row < args.M) {
+                  const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
+                  const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
+                  *reinterpret_cast<float2*>((float*)args.out0 + (size_t)row * args.N + col) = make_float2(x0, x1);
                 }
               }
             }
