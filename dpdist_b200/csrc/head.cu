@@ -352,6 +352,7 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
   int* active = (int*)(ws + W.active);
   float* part = (float*)(ws + W.part); float* part_bias = (float*)(ws + W.part_bias); float* part4 = (float*)(ws + W.part4);
   const bool all = stage == DPD_BWD_ALL;
+  const bool tc_bwd = is_tc(L.impl) && tc_backward_supported(*cfg, is_f16(L.impl));
   // fp32 views of the forward activations (valid after dpd_head_forward with the same cfg and workspace).
   // SIMT forward leaves H1 in ha and H2 in hb; the tensor-core forwards leave (hi, lo) pairs, merged into
   // ha / hb by the first stage.
@@ -375,8 +376,13 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
       if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
       if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw3, d_gb3, st))) return rc;
     }
-    gp.A = g0; gp.B = (const float*)(pk + L.w3t); gp.gate = H2; gp.Cout = g1;     // dZ2 = (dZ3 . W3^T) * (H2 > 0)
-    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    // dZ2 = (dZ3 . W3^T) * (H2 > 0)
+    if (tc_bwd) {
+      if ((rc = tc_backward_dx(*cfg, 3, pk + L.tc, ws + W.tc, chunk, rows, g0, g1, active, st))) return rc;
+    } else {
+      gp.A = g0; gp.B = (const float*)(pk + L.w3t); gp.gate = H2; gp.Cout = g1;
+      if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    }
   }
   if (all || stage == DPD_BWD_L2) {
     tp.A = H1; tp.B = g1; tp.Kp = H;
@@ -384,8 +390,13 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
       if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
       if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw2, d_gb2, st))) return rc;
     }
-    gp.A = g1; gp.B = (const float*)(pk + L.w2t); gp.gate = H1; gp.Cout = g0;     // dZ1 = (dZ2 . W2^T) * (H1 > 0)
-    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    // dZ1 = (dZ2 . W2^T) * (H1 > 0)
+    if (tc_bwd) {
+      if ((rc = tc_backward_dx(*cfg, 2, pk + L.tc, ws + W.tc, chunk, rows, g1, g0, active, st))) return rc;
+    } else {
+      gp.A = g1; gp.B = (const float*)(pk + L.w2t); gp.gate = H1; gp.Cout = g0;
+      if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    }
   }
   if ((all || stage == DPD_BWD_L1) && d_gw1) {
     GatherDesc g;

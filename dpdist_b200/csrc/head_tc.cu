@@ -118,6 +118,53 @@ __global__ void activation_scales_kernel(float* __restrict__ ws, const float* __
   ws[S_ACC1] = 1.0f / (a1 * ps[P_W1]); ws[S_ACC2] = 1.0f / (a2 * ps[P_W2]); ws[S_ACC3] = 1.0f / (a3 * ps[P_W3]);
 }
 
+__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+// |x|max over the ACTIVE 128-row blocks of x [rows, H] (inactive blocks hold stale data and are never read)
+__global__ void absmax_active_kernel(const float* __restrict__ x, int rows, int H, const int* __restrict__ active,
+                                     unsigned* __restrict__ out_bits) {
+  const int blk = blockIdx.x;
+  if (active && !active[blk]) return;
+  const size_t lo = (size_t)blk * 128 * H, hi = min((size_t)rows, (size_t)(blk + 1) * 128) * H;
+  float m = 0.f;
+  for (size_t i = lo + threadIdx.x * 4; i < hi; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// (hi, lo) = fp16 split of x * scale for active 128-row blocks, zeros for inactive ones
+__global__ void split_f16_active_kernel(const float* __restrict__ x, int rows, int H, const int* __restrict__ active,
+                                        const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int blk = blockIdx.x;
+  const bool on = !active || active[blk];
+  const float s = *scale;
+  const size_t b0 = (size_t)blk * 128 * H, b1 = min((size_t)rows, (size_t)(blk + 1) * 128) * H;
+  for (size_t i = b0 + threadIdx.x * 4; i < b1; i += blockDim.x * 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) v = *reinterpret_cast<const float4*>(x + i);
+    __half h[4], l[4];
+    split_half(v.x * s, h[0], l[0]); split_half(v.y * s, h[1], l[1]);
+    split_half(v.z * s, h[2], l[2]); split_half(v.w * s, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// backward products: sc[0] = |dZ|max bits -> sc[1] = s_g, sc[2] = 1 / (s_g * *other_scale)
+__global__ void bwd_scales_kernel(float* __restrict__ sc, const float* __restrict__ other_scale) {   // one thread
+  const float m = __uint_as_float(reinterpret_cast<const unsigned*>(sc)[0]);
+  const float sg = m > 0.f ? pow2_floor_scale(m) : 1.0f;
+  sc[1] = sg;
+  sc[2] = 1.0f / (sg * *other_scale);
+}
+
 __global__ void debug_scales_kernel(float* __restrict__ sc) {   // one thread (tc_debug_gemm)
   const unsigned* b = reinterpret_cast<const unsigned*>(sc);
   sc[0] = pow2_floor_scale(__uint_as_float(b[4]));
@@ -125,10 +172,6 @@ __global__ void debug_scales_kernel(float* __restrict__ sc) {   // one thread (t
   sc[2] = 1.0f / (sc[0] * sc[1]);
 }
 
-__device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn(x - __half2float(hi));
-}
 
 // Wt_hi/lo[n][k] (fp16, [N, Kp], zero beyond K) from W[k][n] times *scale
 __global__ void transpose_split_f16_kernel(const float* __restrict__ w, int K, int Kp, int N, const float* __restrict__ scale,
@@ -258,7 +301,7 @@ static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const C
     DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
     attr_done = true;
   }
-  DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : "tc_gemm2_dense_f16"), st,
+  DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
              tc_gemm2_kernel<GATHER><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
   DPD_CUDA_CHECK_LAUNCH("tc_gemm2_kernel");
   return 0;
@@ -278,9 +321,22 @@ static bool fuse_l4() {
   return v != 0;
 }
 
+// optional backward-pass behaviour of launch2 (see KernelArgs)
+struct BwdExtras {
+  int mode = 0;
+  const void* gate_hi = nullptr;
+  const void* gate_lo = nullptr;
+  const int* active = nullptr;
+  int slices = 1;
+  const int* k_limit = nullptr;
+  long long slice_stride = 0;
+  const char* name = nullptr;
+};
+
 static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo, int N,
                    const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
-                   const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr) {
+                   const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr,
+                   const BwdExtras* bx = nullptr) {
   DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -298,7 +354,15 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
   ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4;
   if (g) ka.g = *g;
-  const int tiles = ceil_div(M, 2 * BM) * (N / BN);
+  int tiles = ceil_div(M, 2 * BM) * (N / BN);
+  if (bx) {
+    DPD_REQUIRE(!gather && !split && part4 == nullptr, DPD_E_UNSUPPORTED, "tc gemm2: backward modes need the dense fp32-output kernel");
+    ka.mode = bx->mode; ka.gate_hi = bx->gate_hi; ka.gate_lo = bx->gate_lo; ka.active = bx->active; ka.k_limit = bx->k_limit;
+    ka.slices = bx->slices; ka.slice_stride = bx->slice_stride;
+    // K-blocks per slice: a multiple of the promotion segment so that segments never straddle slices
+    ka.kb_per_slice = round_up(ceil_div(K / 64, bx->slices > 1 ? bx->slices : 1), 4);
+    tiles *= bx->slices > 1 ? bx->slices : 1;
+  }
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + 2 * (size_t)(K / 4) * sizeof(uint32_t);
   return gather ? launch2_t<true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st)
@@ -352,16 +416,29 @@ namespace {
 size_t up256(size_t x) { return round_up<size_t>(x, 256); }
 int kp1_of(const dpd_head_config& c, bool f16) { return round_up(c.k * c.k * c.k * c.C + 3, f16 ? 64 : 32); }
 
-struct TcBlob { size_t w1h, w1l, w2h, w2l, w3h, w3l, scales, total; };
+bool tc_train(const dpd_head_config& c) { return (c.flags & DPD_HEAD_TRAIN) != 0; }
+// tensor-core backward: fp16x3 2-CTA kernel only (DPD_TC_BWD=0 keeps the fp32 SIMT backward for A/B measurements)
+bool tc_bwd_env() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DPD_TC_BWD"); v = e ? (atoi(e) != 0) : 1; }
+  return v != 0;
+}
+
+struct TcBlob { size_t w1h, w1l, w2h, w2l, w3h, w3l, w2nh, w2nl, w3nh, w3nl, scales, total; };
 TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
   TcBlob b; size_t o = 0; const size_t H = c.H, e = f16 ? 2 : 4, Kp1 = kp1_of(c, f16);
   b.w1h = o; o += up256(H * Kp1 * e); b.w1l = o; o += up256(H * Kp1 * e);
   b.w2h = o; o += up256(H * H * e);   b.w2l = o; o += up256(H * H * e);
   b.w3h = o; o += up256(H * H * e);   b.w3l = o; o += up256(H * H * e);
+  b.w2nh = b.w2nl = b.w3nh = b.w3nl = o;
+  if (f16 && tc_train(c)) {   // W2, W3 as stored ([K_in, K_out] = the K-major B operand of dX = dZ . W^T)
+    b.w2nh = o; o += up256(H * H * e); b.w2nl = o; o += up256(H * H * e);
+    b.w3nh = o; o += up256(H * H * e); b.w3nl = o; o += up256(H * H * e);
+  }
   b.scales = o; o += up256(tc::P_COUNT * 4);
   b.total = o; return b;
 }
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, scales, total; };
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, bsc, scales, total; };
 TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -370,6 +447,11 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
   w.yh = w.yl = o;
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
+  w.gh = w.gl = w.bsc = o;
+  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, per-product scales
+    w.gh = o; o += up256(rows * (size_t)c.H * e); w.gl = o; o += up256(rows * (size_t)c.H * e);
+    w.bsc = o; o += up256(64 * 4);
+  }
   w.scales = o; o += up256(tc::S_COUNT * 4);
   w.total = o; return w;
 }
@@ -413,8 +495,44 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
       w2, H, H, H, ps + tc::P_W2, (__half*)(base + b.w2h), (__half*)(base + b.w2l)));
   DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
       w3, H, H, H, ps + tc::P_W3, (__half*)(base + b.w3h), (__half*)(base + b.w3l)));
+  if (tc_train(c)) {
+    const size_t n2e = (size_t)H * H;
+    DPD_LAUNCH("tc_pack_w", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(n2e, 256), 256, 0, st>>>(
+        w2, n2e, ps + tc::P_W2, (__half*)(base + b.w2nh), (__half*)(base + b.w2nl)));
+    DPD_LAUNCH("tc_pack_w", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(n2e, 256), 256, 0, st>>>(
+        w3, n2e, ps + tc::P_W3, (__half*)(base + b.w3nh), (__half*)(base + b.w3nl)));
+  }
   DPD_CUDA_CHECK_LAUNCH("tc_pack_weights f16");
   return 0;
+}
+
+bool tc_backward_supported(const dpd_head_config& c, bool f16) { return f16 && tc::use_2cta() && tc_bwd_env() && tc_train(c); }
+
+// dZ_out = (dZ_in . W^T) * ReLU'(H) for layer 3 (H = H2, W = W3) or layer 2 (H = H1, W = W2) on the tensor cores:
+// dZ_in is measured (|.|max), scaled by a power of two and split into an fp16 (hi, lo) pair; the product runs through
+// the forward GEMM kernel with B = W as stored (its rows are K-major for this product) and the gate epilogue.
+int tc_backward_dx(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
+                   const float* dz_in, float* dz_out, const int* active, cudaStream_t st) {
+  const TcBlob b = tc_blob_layout(c, true);
+  const TcWs w = tc_ws_layout(c, true, ws_rows);
+  const char* blob = (const char*)tc_blob;
+  char* ws = (char*)tc_ws;
+  const int H = c.H;
+  float* bsc = (float*)(ws + w.bsc);      // [0] |dZ|max bits  [1] s_g  [2] 1 / (s_g * s_W)
+  const float* ps = (const float*)(blob + b.scales);
+  DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
+  const int nblk = ceil_div(rows, 128);
+  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<nblk, 256, 0, st>>>(dz_in, rows, H, active, (unsigned*)bsc));
+  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, ps + (layer == 3 ? tc::P_W3 : tc::P_W2)));
+  DPD_LAUNCH("bwd_split", st, tc::split_f16_active_kernel<<<nblk, 256, 0, st>>>(
+      dz_in, rows, H, active, bsc + 1, (__half*)(ws + w.gh), (__half*)(ws + w.gl)));
+  DPD_CUDA_CHECK_LAUNCH("tc_backward_dx prep");
+  tc::BwdExtras bx;
+  bx.mode = 1; bx.active = active;
+  bx.gate_hi = ws + (layer == 3 ? w.yh : w.xh); bx.gate_lo = ws + (layer == 3 ? w.yl : w.xl);
+  return tc::launch2(false, ws + w.gh, ws + w.gl, rows, H, blob + (layer == 3 ? b.w3nh : b.w2nh),
+                     blob + (layer == 3 ? b.w3nl : b.w2nl), H, nullptr, dz_out, nullptr, 0, bsc + 2, nullptr, nullptr, st,
+                     nullptr, nullptr, &bx);
 }
 
 // mode 0: foreign fv (measure |fv|max, split)   1: |fv| <= 1 known (3DmFV output), split here

@@ -33,6 +33,11 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
 int tc_merge_activations(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, int rows, float* ha, float* hb,
                          cudaStream_t st);
 
+// tensor-core backward (fp16x3, 2-CTA kernel, training configuration)
+bool tc_backward_supported(const dpd_head_config& c, bool f16);
+int tc_backward_dx(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
+                   const float* dz_in, float* dz_out, const int* active, cudaStream_t st);
+
 int tc_debug_gemm(const float* a, int M, int K, const float* w, int N, const float* bias, float* out, void* scratch,
                   size_t scratch_bytes, int f16, cudaStream_t st);
 

@@ -41,6 +41,15 @@ struct KernelArgs {
   // each (N-tile, column half) instead writes its share of H3 . W4 as one float4 per row
   const float* w4;         // [N,3] fp32 (reference layout of mapper_conv4/weights)
   float* part4;            // [M, 2*N/BN, 4]
+  // ---- backward-pass extensions (2-CTA kernel, fp32 output only); all zero / nullptr in the forward pass ----
+  int mode;                // 0: relu(acc*scale + bias)   1: acc*scale where the gate is non-zero, else 0   2: acc*scale
+  const void* gate_hi;     // mode 1: (hi, lo) fp16 pair [M,N] of the forward activation; gate = (hi | lo) != 0, i.e. ReLU'
+  const void* gate_lo;
+  const int* active;       // optional per-128-row flags: a 256-row tile with both flags clear is skipped by every role
+  int slices;              // split-K: work items = slices * tiles, item -> (slice, tile); 0 or 1 = no split
+  int kb_per_slice;        // K-blocks per slice
+  const int* k_limit;      // optional device scalar: valid K extent in elements (K-blocks beyond it are not visited)
+  long long slice_stride;  // elements between the fp32 outputs of consecutive slices
   GatherArgs g;
 };
 

@@ -100,6 +100,18 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int num_m_tiles = (args.M + 2 * BM - 1) / (2 * BM);
   const int num_n_tiles = args.N / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
+  // work items: (slice, tile).  Forward: one slice covering all K-blocks.  Backward weight gradients split the long
+  // reduction axis into slices whose partial results are summed afterwards in a fixed order.
+  const int num_slices = args.slices > 1 ? args.slices : 1;
+  const int num_items = num_tiles * num_slices;
+  const int nkb_eff = args.k_limit ? min(args.num_kb, (__ldg(args.k_limit) + KB_ELEMS - 1) / KB_ELEMS) : args.num_kb;
+  const int kbps = num_slices > 1 ? args.kb_per_slice : args.num_kb;
+  const int num_row_blocks = (args.M + BM - 1) / BM;
+  auto item_skipped = [&](int mt) -> bool {
+    if (args.active == nullptr) return false;
+    const int b0 = 2 * mt;
+    return !__ldg(args.active + b0) && !(b0 + 1 < num_row_blocks && __ldg(args.active + b0 + 1));
+  };
 
   auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 Ah, 1 Al, 2 Bh (half), 3 Bl (half)
     uint8_t* b = smem + s * STAGE2_BYTES;
@@ -153,11 +165,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
       int s = 0; uint32_t ph = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int t = w % num_tiles, sl = w / num_tiles;
         const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+        if (item_skipped(mt)) continue;
         const int row0 = mt * 2 * BM + (int)rank * BM;
         const int brow0 = nt * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < args.num_kb; ++kb) {
+        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&ctl->empty[s], ph ^ 1);
           const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
@@ -174,13 +189,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       // ===================== MMA issuer (leader only) =====================
       int s = 0; uint32_t ph = 0;
       int sb = 0; uint32_t sb_ph = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG) {
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int t = w % num_tiles, sl = w / num_tiles;
+        if (item_skipped(t / num_n_tiles)) continue;
+        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += SEG) {
           mbar_wait_cluster(&ctl->seg_empty[sb], sb_ph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
           uint32_t accumulate = 0;
-          const int kb1 = min(kb0 + SEG, args.num_kb);
+          const int kb1 = min(kb0 + SEG, kb_hi);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait_cluster(&ctl->full[s], ph);
             tc_fence_after();
@@ -206,8 +224,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     } else if (GATHER && warp == 3 && lane == 0 && !leader) {
       // ===================== gather relay (peer only): local gfull[s] -> leader's full[s] =====================
       int s = 0; uint32_t ph = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        for (int kb = 0; kb < args.num_kb; ++kb) {
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int t = w % num_tiles, sl = w / num_tiles;
+        if (item_skipped(t / num_n_tiles)) continue;
+        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&ctl->gfull[s], ph);
           fence_proxy_async();
           mbar_arrive_remote(map_to_rank(smem_u32(&ctl->full[s]), 0));
@@ -225,11 +246,18 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const float out_scale = args.out_scale ? __ldg(args.out_scale) : 1.0f;
     int sb = 0; uint32_t sb_ph = 0;
     float sum[EPI_COLS];
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+    for (int w = cluster_id; w < num_items; w += num_clusters) {
+      const int t = w % num_tiles, sl = w / num_tiles;
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+      if (item_skipped(mt)) continue;
       const int row_base = mt * 2 * BM + (int)rank * BM;
+      const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
       bool first = true;
-      for (int kb0 = 0; kb0 < args.num_kb; kb0 += SEG) {
+      if (kb_lo >= kb_hi) {          // an empty slice (k_limit cut it off) contributes zeros
+#pragma unroll
+        for (int j = 0; j < EPI_COLS; ++j) sum[j] = 0.f;
+      }
+      for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += SEG) {
         mbar_wait(&ctl->seg_full[sb], sb_ph);
         tc_fence_after();
 #pragma unroll
@@ -367,7 +395,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int col = col0 + cg * 64 + j * 8;
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+            const float2 bb = args.bias ? __ldg(reinterpret_cast<const float2*>(args.bias + col)) : make_float2(0.f, 0.f);
 #pragma unroll
             for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
@@ -375,8 +403,20 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const int row = row_base + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
                 if (row < args.M) {
                   const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
-                  const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
-                  *reinterpret_cast<float2*>((float*)args.out0 + (size_t)row * args.N + col) = make_float2(x0, x1);
+                  const size_t o = (size_t)row * args.N + col;
+                  float x0, x1;
+                  if (args.mode == 0) {
+                    x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f); x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
+                  } else {
+                    x0 = sp[0] * acc_scale; x1 = sp[1] * acc_scale;
+                    if (args.mode == 1) {      // ReLU' of the forward activation: non-zero (hi | lo), sign bits ignored
+                      const uint32_t gb = (__ldg(reinterpret_cast<const uint32_t*>((const __half*)args.gate_hi + o)) |
+                                           __ldg(reinterpret_cast<const uint32_t*>((const __half*)args.gate_lo + o))) & 0x7fff7fffu;
+                      if ((gb & 0xffffu) == 0) x0 = 0.f;
+                      if ((gb >> 16) == 0) x1 = 0.f;
+                    }
+                  }
+                  *reinterpret_cast<float2*>((float*)args.out0 + (size_t)sl * (size_t)args.slice_stride + o) = make_float2(x0, x1);
                 }
               }
             }
@@ -398,8 +438,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const uint8_t* o4_hi = (const uint8_t*)g.off4_hi; const uint8_t* o4_lo = (const uint8_t*)g.off4_lo;
     const uint32_t lut_s = smem_u32(lut), lutd_s = lut_s + (uint32_t)(args.num_kb * CHUNKS) * 4u;
     int s = 0; uint32_t ph = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+    for (int w = cluster_id; w < num_items; w += num_clusters) {
+      const int t = w % num_tiles;
       const int mt = t / num_n_tiles;
+      if (item_skipped(mt)) continue;
       const int row_base = mt * 2 * BM + (int)rank * BM;
       int32_t rel[NIT];
       uint32_t rmsk[NIT];
