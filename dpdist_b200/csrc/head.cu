@@ -360,7 +360,7 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
   float* H2 = hb;
 
   if (all || stage == DPD_BWD_L4) {
-    if (is_tc(L.impl) && (rc = tc_merge_activations(*cfg, is_f16(L.impl), ws + W.tc, chunk, rows, ha, hb, st))) return rc;
+    if (is_tc(L.impl) && !tc_bwd && (rc = tc_merge_activations(*cfg, is_f16(L.impl), ws + W.tc, chunk, rows, ha, hb, st))) return rc;
     if ((rc = launch_row_active(d_grad_out, rows, active, st))) return rc;
     if ((rc = launch_out_backward(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
                                   d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st))) return rc;
@@ -370,19 +370,28 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
   tp.M = rows; tp.N = H; tp.active = active; tp.partial = part; tp.partial_bias = part_bias; tp.lda = H;
   SimtGemmParams gp;
   gp.M = rows; gp.N = H; gp.Kp = H; gp.relu = 0; gp.bias = nullptr; gp.lda = H; gp.active = active;
+  if (tc_bwd) {
+    // tensor-core backward: every product of a layer in tc_backward_layer (head_tc.cu)
+    if (all || stage == DPD_BWD_L3)
+      if ((rc = tc_backward_layer(*cfg, 3, pk + L.tc, ws + W.tc, chunk, rows, nullptr, g0, g1, active, d_gw3, d_gb3, st))) return rc;
+    if (all || stage == DPD_BWD_L2)
+      if ((rc = tc_backward_layer(*cfg, 2, pk + L.tc, ws + W.tc, chunk, rows, nullptr, g1, g0, active, d_gw2, d_gb2, st))) return rc;
+    if ((all || stage == DPD_BWD_L1) && d_gw1) {
+      GatherDesc g;
+      g.fv = d_fv; g.idx = (const int32_t*)(ws + W.idx); g.offset = (const float*)(ws + W.off); g.row0 = 0;
+      g.n_query = cfg->n_query; g.G = cfg->G; g.C = cfg->C; g.k = cfg->k; g.E = L.E;
+      if ((rc = tc_backward_layer(*cfg, 1, pk + L.tc, ws + W.tc, chunk, rows, &g, g0, nullptr, active, d_gw1, d_gb1, st))) return rc;
+    }
+    return 0;
+  }
   if (all || stage == DPD_BWD_L3) {
     tp.A = H2; tp.B = g0; tp.Kp = H;
     if (d_gw3) {
       if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
       if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw3, d_gb3, st))) return rc;
     }
-    // dZ2 = (dZ3 . W3^T) * (H2 > 0)
-    if (tc_bwd) {
-      if ((rc = tc_backward_dx(*cfg, 3, pk + L.tc, ws + W.tc, chunk, rows, g0, g1, active, st))) return rc;
-    } else {
-      gp.A = g0; gp.B = (const float*)(pk + L.w3t); gp.gate = H2; gp.Cout = g1;
-      if ((rc = launch_simt_gemm(gp, false, st))) return rc;
-    }
+    gp.A = g0; gp.B = (const float*)(pk + L.w3t); gp.gate = H2; gp.Cout = g1;     // dZ2 = (dZ3 . W3^T) * (H2 > 0)
+    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
   }
   if (all || stage == DPD_BWD_L2) {
     tp.A = H1; tp.B = g1; tp.Kp = H;
@@ -390,13 +399,8 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
       if ((rc = launch_simt_gemm_tn(tp, false, st))) return rc;
       if ((rc = launch_reduce_partials(part, part_bias, H, H, H, 0, 0, d_gw2, d_gb2, st))) return rc;
     }
-    // dZ1 = (dZ2 . W2^T) * (H1 > 0)
-    if (tc_bwd) {
-      if ((rc = tc_backward_dx(*cfg, 2, pk + L.tc, ws + W.tc, chunk, rows, g1, g0, active, st))) return rc;
-    } else {
-      gp.A = g1; gp.B = (const float*)(pk + L.w2t); gp.gate = H1; gp.Cout = g0;
-      if ((rc = launch_simt_gemm(gp, false, st))) return rc;
-    }
+    gp.A = g1; gp.B = (const float*)(pk + L.w2t); gp.gate = H1; gp.Cout = g0;     // dZ1 = (dZ2 . W2^T) * (H1 > 0)
+    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
   }
   if ((all || stage == DPD_BWD_L1) && d_gw1) {
     GatherDesc g;

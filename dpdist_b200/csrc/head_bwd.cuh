@@ -33,7 +33,7 @@ int launch_simt_gemm_tn(const TnParams& p, bool gather, cudaStream_t st);
 // grad[row_map(k)][n] = sum_s partial[s][k][n]; unpermute != 0 maps packed layer-1 rows (patch | offset | pad)
 // back to the reference's (offset | patch) order and drops the padding rows.
 int launch_reduce_partials(const float* partial, const float* partial_bias, int Kp, int K_valid, int N, int E, int unpermute,
-                           float* gw, float* gb, cudaStream_t st);
+                           float* gw, float* gb, cudaStream_t st, int nslices = BWD_SLICES);
 
 int launch_add_inplace(float* a, const float* b, size_t n, cudaStream_t st);
 

@@ -157,12 +157,142 @@ __global__ void split_f16_active_kernel(const float* __restrict__ x, int rows, i
   }
 }
 
+// out[c][m] = in[m][c] for an fp16 matrix in [rows, H] (row stride H) -> out [H, Mp]; 64x64 tiles through shared memory
+__global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int H, int Mp, __half* __restrict__ out,
+                                     const int* __restrict__ extent) {
+  __shared__ __half tile[64][66];
+  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  if (extent && m0 >= *extent) return;       // rows past the active extent are never read (k_limit of the dW product)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: 32 x 8
+  for (int r = ty; r < 64; r += 8) {
+    const int m = m0 + r;
+    __half2 v = __floats2half2_rn(0.f, 0.f);
+    if (m < rows) v = *reinterpret_cast<const __half2*>(in + (size_t)m * H + c0 + 2 * tx);
+    tile[r][2 * tx] = __low2half(v); tile[r][2 * tx + 1] = __high2half(v);
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8)
+    *reinterpret_cast<__half2*>(out + (size_t)(c0 + c) * Mp + m0 + 2 * tx) = __halves2half2(tile[2 * tx][c], tile[2 * tx + 1][c]);
+}
+
+// One pass over the upstream gradient dz [rows, H] (fp32): the scaled fp16 (hi, lo) pair row-major (operand of
+// dX = dZ . W^T) AND transposed [H, Mp] (operand of dW = A^T . dZ); zeros for inactive 128-row blocks.
+__global__ void split_transpose_f16_kernel(const float* __restrict__ dz, int rows, int H, int Mp, const int* __restrict__ active,
+                                           const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                           __half* __restrict__ thi, __half* __restrict__ tlo, const int* __restrict__ extent) {
+  __shared__ __half th[64][66], tl[64][66];
+  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  if (extent && m0 >= *extent) return;       // past the last active block: neither product reads these rows
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool on = !active || active[m0 >> 7];
+  const float s = *scale;
+  for (int r = ty; r < 64; r += 8) {
+    const int m = m0 + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (on && m < rows) v = *reinterpret_cast<const float2*>(dz + (size_t)m * H + c0 + 2 * tx);
+    __half h0, l0, h1, l1;
+    split_half(v.x * s, h0, l0); split_half(v.y * s, h1, l1);
+    if (m < rows) {
+      *reinterpret_cast<__half2*>(hi + (size_t)m * H + c0 + 2 * tx) = __halves2half2(h0, h1);
+      *reinterpret_cast<__half2*>(lo + (size_t)m * H + c0 + 2 * tx) = __halves2half2(l0, l1);
+    }
+    th[r][2 * tx] = h0; th[r][2 * tx + 1] = h1; tl[r][2 * tx] = l0; tl[r][2 * tx + 1] = l1;
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 8) {
+    const size_t o = (size_t)(c0 + c) * Mp + m0 + 2 * tx;
+    *reinterpret_cast<__half2*>(thi + o) = __halves2half2(th[2 * tx][c], th[2 * tx + 1][c]);
+    *reinterpret_cast<__half2*>(tlo + o) = __halves2half2(tl[2 * tx][c], tl[2 * tx + 1][c]);
+  }
+}
+
+// Transposed layer-1 operand: pt[kk][m] = element kk of the virtual row m = [patch | offset | 0] (same decode as the
+// forward gather producers), from the scaled fp16 FV tensor and offsets.  Block = 64 rows x one 64-element K-block.
+__global__ void gather_transpose_f16_kernel(const GatherArgs g, int rows, int Mp, __half* __restrict__ pth,
+                                            __half* __restrict__ ptl, const int* __restrict__ extent) {
+  __shared__ __half th[64][66], tl[64][66];     // [k within block][row]
+  const int m0 = blockIdx.x * 64, kb = blockIdx.y;
+  if (extent && m0 >= *extent) return;
+  const int G = g.G, Cc = g.C, kk = g.k, pb = (g.k - 1) >> 1, V = G * G * G, ech = g.E / 4;
+  const __half* fv_hi = (const __half*)g.fv_hi; const __half* fv_lo = (const __half*)g.fv_lo;
+  const __half* o4_hi = (const __half*)g.off4_hi; const __half* o4_lo = (const __half*)g.off4_lo;
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+    const int r = i >> 4, chunk = i & 15;
+    const int m = m0 + r, q = kb * 16 + chunk;
+    uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
+    if (m < rows) {
+      if (q < ech) {
+        const int e = q * 4, j = e / Cc, part = e - j * Cc;
+        const int a2 = j % kk, a1 = (j / kk) % kk, a0 = j / (kk * kk);
+        const int v = __ldg(g.idx + m);
+        const int n0 = v / (G * G) + a0 - pb, n1 = (v / G) % G + a1 - pb, n2 = v % G + a2 - pb;
+        if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
+          const long long cloud = (g.row0 + m) / g.n_query;
+          const size_t el = (size_t)cloud * V * Cc + (size_t)((n0 * G + n1) * G + n2) * Cc + part;
+          vh = *reinterpret_cast<const uint2*>(fv_hi + el);
+          vl = *reinterpret_cast<const uint2*>(fv_lo + el);
+        }
+      } else if (q == ech) {
+        vh = *reinterpret_cast<const uint2*>(o4_hi + (size_t)m * 4);
+        vl = *reinterpret_cast<const uint2*>(o4_lo + (size_t)m * 4);
+      }
+    }
+    const __half* ph = reinterpret_cast<const __half*>(&vh);
+    const __half* pl = reinterpret_cast<const __half*>(&vl);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { th[chunk * 4 + e][r] = ph[e]; tl[chunk * 4 + e][r] = pl[e]; }
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 64; c += 8) {
+    const size_t o = (size_t)(kb * 64 + c) * Mp + m0 + 2 * tx;
+    *reinterpret_cast<__half2*>(pth + o) = __halves2half2(th[c][2 * tx], th[c][2 * tx + 1]);
+    *reinterpret_cast<__half2*>(ptl + o) = __halves2half2(tl[c][2 * tx], tl[c][2 * tx + 1]);
+  }
+}
+
+// bias gradients: column sums of dz over the active rows, two deterministic levels (32 row slices, then in order)
+constexpr int COLSUM_SLICES = 32;
+__global__ void colsum_partial_kernel(const float* __restrict__ dz, int rows, int H, const int* __restrict__ active,
+                                      float* __restrict__ partial) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), ty = threadIdx.x >> 6, sl = blockIdx.y;
+  const int nblk = (rows + 127) / 128;
+  float a = 0.f;
+  for (int blk = sl; blk < nblk; blk += COLSUM_SLICES) {
+    if (active && !active[blk]) continue;
+    const int r1 = min(rows, (blk + 1) * 128);
+    for (int r = blk * 128 + ty; r < r1; r += 4) a += dz[(size_t)r * H + c];
+  }
+  red[ty][threadIdx.x & 63] = a;
+  __syncthreads();
+  if (ty == 0) partial[(size_t)sl * H + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int H, float* __restrict__ gb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float a = 0.f;
+  for (int s = 0; s < COLSUM_SLICES; ++s) a += partial[(size_t)s * H + c];
+  gb[c] = a;
+}
+
+// rows covered by the active blocks: (index of the last active 128-row block + 1) * 128, clipped to `rows`
+__global__ void active_extent_kernel(const int* __restrict__ active, int nblk, int rows, int* __restrict__ out) {   // one warp
+  int last = -1;
+  for (int b = threadIdx.x; b < nblk; b += 32) if (active[b]) last = b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (threadIdx.x == 0) *out = min(rows, (last + 1) * 128);
+}
+
 // backward products: sc[0] = |dZ|max bits -> sc[1] = s_g, sc[2] = 1 / (s_g * *other_scale)
-__global__ void bwd_scales_kernel(float* __restrict__ sc, const float* __restrict__ other_scale) {   // one thread
+// and sc[3] = 1 / (s_g * *act_scale) for the weight-gradient product
+__global__ void bwd_scales_kernel(float* __restrict__ sc, const float* __restrict__ other_scale, const float* __restrict__ act_scale) {   // one thread
   const float m = __uint_as_float(reinterpret_cast<const unsigned*>(sc)[0]);
   const float sg = m > 0.f ? pow2_floor_scale(m) : 1.0f;
   sc[1] = sg;
-  sc[2] = 1.0f / (sg * *other_scale);
+  sc[2] = other_scale ? 1.0f / (sg * *other_scale) : 0.f;
+  sc[3] = 1.0f / (sg * *act_scale);
 }
 
 __global__ void debug_scales_kernel(float* __restrict__ sc) {   // one thread (tc_debug_gemm)
@@ -338,7 +468,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
                    const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr,
                    const BwdExtras* bx = nullptr) {
   DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
-  DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
+  DPD_REQUIRE(!gather || K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if ((rc = make_tmap(&tb_hi, bt_hi, true, N, K, BN / 2))) return rc;
@@ -364,7 +494,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
     tiles *= bx->slices > 1 ? bx->slices : 1;
   }
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + 2 * (size_t)(K / 4) * sizeof(uint32_t);
+  const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + (gather ? 2 * (size_t)(K / 4) * sizeof(uint32_t) : 0);
   return gather ? launch2_t<true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st)
                 : launch2_t<false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st);
 }
@@ -438,7 +568,9 @@ TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
   b.scales = o; o += up256(tc::P_COUNT * 4);
   b.total = o; return b;
 }
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, bsc, scales, total; };
+constexpr int TC_DW_SLICES = 9;       // dW2 / dW3: 16 tiles x 9 slices = 144 work items on 74 clusters (1.95 waves)
+constexpr int TC_DW1_SLICES = 11;     // dW1: 40 tiles x 11 = 440 (5.95 waves)
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, gth, gtl, hth, htl, pth, ptl, part, cpart, bsc, scales, total; };
 TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -447,9 +579,15 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
   w.yh = w.yl = o;
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
-  w.gh = w.gl = w.bsc = o;
-  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, per-product scales
-    w.gh = o; o += up256(rows * (size_t)c.H * e); w.gl = o; o += up256(rows * (size_t)c.H * e);
+  w.gh = w.gl = w.gth = w.gtl = w.hth = w.htl = w.pth = w.ptl = w.part = w.cpart = w.bsc = o;
+  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient (row-major and transposed), transposed
+    const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);        // activations / patches, partials
+    w.gh = o; o += act; w.gl = o; o += act; w.gth = o; o += act; w.gtl = o; o += act;
+    w.hth = o; o += act; w.htl = o; o += act;
+    w.pth = o; o += up256(rows * Kp1 * e); w.ptl = o; o += up256(rows * Kp1 * e);
+    const size_t p1 = (size_t)TC_DW1_SLICES * Kp1 * c.H * 4, p2 = (size_t)TC_DW_SLICES * c.H * c.H * 4;
+    w.part = o; o += up256(p1 > p2 ? p1 : p2);
+    w.cpart = o; o += up256((size_t)tc::COLSUM_SLICES * c.H * 4);
     w.bsc = o; o += up256(64 * 4);
   }
   w.scales = o; o += up256(tc::S_COUNT * 4);
@@ -508,31 +646,79 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
 
 bool tc_backward_supported(const dpd_head_config& c, bool f16) { return f16 && tc::use_2cta() && tc_bwd_env() && tc_train(c); }
 
-// dZ_out = (dZ_in . W^T) * ReLU'(H) for layer 3 (H = H2, W = W3) or layer 2 (H = H1, W = W2) on the tensor cores:
-// dZ_in is measured (|.|max), scaled by a power of two and split into an fp16 (hi, lo) pair; the product runs through
-// the forward GEMM kernel with B = W as stored (its rows are K-major for this product) and the gate epilogue.
-int tc_backward_dx(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
-                   const float* dz_in, float* dz_out, const int* active, cudaStream_t st) {
+// One layer of the backward pass on the tensor cores (fp16x3, 2-CTA kernel), layer = 3, 2 or 1:
+//   gw = A^T . dZ   with A = H2 (layer 3), H1 (layer 2) or the gathered layer-1 operand (layer 1); gb = column sums of dZ
+//   dz_next = (dZ . W^T) * ReLU'(A)                                              (layers 3 and 2 only)
+// dZ (fp32) is measured over its active row blocks, scaled by a power of two and split once into fp16 (hi, lo) pairs,
+// row-major for the dX product and transposed for the dW product.  Both products run through the forward GEMM kernel:
+// dX with B = W as stored (K-major for this product) and the ReLU' gate in the epilogue; dW as A^T[k, m] . dZ^T[n, m]
+// over the row axis, split into slices of the active extent whose fp32 partials are summed in a fixed order.
+int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
+                      const GatherDesc* g, const float* dz, float* dz_next, const int* active, float* gw, float* gb,
+                      cudaStream_t st) {
   const TcBlob b = tc_blob_layout(c, true);
   const TcWs w = tc_ws_layout(c, true, ws_rows);
   const char* blob = (const char*)tc_blob;
   char* ws = (char*)tc_ws;
-  const int H = c.H;
-  float* bsc = (float*)(ws + w.bsc);      // [0] |dZ|max bits  [1] s_g  [2] 1 / (s_g * s_W)
-  const float* ps = (const float*)(blob + b.scales);
-  DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
+  const int H = c.H, Kp1 = kp1_of(c, true);
+  const int Mp = round_up(rows, 128);
   const int nblk = ceil_div(rows, 128);
-  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<nblk, 256, 0, st>>>(dz_in, rows, H, active, (unsigned*)bsc));
-  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, ps + (layer == 3 ? tc::P_W3 : tc::P_W2)));
-  DPD_LAUNCH("bwd_split", st, tc::split_f16_active_kernel<<<nblk, 256, 0, st>>>(
-      dz_in, rows, H, active, bsc + 1, (__half*)(ws + w.gh), (__half*)(ws + w.gl)));
-  DPD_CUDA_CHECK_LAUNCH("tc_backward_dx prep");
-  tc::BwdExtras bx;
-  bx.mode = 1; bx.active = active;
-  bx.gate_hi = ws + (layer == 3 ? w.yh : w.xh); bx.gate_lo = ws + (layer == 3 ? w.yl : w.xl);
-  return tc::launch2(false, ws + w.gh, ws + w.gl, rows, H, blob + (layer == 3 ? b.w3nh : b.w2nh),
-                     blob + (layer == 3 ? b.w3nl : b.w2nl), H, nullptr, dz_out, nullptr, 0, bsc + 2, nullptr, nullptr, st,
-                     nullptr, nullptr, &bx);
+  float* bsc = (float*)(ws + w.bsc);      // [0] |dZ|max bits  [1] s_g  [2] 1/(s_g s_W)  [3] 1/(s_g s_A)  [8] active extent (int)
+  int* extent = (int*)(bsc + 8);
+  const float* ps = (const float*)(blob + b.scales);
+  const float* sc = (const float*)(ws + w.scales);
+  const float* act_scale = sc + (layer == 3 ? tc::S_A3 : layer == 2 ? tc::S_A2 : tc::S_A1);
+  const float* w_scale = layer == 3 ? ps + tc::P_W3 : layer == 2 ? ps + tc::P_W2 : nullptr;
+  __half* gh = (__half*)(ws + w.gh); __half* gl = (__half*)(ws + w.gl);
+  __half* gth = (__half*)(ws + w.gth); __half* gtl = (__half*)(ws + w.gtl);
+  DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
+  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<nblk, 256, 0, st>>>(dz, rows, H, active, (unsigned*)bsc));
+  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, w_scale, act_scale));
+  DPD_LAUNCH("bwd_scales", st, tc::active_extent_kernel<<<1, 32, 0, st>>>(active, nblk, rows, extent));
+  DPD_LAUNCH("bwd_split_transpose", st, tc::split_transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(
+      dz, rows, H, Mp, active, bsc + 1, gh, gl, gth, gtl, extent));
+  DPD_CUDA_CHECK_LAUNCH("tc_backward_layer prep");
+  int rc;
+  if (gw != nullptr) {
+    const __half* ath; const __half* atl;
+    int Mo;       // rows of the weight gradient in kernel order
+    if (layer == 1) {
+      tc::GatherArgs ga;
+      ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g->idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g->row0;
+      ga.n_query = g->n_query; ga.G = g->G; ga.C = g->C; ga.k = g->k; ga.E = g->E;
+      DPD_LAUNCH("bwd_gather_transpose", st, tc::gather_transpose_f16_kernel<<<dim3(Mp / 64, Kp1 / 64), 256, 0, st>>>(
+          ga, rows, Mp, (__half*)(ws + w.pth), (__half*)(ws + w.ptl), extent));
+      ath = (const __half*)(ws + w.pth); atl = (const __half*)(ws + w.ptl); Mo = Kp1;
+    } else {
+      const __half* sh = (const __half*)(ws + (layer == 3 ? w.yh : w.xh));
+      const __half* sl = (const __half*)(ws + (layer == 3 ? w.yl : w.xl));
+      DPD_LAUNCH("bwd_transpose", st, tc::transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(sh, rows, H, Mp, (__half*)(ws + w.hth), extent));
+      DPD_LAUNCH("bwd_transpose", st, tc::transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(sl, rows, H, Mp, (__half*)(ws + w.htl), extent));
+      ath = (const __half*)(ws + w.hth); atl = (const __half*)(ws + w.htl); Mo = H;
+    }
+    DPD_CUDA_CHECK_LAUNCH("tc_backward_layer transposes");
+    tc::BwdExtras bx;
+    bx.mode = 2; bx.slices = layer == 1 ? TC_DW1_SLICES : TC_DW_SLICES; bx.k_limit = extent; bx.slice_stride = (long long)Mo * H;
+    float* part = (float*)(ws + w.part);
+    if ((rc = tc::launch2(false, ath, atl, Mo, Mp, gth, gtl, H, nullptr, part, nullptr, 0, bsc + 3, nullptr, nullptr, st, nullptr,
+                          nullptr, &bx))) return rc;
+    // gb = column sums of dZ over the active rows
+    float* cpart = (float*)(ws + w.cpart);
+    DPD_LAUNCH("bwd_colsum", st, tc::colsum_partial_kernel<<<dim3(H / 64, tc::COLSUM_SLICES), 256, 0, st>>>(dz, rows, H, active, cpart));
+    DPD_LAUNCH("bwd_colsum", st, tc::colsum_final_kernel<<<ceil_div(H, 256), 256, 0, st>>>(cpart, H, gb));
+    DPD_CUDA_CHECK_LAUNCH("tc_backward_layer colsum");
+    if (layer == 1) rc = launch_reduce_partials(part, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices);
+    else rc = launch_reduce_partials(part, nullptr, H, H, H, 0, 0, gw, nullptr, st, bx.slices);
+    if (rc) return rc;
+  }
+  if (dz_next != nullptr) {
+    tc::BwdExtras bx;
+    bx.mode = 1; bx.active = active;
+    bx.gate_hi = ws + (layer == 3 ? w.yh : w.xh); bx.gate_lo = ws + (layer == 3 ? w.yl : w.xl);
+    if ((rc = tc::launch2(false, gh, gl, rows, H, blob + (layer == 3 ? b.w3nh : b.w2nh), blob + (layer == 3 ? b.w3nl : b.w2nl), H,
+                          nullptr, dz_next, nullptr, 0, bsc + 2, nullptr, nullptr, st, nullptr, nullptr, &bx))) return rc;
+  }
+  return 0;
 }
 
 // mode 0: foreign fv (measure |fv|max, split)   1: |fv| <= 1 known (3DmFV output), split here

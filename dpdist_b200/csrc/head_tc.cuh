@@ -35,8 +35,10 @@ int tc_merge_activations(const dpd_head_config& c, bool f16, void* tc_ws, size_t
 
 // tensor-core backward (fp16x3, 2-CTA kernel, training configuration)
 bool tc_backward_supported(const dpd_head_config& c, bool f16);
-int tc_backward_dx(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
-                   const float* dz_in, float* dz_out, const int* active, cudaStream_t st);
+// one layer (3, 2 or 1) of the backward pass: gw / gb (skipped when gw == nullptr) and, for layers 3 and 2, dz_next
+int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
+                      const GatherDesc* g, const float* dz, float* dz_next, const int* active, float* gw, float* gb,
+                      cudaStream_t st);
 
 int tc_debug_gemm(const float* a, int M, int K, const float* w, int N, const float* bias, float* out, void* scratch,
                   size_t scratch_bytes, int f16, cudaStream_t st);

@@ -105,7 +105,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int num_slices = args.slices > 1 ? args.slices : 1;
   const int num_items = num_tiles * num_slices;
   const int nkb_eff = args.k_limit ? min(args.num_kb, (__ldg(args.k_limit) + KB_ELEMS - 1) / KB_ELEMS) : args.num_kb;
-  const int kbps = num_slices > 1 ? args.kb_per_slice : args.num_kb;
+  // with a device-side K limit the slices divide the VALID extent evenly (multiples of the promotion segment)
+  const int kbps = num_slices > 1 ? (args.k_limit ? ((nkb_eff + num_slices - 1) / num_slices + SEG - 1) / SEG * SEG : args.kb_per_slice)
+                                  : args.num_kb;
   const int num_row_blocks = (args.M + BM - 1) / BM;
   auto item_skipped = [&](int mt) -> bool {
     if (args.active == nullptr) return false;
