@@ -117,7 +117,10 @@ WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
     W.part_bias = o; o += up((size_t)BWD_SLICES * H * 4);
     W.part4 = o; o += up((size_t)OUT_BWD_CTAS * (H * 3 + 3) * 4);
     W.dx1 = o;
-    if (L.input_grad) o += up((size_t)input_grad_group_clouds(c) * c.n_query * L.Kp1 * 4);
+    if (L.input_grad) {
+      const size_t ld = is_tc(L.impl) && is_f16(L.impl) && tc_kp1(c) > L.Kp1 ? (size_t)tc_kp1(c) : (size_t)L.Kp1;   // tensor-core dX1: ld 2560
+      o += up((size_t)input_grad_group_clouds(c) * c.n_query * ld * 4);
+    }
   }
   W.tc = o;
   if (is_tc(L.impl)) o += up(tc_workspace_bytes(c, is_f16(L.impl), rows));
@@ -437,14 +440,22 @@ extern "C" int dpd_head_backward_inputs(const dpd_head_config* cfg, const void* 
   const int* active = (const int*)(ws + W.active);
   float* dx1 = (float*)(ws + W.dx1);
   const int cpg = input_grad_group_clouds(*cfg);
+  // the tensor-core product needs its N extent (the padded layer-1 width) to be a whole number of 256-column tiles
+  const bool tc_bwd = is_tc(L.impl) && tc_backward_supported(*cfg, is_f16(L.impl)) && tc_kp1(*cfg) % 256 == 0;
+  if (tc_bwd && (rc = tc_backward_inputs_prepare(*cfg, pk + L.tc, ws + W.tc, chunk, (int)M, dz1, active, st))) return rc;
+  const int ldx = tc_bwd ? tc_kp1(*cfg) : L.Kp1;
   for (int c0 = 0; c0 < cfg->n_clouds; c0 += cpg) {
     const int nc = cfg->n_clouds - c0 < cpg ? cfg->n_clouds - c0 : cpg;
     const size_t r0 = (size_t)c0 * cfg->n_query;       // multiple of 128 by construction
-    SimtGemmParams gp;
-    gp.A = dz1 + r0 * H; gp.lda = H; gp.B = (const float*)(pk + L.w1pt); gp.bias = nullptr; gp.Cout = dx1;
-    gp.M = nc * cfg->n_query; gp.N = L.Kp1; gp.Kp = H; gp.relu = 0; gp.gate = nullptr; gp.active = active + r0 / 128;
-    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
-    if ((rc = launch_patch_scatter(dx1, L.Kp1, (const int32_t*)(ws + W.idx), active, c0, nc, cfg->n_query, cfg->G, cfg->C, cfg->k,
+    if (tc_bwd) {
+      if ((rc = tc_backward_inputs_rows(*cfg, pk + L.tc, ws + W.tc, chunk, r0, nc * cfg->n_query, active, dx1, st))) return rc;
+    } else {
+      SimtGemmParams gp;
+      gp.A = dz1 + r0 * H; gp.lda = H; gp.B = (const float*)(pk + L.w1pt); gp.bias = nullptr; gp.Cout = dx1;
+      gp.M = nc * cfg->n_query; gp.N = L.Kp1; gp.Kp = H; gp.relu = 0; gp.gate = nullptr; gp.active = active + r0 / 128;
+      if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    }
+    if ((rc = launch_patch_scatter(dx1, ldx, (const int32_t*)(ws + W.idx), active, c0, nc, cfg->n_query, cfg->G, cfg->C, cfg->k,
                                    d_grad_fv, d_grad_query, st))) return rc;
   }
   return 0;

@@ -554,7 +554,7 @@ bool tc_bwd_env() {
   return v != 0;
 }
 
-struct TcBlob { size_t w1h, w1l, w2h, w2l, w3h, w3l, w2nh, w2nl, w3nh, w3nl, scales, total; };
+struct TcBlob { size_t w1h, w1l, w2h, w2l, w3h, w3l, w2nh, w2nl, w3nh, w3nl, w1nh, w1nl, scales, total; };
 TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
   TcBlob b; size_t o = 0; const size_t H = c.H, e = f16 ? 2 : 4, Kp1 = kp1_of(c, f16);
   b.w1h = o; o += up256(H * Kp1 * e); b.w1l = o; o += up256(H * Kp1 * e);
@@ -564,6 +564,10 @@ TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
   if (f16 && tc_train(c)) {   // W2, W3 as stored ([K_in, K_out] = the K-major B operand of dX = dZ . W^T)
     b.w2nh = o; o += up256(H * H * e); b.w2nl = o; o += up256(H * H * e);
     b.w3nh = o; o += up256(H * H * e); b.w3nl = o; o += up256(H * H * e);
+  }
+  b.w1nh = b.w1nl = o;
+  if (f16 && tc_train(c) && (c.flags & DPD_HEAD_INPUT_GRAD)) {   // W1p as stored ([Kp1, H]): B operand of dX1 = dZ1 . W1p^T
+    b.w1nh = o; o += up256(H * Kp1 * e); b.w1nl = o; o += up256(H * Kp1 * e);
   }
   b.scales = o; o += up256(tc::P_COUNT * 4);
   b.total = o; return b;
@@ -633,6 +637,13 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
       w2, H, H, H, ps + tc::P_W2, (__half*)(base + b.w2h), (__half*)(base + b.w2l)));
   DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
       w3, H, H, H, ps + tc::P_W3, (__half*)(base + b.w3h), (__half*)(base + b.w3l)));
+  if (tc_train(c) && (c.flags & DPD_HEAD_INPUT_GRAD)) {
+    // rows [Kp1_src, Kp1) of the kernel-order operand are padding: zero them, split the rest in place
+    DPD_CUDA_CALL(cudaMemsetAsync(base + b.w1nh, 0, (size_t)Kp1 * H * 2, st));
+    DPD_CUDA_CALL(cudaMemsetAsync(base + b.w1nl, 0, (size_t)Kp1 * H * 2, st));
+    DPD_LAUNCH("tc_pack_w", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(n1, 256), 256, 0, st>>>(
+        w1p, n1, ps + tc::P_W1, (__half*)(base + b.w1nh), (__half*)(base + b.w1nl)));
+  }
   if (tc_train(c)) {
     const size_t n2e = (size_t)H * H;
     DPD_LAUNCH("tc_pack_w", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(n2e, 256), 256, 0, st>>>(
@@ -719,6 +730,40 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
                           nullptr, dz_next, nullptr, 0, bsc + 2, nullptr, nullptr, st, nullptr, nullptr, &bx))) return rc;
   }
   return 0;
+}
+
+int tc_kp1(const dpd_head_config& c) { return kp1_of(c, true); }
+
+// dX1 = dZ1 . W1p^T for the input-gradient path.  prepare: measure / scale / split dZ1 once; rows: one group of rows.
+int tc_backward_inputs_prepare(const dpd_head_config& c, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
+                               const float* dz1, const int* active, cudaStream_t st) {
+  const TcBlob b = tc_blob_layout(c, true);
+  const TcWs w = tc_ws_layout(c, true, ws_rows);
+  char* ws = (char*)tc_ws;
+  const int H = c.H, nblk = ceil_div(rows, 128);
+  float* bsc = (float*)(ws + w.bsc);
+  const float* ps = (const float*)((const char*)tc_blob + b.scales);
+  DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
+  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<nblk, 256, 0, st>>>(dz1, rows, H, active, (unsigned*)bsc));
+  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, ps + tc::P_W1, ps + tc::P_W1));
+  DPD_LAUNCH("bwd_split", st, tc::split_f16_active_kernel<<<nblk, 256, 0, st>>>(
+      dz1, rows, H, active, bsc + 1, (__half*)(ws + w.gh), (__half*)(ws + w.gl)));
+  DPD_CUDA_CHECK_LAUNCH("tc_backward_inputs_prepare");
+  return 0;
+}
+
+int tc_backward_inputs_rows(const dpd_head_config& c, const void* tc_blob, void* tc_ws, size_t ws_rows, size_t r0, int nrows,
+                            const int* active, float* dx1, cudaStream_t st) {
+  const TcBlob b = tc_blob_layout(c, true);
+  const TcWs w = tc_ws_layout(c, true, ws_rows);
+  const char* blob = (const char*)tc_blob;
+  char* ws = (char*)tc_ws;
+  const int H = c.H, Kp1 = kp1_of(c, true);
+  const float* bsc = (const float*)(ws + w.bsc);
+  tc::BwdExtras bx;
+  bx.mode = 2; bx.active = active + r0 / 128;
+  return tc::launch2(false, (const __half*)(ws + w.gh) + r0 * H, (const __half*)(ws + w.gl) + r0 * H, nrows, H, blob + b.w1nh,
+                     blob + b.w1nl, Kp1, nullptr, dx1, nullptr, 0, bsc + 2, nullptr, nullptr, st, nullptr, nullptr, &bx);
 }
 
 // mode 0: foreign fv (measure |fv|max, split)   1: |fv| <= 1 known (3DmFV output), split here

@@ -40,6 +40,13 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
                       const GatherDesc* g, const float* dz, float* dz_next, const int* active, float* gw, float* gb,
                       cudaStream_t st);
 
+// input gradients: dX1 = dZ1 . W1p^T (leading dimension tc_kp1(c)) for a group of rows, after one prepare per backward
+int tc_kp1(const dpd_head_config& c);
+int tc_backward_inputs_prepare(const dpd_head_config& c, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
+                               const float* dz1, const int* active, cudaStream_t st);
+int tc_backward_inputs_rows(const dpd_head_config& c, const void* tc_blob, void* tc_ws, size_t ws_rows, size_t r0, int nrows,
+                            const int* active, float* dx1, cudaStream_t st);
+
 int tc_debug_gemm(const float* a, int M, int K, const float* w, int N, const float* bias, float* out, void* scratch,
                   size_t scratch_bytes, int f16, cudaStream_t st);
 

@@ -36,3 +36,29 @@ prof = _lib.profile_read(reset=True)
 lib.dpd_profile_enable(0)
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
     print("  %-28s %8.3f ms/step  (%d launches/step)" % (k, v[0] / 3, v[1] // 3))
+
+# DPDist as a frozen loss: gradient into input1 only (the PCRNet-ours / AUE use), same batch
+from dpdist_b200.dpdist_loss import DPDistLoss  # noqa: E402
+dl = DPDistLoss(num_point=64, device=dev, seed=1)
+x = a.clone().requires_grad_(True)
+for _ in range(3):
+    x.grad = None
+    dl.loss(x, b).backward()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(n):
+    x.grad = None
+    dl.loss(x, b).backward()
+e1.record()
+torch.cuda.synchronize()
+print("frozen-loss forward + backward into input1, %d pairs: %.3f ms" % (pairs, e0.elapsed_time(e1) / n))
+lib.dpd_profile_enable(1)
+_lib.profile_read(reset=True)
+for _ in range(3):
+    x.grad = None
+    dl.loss(x, b).backward()
+torch.cuda.synchronize()
+prof = _lib.profile_read(reset=True)
+lib.dpd_profile_enable(0)
+for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]:
+    print("  %-28s %8.3f ms/step  (%d launches/step)" % (k, v[0] / 3, v[1] // 3))
