@@ -303,6 +303,35 @@ def run_ours(args, rank, world, local_rank):
         fv_kernel["steady_state"] = fv_large
         del big
 
+    # BASELINE configs[2] (training loop) beside the headline: forward + tensor-core backward + per-layer gradient
+    # all-reduce + Adam on 1024 synthetic pairs per GPU.  Informational; never allowed to break the bench line.
+    train_info = None
+    try:
+        from dpdist_b200 import train as TR, synthetic
+        trainer = TR.DPDistTrainer(dev, seed=1)
+        pa, pb, lab = synthetic.uniform_batch(2 + 1000 * rank, CFG["pairs_per_gpu"], CFG["N"])
+        ta, tb, tl = (torch.tensor(x, device=dev) for x in (pa, pb, lab))
+        for _ in range(3):
+            trainer.step(ta, tb, tl)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tsteps = 10
+        t0.record()
+        for _ in range(tsteps):
+            trainer.step(ta, tb, tl)
+        t1.record()
+        torch.cuda.synchronize()
+        tms = t0.elapsed_time(t1) / tsteps
+        if dist is not None:
+            tt = torch.tensor([tms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tms = float(tt.item())
+        train_info = {"workload": "configs[2]: DPDist training step, %d pairs per GPU, Adam, gradient all-reduce" % CFG["pairs_per_gpu"],
+                      "ms_per_step": tms, "pairs_per_s": CFG["pairs_per_gpu"] * world / (tms * 1e-3), "steps": tsteps}
+        del trainer, ta, tb, tl
+    except Exception as e:      # noqa: BLE001
+        train_info = {"error": "%s: %s" % (type(e).__name__, e)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("DPD_BENCH_NO_CPU"):
         # bounded sample of the same workload on this box's host cores (about 10-30 s of CPU work)
@@ -330,6 +359,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline,
             "fv_kernel": fv_kernel,
             "kernels": kernels,
+            "train": train_info,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
