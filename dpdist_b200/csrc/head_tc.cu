@@ -86,15 +86,24 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned* _
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like their bits
 }
 
-// max over columns n of sum_k |w[k][n]|   (w row-major [K, N])
-__global__ void col_l1_max_kernel(const float* __restrict__ w, int K, int N, unsigned* __restrict__ out_bits) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// max over columns n of sum_k |w[k][n]|   (w row-major [K, N]).  Block = 32 columns x 32 row lanes; the row lanes of a
+// column are summed in a fixed order (deterministic), then the block's 32 column sums are max-reduced.
+__global__ void __launch_bounds__(1024) col_l1_max_kernel(const float* __restrict__ w, int K, int N, unsigned* __restrict__ out_bits) {
+  __shared__ float part[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (n < N)
-    for (int k = 0; k < K; ++k) s += fabsf(w[(size_t)k * N + n]);
+    for (int k = ty; k < K; k += 32) s += fabsf(w[(size_t)k * N + n]);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float c = 0.f;
+    for (int j = 0; j < 32; ++j) c += part[j][tx];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(s));
+    for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if (tx == 0) atomicMax(out_bits, __float_as_uint(c));
+  }
 }
 
 __global__ void weight_scales_kernel(float* __restrict__ ps) {   // one thread
@@ -126,9 +135,9 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
 // |x|max over the ACTIVE 128-row blocks of x [rows, H] (inactive blocks hold stale data and are never read)
 __global__ void absmax_active_kernel(const float* __restrict__ x, int rows, int H, const int* __restrict__ active,
                                      unsigned* __restrict__ out_bits) {
-  const int blk = blockIdx.x;
-  if (active && !active[blk]) return;
-  const size_t lo = (size_t)blk * 128 * H, hi = min((size_t)rows, (size_t)(blk + 1) * 128) * H;
+  const int sub = blockIdx.x;                 // 32-row sub-block of a 128-row block
+  if (active && !active[sub >> 2]) return;
+  const size_t lo = (size_t)sub * 32 * H, hi = min((size_t)rows, (size_t)(sub + 1) * 32) * H;
   float m = 0.f;
   for (size_t i = lo + threadIdx.x * 4; i < hi; i += blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -628,8 +637,8 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
   DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<256, 256, 0, st>>>(w3, n2, pb + tc::P_W3MAX_BITS));
   DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<4, 256, 0, st>>>(b1, (size_t)H, pb + tc::P_B1MAX_BITS));
   DPD_LAUNCH("tc_pack_stats", st, tc::absmax_kernel<<<4, 256, 0, st>>>(b2, (size_t)H, pb + tc::P_B2MAX_BITS));
-  DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 256), 256, 0, st>>>(w1p, Kp1_src, H, pb + tc::P_C1_BITS));
-  DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 256), 256, 0, st>>>(w2, H, H, pb + tc::P_C2_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 32), 1024, 0, st>>>(w1p, Kp1_src, H, pb + tc::P_C1_BITS));
+  DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 32), 1024, 0, st>>>(w2, H, H, pb + tc::P_C2_BITS));
   DPD_LAUNCH("tc_pack_stats", st, tc::weight_scales_kernel<<<1, 1, 0, st>>>(ps));
   DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(Kp1, 32)), blk, 0, st>>>(
       w1p, Kp1_src, Kp1, H, ps + tc::P_W1, (__half*)(base + b.w1h), (__half*)(base + b.w1l)));
@@ -683,7 +692,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
   __half* gh = (__half*)(ws + w.gh); __half* gl = (__half*)(ws + w.gl);
   __half* gth = (__half*)(ws + w.gth); __half* gtl = (__half*)(ws + w.gtl);
   DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
-  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<nblk, 256, 0, st>>>(dz, rows, H, active, (unsigned*)bsc));
+  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<ceil_div(rows, 32), 256, 0, st>>>(dz, rows, H, active, (unsigned*)bsc));
   DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, w_scale, act_scale));
   DPD_LAUNCH("bwd_scales", st, tc::active_extent_kernel<<<1, 32, 0, st>>>(active, nblk, rows, extent));
   DPD_LAUNCH("bwd_split_transpose", st, tc::split_transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(
@@ -709,7 +718,10 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
     }
     DPD_CUDA_CHECK_LAUNCH("tc_backward_layer transposes");
     tc::BwdExtras bx;
-    bx.mode = 2; bx.slices = layer == 1 ? TC_DW1_SLICES : TC_DW_SLICES; bx.k_limit = extent; bx.slice_stride = (long long)Mo * H;
+    // at most the configured number of slices, at least 8 K-blocks (512 rows) per slice: small batches need few partials
+    const int max_slices = layer == 1 ? TC_DW1_SLICES : TC_DW_SLICES;
+    const int by_rows = Mp / (64 * 8) > 0 ? Mp / (64 * 8) : 1;
+    bx.mode = 2; bx.slices = by_rows < max_slices ? by_rows : max_slices; bx.k_limit = extent; bx.slice_stride = (long long)Mo * H;
     float* part = (float*)(ws + w.part);
     if ((rc = tc::launch2(false, ath, atl, Mo, Mp, gth, gtl, H, nullptr, part, nullptr, 0, bsc + 3, nullptr, nullptr, st, nullptr,
                           nullptr, &bx))) return rc;
@@ -744,7 +756,7 @@ int tc_backward_inputs_prepare(const dpd_head_config& c, const void* tc_blob, vo
   float* bsc = (float*)(ws + w.bsc);
   const float* ps = (const float*)((const char*)tc_blob + b.scales);
   DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
-  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<nblk, 256, 0, st>>>(dz1, rows, H, active, (unsigned*)bsc));
+  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<ceil_div(rows, 32), 256, 0, st>>>(dz1, rows, H, active, (unsigned*)bsc));
   DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, ps + tc::P_W1, ps + tc::P_W1));
   DPD_LAUNCH("bwd_split", st, tc::split_f16_active_kernel<<<nblk, 256, 0, st>>>(
       dz1, rows, H, active, bsc + 1, (__half*)(ws + w.gh), (__half*)(ws + w.gl)));

@@ -177,6 +177,13 @@ int dpd_head_backward_inputs(const dpd_head_config* cfg, const void* d_packed, f
 int dpd_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, size_t n, float lr,
                   float beta1, float beta2, float eps, int step, void* stream);
 
+/* The same update with the bias-corrected rate lr_t = dpd_adam_lr_t(lr, beta1, beta2, step) read from DEVICE memory:
+ * lets a captured CUDA graph of the whole training step (forward, backward, Adam) be replayed while the host only
+ * rewrites that scalar -- the reference's batch of 16 pairs (train_multi_gpu_pc_compare_dist.py:57) is launch-bound. */
+float dpd_adam_lr_t(float lr, float beta1, float beta2, int step);
+int dpd_adam_step_dev(float* d_param, const float* d_grad, float* d_m, float* d_v, size_t n, const float* d_lr_t,
+                      float beta1, float beta2, float eps, void* stream);
+
 /* Test hook for the tensor-core GEMM used by layers 2-3 of the head:
  *   d_out[M,N] = relu(d_a[M,K] . d_w[K,N] + d_bias[N]),  K % 64 == 0, N % 256 == 0,
  * computed with the split-precision tcgen05 kernel (f16 != 0: fp16x3, else 3xTF32).

@@ -105,3 +105,23 @@ def test_inference_path_unchanged_by_training_mode():
     # slice), training keeps H3 and uses the separate output kernel: fp32 re-association of a 1024-term dot product
     d = (p_train["pred_listAB"].detach() - p_eval["pred_listAB"]).abs()
     assert float(d.max()) <= 4e-6, float(d.max())
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """The captured training step (reference batch of 16 pairs) replays to the same weights as the eager one."""
+    pcA, pcB, labels = synthetic.chair_batch(3, 16, 64)
+    a, b, l = (torch.tensor(x, device=DEV) for x in (pcA, pcB, labels))
+    a2, b2 = a.flip(0).contiguous(), b.flip(0).contiguous()
+    res = []
+    for graph in (False, True):
+        tr = train.DPDistTrainer(DEV, seed=5, cuda_graph=graph)
+        losses = []
+        for i in range(8):                      # 3 eager warm-up steps, then (graph=True) capture + replays
+            x, y = (a, b) if i % 2 == 0 else (a2, b2)
+            losses.append(tr.step(x, y, l).clone())
+        torch.cuda.synchronize()
+        res.append((torch.stack(losses).cpu(), {n: v.detach().cpu().clone() for n, v in tr.store.vars.items()}))
+    assert tr._graph is not None and tr.batch == 8
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-6, atol=1e-7), (res[0][0], res[1][0])
+    for n in res[0][1]:
+        assert torch.equal(res[0][1][n], res[1][1][n]), n          # same kernels, same order: bit-identical weights
