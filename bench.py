@@ -264,8 +264,8 @@ def run_ours(args, rank, world, local_rank):
         # the kernel is timed inside a long step -> sustained peak
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
-        # very command (profiles/ncu_r1_summary.md, final kernels): layer 1 = 109 + 487 MB, layer 2 = 553 + 494 MB
-        traffic = {"tc_gemm2_gather_l1_f16": 596.1e6, "tc_gemm2_dense_f16": 1047.1e6, "tc_gemm2_dense_l3_l4_f16": 560.9e6}.get(dom)
+        # very command (profiles/ncu_r1_summary.md, round-1 end state): layer 1 = 97 + 487 MB, layer 2 = 541 + 498 MB
+        traffic = {"tc_gemm2_gather_l1_f16": 584.0e6, "tc_gemm2_dense_f16": 1039.0e6, "tc_gemm2_dense_l3_l4_f16": 559.3e6}.get(dom)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_source": "ncu --set full, profiles/ncu_r1_summary.md (bytes per launch)",
                     "tensor_work_frac": 3 * ach / peak, "peak_source": peaks["source"] + ", dense bf16 sustained; the fp32-accurate fp16x3 split issues 3 tensor "
