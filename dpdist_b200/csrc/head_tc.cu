@@ -492,7 +492,13 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   memset(&ka, 0, sizeof(ka));
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
   ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4;
-  if (g) ka.g = *g;
+  if (g) {
+    ka.g = *g;
+    if (gather) {   // valid operand length E + 3; everything from there to K is zero padding
+      const int tail = g->E + 3 - (K - 64);
+      ka.last_ks = tail >= 64 ? 0 : (tail <= 0 ? 1 : ceil_div(tail, 16));
+    }
+  }
   int tiles = ceil_div(M, 2 * BM) * (N / BN);
   if (bx) {
     DPD_REQUIRE(!gather && !split && part4 == nullptr, DPD_E_UNSUPPORTED, "tc gemm2: backward modes need the dense fp32-output kernel");

@@ -208,8 +208,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const uint64_t al = make_desc_sw128(smem_u32(stage_ptr(s, 1)));
             const uint64_t bh = make_desc_sw128(smem_u32(stage_ptr(s, 2)));
             const uint64_t bl = make_desc_sw128(smem_u32(stage_ptr(s, 3)));
+            const int nks = (kb == args.num_kb - 1 && args.last_ks > 0) ? args.last_ks : 4;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+              if (ks >= nks) break;
               const uint64_t o = (uint64_t)(ks * 2);
               umma_f16_cg2(d_tmem, al + o, bh + o, IDESC_F16_M256, accumulate);
               umma_f16_cg2(d_tmem, ah + o, bl + o, IDESC_F16_M256, 1);
