@@ -91,6 +91,10 @@ class DPDistTrainer:
         self.cuda_graph = bool(cuda_graph)
         self._graph = None
         self._eager_steps = 0
+        # warm-up steps and the capture share one side stream (the pattern torch documents for whole-step capture): autograd
+        # remembers the stream a parameter's gradient accumulator was created on, and a capture must never make the legacy
+        # default stream wait on it
+        self._side = torch.cuda.Stream(device=self.device) if self.cuda_graph else None
 
     def variables(self):
         return self.store.trainable_variables("pc_compare")
@@ -111,19 +115,20 @@ class DPDistTrainer:
                     self.m[id(p)] = torch.zeros_like(p)
                     self.v[id(p)] = torch.zeros_like(p)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._side):
                 tf_util.clear_collections()
                 with tf_util.use_store(self.store):
                     pred, end_points, _ = MODEL.get_model(gs["a"], gs["b"], True, **self.kw)
                     MODEL.get_loss(pred, end_points, gs["l"])
                 loss = tf_util.get_collection("loss_samples")[-1]
-                for p in params:
-                    p.grad = None
-                loss.backward()
+                # autograd.grad, not backward(): no AccumulateGrad nodes, whose streams (the default stream of the eager
+                # steps) would make the legacy stream wait on the capturing one and invalidate the capture
+                grads = torch.autograd.grad(loss, params)
+                gs["grads"] = grads
                 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
                 with torch.no_grad():
-                    for p in params:
-                        rc = lib.dpd_adam_step_dev(p.data_ptr(), p.grad.data_ptr(), self.m[id(p)].data_ptr(),
+                    for p, g in zip(params, grads):
+                        rc = lib.dpd_adam_step_dev(p.data_ptr(), g.data_ptr(), self.m[id(p)].data_ptr(),
                                                    self.v[id(p)].data_ptr(), p.numel(), gs["lr_t"].data_ptr(),
                                                    ADAM_BETA1, ADAM_BETA2, ADAM_EPS, stream)
                         _lib.check(rc, "dpd_adam_step_dev")
@@ -147,6 +152,15 @@ class DPDistTrainer:
             if self._eager_steps >= 3:
                 return self._graph_step(pcA, pcB, labels_AB)
             self._eager_steps += 1
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                loss = self._eager_step(pcA, pcB, labels_AB, add_noise)
+            cur.wait_stream(self._side)
+            return loss
+        return self._eager_step(pcA, pcB, labels_AB, add_noise)
+
+    def _eager_step(self, pcA, pcB, labels_AB, add_noise=0):
         lib = _lib.load()
         tf_util.clear_collections()
         with tf_util.use_store(self.store):
