@@ -274,3 +274,41 @@ def test_stress_config_E_properties():
         oab, oba = O.forward_chunked(torch.tensor(pcA[2049:2051]), torch.tensor(pcB[2049:2051]), var, chunk=1)
     assert_out_close(ab[2049:2051], oab, "config E vs oracle (AB)")
     assert_out_close(ba[2049:2051], oba, "config E vs oracle (BA)")
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_fv_permutation_and_mirror_properties():
+    rng = np.random.default_rng(21)
+    pts = rng.uniform(-0.8, 0.8, size=(5, 64, 3)).astype(np.float32)
+    x = torch.tensor(pts, device=DEV)
+    fv = dpdist_util.get_3dmfv_tf(x, n_gaussians=512, sigma=0.125, flatten=False)
+    # (1) the encoding is a set function: max / min statistics do not depend on the point order at all, means only
+    #     through fp32 summation order (the per-channel L2 norm couples the channels' Gaussians, hence a tolerance)
+    perm = torch.tensor(rng.permutation(64), device=DEV)
+    fvp = dpdist_util.get_3dmfv_tf(x[:, perm].contiguous(), n_gaussians=512, sigma=0.125, flatten=False)
+    assert_close(fvp, fv, 1e-5, 2e-6, "fv of permuted points")
+    mm = [1, 5, 6, 7, 8, 9, 10, 14, 15, 16, 17, 18, 19]              # max / min channels (:134-137)
+    assert torch.equal(fvp[:, :, mm], fv[:, :, mm])
+    # (2) mirroring the cloud in x mirrors the grid in i1 (centre x = l[i1], :47-48), negates the d/dmu_x channels and
+    #     swaps their max and min; every other channel is unchanged (up to the summation order of the 8 cell weights).
+    xm = x.clone()
+    xm[:, :, 0] = -xm[:, :, 0]
+    fvm = dpdist_util.get_3dmfv_tf(xm, n_gaussians=512, sigma=0.125, flatten=False).view(5, 8, 8, 8, 20).flip(2).reshape(5, 512, 20)
+    same = [0, 1, 3, 4, 6, 7, 9, 10] + list(range(11, 20))
+    assert_close(fvm[:, :, same], fv[:, :, same], 1e-5, 2e-6, "mirror: unchanged channels")
+    assert_close(fvm[:, :, 2], -fv[:, :, 2], 1e-5, 2e-6, "mirror: mean d/dmu_x")
+    assert_close(fvm[:, :, 5], -fv[:, :, 8], 1e-5, 2e-6, "mirror: max d/dmu_x <-> -min")
+    assert_close(fvm[:, :, 8], -fv[:, :, 5], 1e-5, 2e-6, "mirror: min d/dmu_x <-> -max")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_head_rows_are_independent(impl):
+    """Permuting the queries of a cloud permutes its outputs bit-exactly; a query outside the cube gives exactly 0."""
+    pcA, pcB, _ = synthetic.uniform_batch(12, 3, 64, outside_frac=0.1)
+    var = O.unit_scale_variables(6)
+    p, _ = _run_model(pcA, pcB, var, impl)
+    perm = np.random.default_rng(0).permutation(64)
+    p2, _ = _run_model(pcA, pcB[:, perm], var, impl)
+    assert torch.equal(p2["pred_listAB"], p["pred_listAB"][:, perm])
+    outside = torch.tensor((np.abs(pcB) > 1).any(-1))
+    assert outside.any() and float(p["pred_listAB"][outside].abs().max()) == 0.0

@@ -155,3 +155,19 @@ def test_golden_fixture_pins_the_oracle():
     assert_out_close(p["pred_listBA"], z["pred_BA"], "pred_BA")
     _, _, am = O.get_pc_grid_binary_mask_from_centers(aux["C"], torch.tensor(z["pcB"]))
     assert np.array_equal(am.numpy().astype(np.int32), z["idx_B"])
+
+
+def test_fv_is_a_set_function_hypothesis():
+    """Property test (hypothesis): the oracle's encoding does not depend on the point order (fp64: to rounding)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=10, deadline=None)
+    @given(st.integers(0, 10 ** 6), st.integers(2, 40))
+    def check(seed, n):
+        rng = np.random.default_rng(seed)
+        pts = torch.tensor(rng.uniform(-0.9, 0.9, size=(1, n, 3)))
+        perm = torch.tensor(rng.permutation(n))
+        a = O.get_3dmfv(pts, 27, 0.3, flatten=False)
+        b = O.get_3dmfv(pts[:, perm], 27, 0.3, flatten=False)
+        assert float((a - b).abs().max()) < 1e-12
+    check()
