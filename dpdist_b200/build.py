@@ -16,6 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libdpdist_b200.so")
+STAMP_PATH = LIB_PATH + ".stamp"     # next to the .so: travels with it (build/ directories may be dropped by snapshots)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -50,10 +51,16 @@ def _stamp():
 
 
 def needs_build():
-    stamp_file = os.path.join(BUILD_DIR, "stamp")
-    if not os.path.exists(LIB_PATH) or not os.path.exists(stamp_file):
+    if not os.path.exists(LIB_PATH):
         return True
-    with open(stamp_file) as fh:
+    if not os.path.exists(STAMP_PATH):
+        # a prebuilt library without its stamp: rebuild if a compiler is here, otherwise trust the library
+        try:
+            _nvcc()
+        except RuntimeError:
+            return False
+        return True
+    with open(STAMP_PATH) as fh:
         return fh.read().strip() != _stamp()
 
 
@@ -81,7 +88,7 @@ def build_library(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(os.path.join(BUILD_DIR, "stamp"), "w") as fh:
+    with open(STAMP_PATH, "w") as fh:
         fh.write(_stamp())
     if verbose:
         print("built", LIB_PATH)
