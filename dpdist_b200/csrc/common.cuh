@@ -50,6 +50,19 @@ inline void fill_tables(GridTables& t, int G, const float* c, const float* lo, c
 
 int num_sms();
 
+// cudaFuncSetAttribute is per device: remember per (call site, device) whether the opt-in shared-memory size was set.
+// One process per GPU is the deployment model, but several devices in one process must work too.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // Counts every kernel launch; when profiling is on, brackets it with CUDA events on its stream.
 struct ProfScope {
   ProfScope(const char* name, cudaStream_t st);

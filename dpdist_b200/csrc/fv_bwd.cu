@@ -299,11 +299,10 @@ extern "C" int dpd_fv_backward(const float* d_points, int n_clouds, int n_points
   DPD_REQUIRE(smem <= 227 * 1024, DPD_E_UNSUPPORTED,
               "dpd_fv_backward: G=%d needs %zu B of shared memory per CTA (limit 227 KB, G <= 10)", G, smem);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     DPD_CUDA_CALL(cudaFuncSetAttribute(fv_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DPD_CUDA_CALL(cudaFuncSetAttribute(fv_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
   }
   const int grid = n_clouds < 4 * num_sms() ? n_clouds : 4 * num_sms();
   if (full_fv) DPD_LAUNCH("fv_backward", st, fv_backward_kernel<true><<<grid, BT, smem, st>>>(p));

@@ -312,10 +312,9 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
 
 int fv_forward_optimized(const FvParams& p, cudaStream_t stream) {
   if (p.G != G8 || !p.full_fv) return 1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     DPD_CUDA_CALL(cudaFuncSetAttribute(fv_g8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    attr_done = true;
   }
   const int max_ctas = num_sms() * 4;
   const int grid = p.n_clouds < max_ctas ? p.n_clouds : max_ctas;

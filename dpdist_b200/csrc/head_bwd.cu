@@ -323,8 +323,8 @@ int launch_out_backward(const float* h3, const float* w4, const float* b4, const
                         const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st) {
   DPD_REQUIRE(H % 128 == 0 && H <= 1024, DPD_E_UNSUPPORTED, "head backward: H=%d must be a multiple of 128, <= 1024", H);
   const size_t smem = (size_t)8 * (H * 3 + 3) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4)); attr_done = true; }
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4)); }
   DPD_LAUNCH("bwd_out_l4", st, out_backward_kernel<<<n_cta, 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3, partial4, M, H));
   DPD_CUDA_CHECK_LAUNCH("out_backward_kernel");
   return 0;

@@ -421,10 +421,9 @@ static int make_tmap(CUtensorMap* m, const void* base, bool f16, uint64_t rows, 
 template <bool GATHER, bool F16>
 static int launch_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
                     const KernelArgs& ka, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel<GATHER, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    attr_done = true;
   }
   const char* name = GATHER ? (F16 ? "tc_gemm_gather_l1_f16" : "tc_gemm_gather_l1_tf32") : (F16 ? "tc_gemm_dense_f16" : "tc_gemm_dense_tf32");
   DPD_LAUNCH(name, st, tc_gemm_kernel<GATHER, F16><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
@@ -435,10 +434,9 @@ static int launch_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CU
 template <bool GATHER>
 static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
                      const KernelArgs& ka, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    attr_done = true;
   }
   DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
              tc_gemm2_kernel<GATHER><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));

@@ -312,3 +312,24 @@ def test_head_rows_are_independent(impl):
     assert torch.equal(p2["pred_listAB"], p["pred_listAB"][:, perm])
     outside = torch.tensor((np.abs(pcB) > 1).any(-1))
     assert outside.any() and float(p["pred_listAB"][outside].abs().max()) == 0.0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """One process per GPU is the deployment model, but nothing may be tied to device 0 (opt-in shared-memory sizes,
+    packed-weight caches, streams)."""
+    pcA, pcB, _ = synthetic.uniform_batch(5, 4, 64)
+    var = O.unit_scale_variables(4)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        store = tf_util.VariableStore(device=dev)
+        store.load_state_dict(var, strict=False)
+        a = torch.tensor(pcA, device=dev, requires_grad=True)
+        with tf_util.use_store(store):
+            pred, _, _ = MODEL.get_model(a, torch.tensor(pcB, device=dev), False, bn=0, Embedding_Size=512, k=5,
+                                         sigma3dmfv=0.125, reuse=True)
+        loss = pred["pred_listAB"][..., 0].mean() + pred["pred_listBA"][..., 0].mean()
+        loss.backward()
+        torch.cuda.synchronize(dev)
+        outs.append((pred["pred_listAB"].detach().cpu(), a.grad.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
