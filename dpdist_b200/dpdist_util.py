@@ -389,23 +389,50 @@ def _check_head_options(k, conv_version, NUM_DIMS, bn, output_act, mlp):
         raise NotImplementedError("conv_version %d: only the shared-MLP head (1) is implemented" % conv_version)
     if NUM_DIMS != 3:
         raise NotImplementedError("NUM_DIMS must be 3")
-    if bn:
-        raise NotImplementedError("bn=True: batch norm is off at the reference defaults (--BN 0) and not implemented")
     if output_act != 'relu':
         raise NotImplementedError("output_act must be 'relu' (models/dpdist_and_aue.py:74)")
     if len(mlp) != 3 or not (mlp[0] == mlp[1] == mlp[2]):
         raise NotImplementedError("mlp must be three equal widths (reference default [1024,1024,1024])")
 
 
-def _head_variables(E, NUM_DIMS, mlp, reuse):
-    """The 8 variables of scope 'dpdist_local' (:514-545), created or looked up exactly as DPDist does."""
+def _head_variables(E, NUM_DIMS, mlp, reuse, bn=False):
+    """The 8 variables of scope 'dpdist_local' (:514-545), created or looked up exactly as DPDist does; with `bn`
+    also the four batch-norm variables of every layer (returned as a second list of 4-tuples)."""
     H = mlp[0]
     with tf_util.variable_scope('dpdist_local', reuse=reuse):                 # :514
         w1, b1 = tf_util.conv2d_variables(1, H, [1, E + NUM_DIMS], 'mapper_conv1', reuse=reuse)   # :516-521
         w2, b2 = tf_util.conv2d_variables(H, mlp[1], [1, 1], 'mapper_conv2', reuse=reuse)         # :529-533
         w3, b3 = tf_util.conv2d_variables(mlp[1], mlp[2], [1, 1], 'mapper_conv3', reuse=reuse)    # :535-539
         w4, b4 = tf_util.conv2d_variables(mlp[2], NUM_DIMS, [1, 1], 'mapper_conv4', reuse=reuse)  # :541-545
+        bns = []
+        if bn:
+            for scope, ch in (('mapper_conv1', H), ('mapper_conv2', mlp[1]), ('mapper_conv3', mlp[2]), ('mapper_conv4', NUM_DIMS)):
+                with tf_util.variable_scope(scope, reuse=reuse):
+                    bns.append(tf_util.batch_norm_variables(ch, reuse=reuse))
+    if bn:
+        return [w1, b1, w2, b2, w3, b3, w4, b4], bns
     return [w1, b1, w2, b2, w3, b3, w4, b4]
+
+
+_BN_FOLDED = {}
+
+
+def _fold_batch_norm(weights, bns):
+    """Inference-mode batch norm (is_training False: moving statistics, utils/tf_util.py:221-224) is a per-channel affine
+    map after conv + bias, so it folds into the layer:  W' = W * s,  b' = (b - mean) * s + beta,  s = gamma / sqrt(var + eps).
+    The folded tensors are cached on the versions of the inputs (the packed-weight cache keys on them in turn)."""
+    out = []
+    for i, (beta, gamma, mean, var) in enumerate(bns):
+        w, b = weights[2 * i], weights[2 * i + 1]
+        key = tuple((t.data_ptr(), t._version) for t in (w, b, beta, gamma, mean, var))
+        hit = _BN_FOLDED.get(i)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                s = gamma * torch.rsqrt(var + tf_util.BN_EPSILON)
+                hit = (key, (w.detach() * s).contiguous(), ((b.detach() - mean) * s + beta).contiguous(), (w, b, beta, gamma, mean, var))
+            _BN_FOLDED[i] = hit
+        out += [hit[1], hit[2]]
+    return out
 
 
 def model_forward(points, query, n_gaussians, sigma, full_fv, k, mlp, reuse=None, impl=None):
@@ -461,7 +488,17 @@ def DPDist(point_cloud, point_cloudB, embedding,
     B, NP, _ = pcA.shape
     E = fvA.shape[2] * k ** 3
     H = mlp[0]
-    weights = _head_variables(E, NUM_DIMS, mlp, reuse)
+    if bn:
+        # batch norm after every conv + bias (utils/tf_util.py:221-224).  Inference (moving statistics) folds into the
+        # layers; training-mode batch statistics are not implemented (the reference trains with --BN 0, the log-dir
+        # name of its shipped run says BN0).
+        if not (isinstance(is_training, (bool, int)) and not is_training):
+            raise NotImplementedError("bn=True with is_training=True (batch statistics) is not implemented; "
+                                      "inference with the moving statistics (is_training=False) is")
+        weights, bns = _head_variables(E, NUM_DIMS, mlp, reuse, bn=True)
+        weights = _fold_batch_norm(weights, bns)
+    else:
+        weights = _head_variables(E, NUM_DIMS, mlp, reuse)
     fv_all = torch.cat([fvA, fvB], 0)             # rows [A-field | B-field]  (:511)
     query = torch.cat([pcB, pcA], 0)              # A's field is queried at B's points and vice versa (:494,498)
     # is_training only switches batch norm in the reference (off here); a literal False/0 additionally

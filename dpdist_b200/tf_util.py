@@ -28,6 +28,8 @@ class VariableStore:
             v = self.vars[name]
             if tuple(v.shape) != tuple(shape):
                 raise ValueError("variable %s exists with shape %s, requested %s" % (name, tuple(v.shape), tuple(shape)))
+            if not trainable and v.requires_grad:      # e.g. moving statistics loaded from a checkpoint before first use
+                v.requires_grad_(False)
             return v
         if reuse is True:
             raise ValueError("Variable %s does not exist, or was not created with tf.get_variable()" % name)
@@ -147,6 +149,22 @@ def conv2d_variables(num_in_channels, num_output_channels, kernel_size, scope, r
                                              stddev=1e-3, wd=0.0, use_xavier=True)
         biases = _variable_on_cpu("biases", [num_output_channels], constant_initializer(0.0))
     return kernel, biases
+
+
+BN_EPSILON = 0.001     # TF-semantics: tf.contrib.layers.batch_norm default epsilon (utils/tf_util.py:573-577 passes none)
+
+
+def batch_norm_variables(num_channels, reuse=None):
+    """The four variables tf.contrib.layers.batch_norm(center=True, scale=True, scope='bn') creates inside a conv
+    scope (utils/tf_util.py:221-224, 558-577): bn/beta (0), bn/gamma (1) trainable; bn/moving_mean (0),
+    bn/moving_variance (1) not trainable."""
+    store = default_store()
+    with variable_scope('bn', reuse=reuse):
+        beta = store.get_variable(_scoped('beta'), [num_channels], constant_initializer(0.0), reuse=_reuse())
+        gamma = store.get_variable(_scoped('gamma'), [num_channels], constant_initializer(1.0), reuse=_reuse())
+        mean = store.get_variable(_scoped('moving_mean'), [num_channels], constant_initializer(0.0), reuse=_reuse(), trainable=False)
+        var = store.get_variable(_scoped('moving_variance'), [num_channels], constant_initializer(1.0), reuse=_reuse(), trainable=False)
+    return beta, gamma, mean, var
 
 
 # ---- graph collections (tf.add_to_collection / tf.get_collection), used for the two losses ----

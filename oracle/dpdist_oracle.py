@@ -295,7 +295,24 @@ def conv2d_1xw(x, weights, biases, relu):
     return torch.relu(y) if relu else y                                # :226-227
 
 
-def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, output_act="relu"):
+BN_EPSILON = 0.001   # TF-semantics: tf.contrib.layers.batch_norm default
+
+
+def bn_inference_variables(seed=2, mlp=(1024, 1024, 1024), dtype=torch.float32):
+    """Random moving statistics / affine parameters under the TF names of tf.contrib.layers.batch_norm(scope='bn')
+    inside each conv scope (utils/tf_util.py:221-224, 573-577)."""
+    gen = torch.Generator().manual_seed(seed)
+    out = {}
+    for scope, ch in zip(MLP_SCOPES, list(mlp) + [3]):
+        p = VAR_PREFIX + scope + "/bn/"
+        out[p + "beta"] = (torch.randn(ch, generator=gen, dtype=torch.float64) * 0.1).to(dtype)
+        out[p + "gamma"] = (1.0 + 0.2 * torch.randn(ch, generator=gen, dtype=torch.float64)).to(dtype)
+        out[p + "moving_mean"] = (torch.randn(ch, generator=gen, dtype=torch.float64) * 0.2).to(dtype)
+        out[p + "moving_variance"] = (0.5 + torch.rand(ch, generator=gen, dtype=torch.float64)).to(dtype)
+    return out
+
+
+def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, output_act="relu", bn=False):
     """utils/dpdist_util.py:412-544,688-700, conv_version 1, k>0, bn off.
 
     embedding / embeddingB are the [B,V,k^3*20] patch tensors from local_z.
@@ -307,7 +324,13 @@ def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, outpu
     x = torch.cat([net, netB], 0)                                                # :511  [2B,NP,E+3]
     for i, scope in enumerate(MLP_SCOPES):                                       # :516-544
         x = conv2d_1xw(x, variables[VAR_PREFIX + scope + "/weights"],
-                       variables[VAR_PREFIX + scope + "/biases"], relu=(i < 3))
+                       variables[VAR_PREFIX + scope + "/biases"], relu=(i < 3) and not bn)
+        if bn:   # inference-mode batch norm between bias_add and the activation (utils/tf_util.py:219-227)
+            p = VAR_PREFIX + scope + "/bn/"
+            x = (x - variables[p + "moving_mean"]) * torch.rsqrt(variables[p + "moving_variance"] + BN_EPSILON) \
+                * variables[p + "gamma"] + variables[p + "beta"]
+            if i < 3:
+                x = torch.relu(x)
     x = x[:, :, None, :]                                                         # [2B,NP,1,3]
     if output_act == "relu":
         x = torch.clamp(x, 0.0, 6.0) / 3                                         # :690-691
@@ -327,7 +350,7 @@ def get_loss(pred_set, end_points, labels, loss_type="l1_dist"):
     return loss, loss_pred
 
 
-def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3dmfv=0.125, add_noise=0):
+def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3dmfv=0.125, add_noise=0, bn=False):
     """models/dpdist_and_aue.py:31-86 (3dmfv encoder, k>0, conv_version 1)."""
     pcA_noise = pcA + add_noise                                                  # :45
     embedding_A = get_3dmfv(pcA_noise, n_gaussians=Embedding_Size, flatten=False,
@@ -338,7 +361,7 @@ def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3
     embedding_A, C = local_z(embedding_A, k=k)                                   # :64
     embedding_B, _ = local_z(embedding_B, k=k)                                   # :65
     C = C.to(pcA.dtype)
-    net = DPDist(pcA, pcB, embedding_A, embedding_B, C, variables)               # :69-75
+    net = DPDist(pcA, pcB, embedding_A, embedding_B, C, variables, bn=bn)        # :69-75
     pred_set = {"pred_listAB": net[0], "pred_listBA": net[1]}                    # :80-81
     embedding_set = {"embedding_A": embedding_A, "embedding_B": embedding_B}
     return pred_set, {"fvA": fvA, "fvB": fvB, "C": C}, embedding_set

@@ -333,3 +333,29 @@ def test_second_device_in_the_same_process():
         torch.cuda.synchronize(dev)
         outs.append((pred["pred_listAB"].detach().cpu(), a.grad.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_inference_batch_norm_folds_into_the_layers(impl):
+    """bn=True, is_training=False: the moving statistics of tf.contrib.layers.batch_norm applied after every conv + bias
+    (utils/tf_util.py:221-224) -- folded into the packed weights here, applied literally in the oracle."""
+    pcA, pcB, _ = synthetic.uniform_batch(14, 3, 64)
+    var = dict(O.unit_scale_variables(7))
+    var.update(O.bn_inference_variables(3))
+    with O.tf_cpu_numerics():
+        want, _, _ = O.get_model(torch.tensor(pcA), torch.tensor(pcB), var, bn=True)
+    dpdist_util.HEAD_IMPL = impl
+    try:
+        store = _store_from(var)
+        with tf_util.use_store(store):
+            p, _, _ = MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), False, bn=1,
+                                      Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+            with pytest.raises(NotImplementedError):
+                MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), True, bn=1,
+                                Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+    finally:
+        dpdist_util.HEAD_IMPL = _lib.HEAD_AUTO
+    assert_out_close(p["pred_listAB"], want["pred_listAB"], "bn inference AB")
+    assert_out_close(p["pred_listBA"], want["pred_listBA"], "bn inference BA")
+    names = [n for n in store.names() if "/bn/" in n]
+    assert len(names) == 16 and not store.vars[O.VAR_PREFIX + "mapper_conv1/bn/moving_mean"].requires_grad
