@@ -22,6 +22,59 @@ import torch.distributed as dist
 from . import synthetic, train
 
 
+def train_on_dataset(FLAGS, tr, dev, rank, world):
+    """The reference's epoch loop on the real files (train_multi_gpu_pc_compare_dist.py:181-188, 332-357, 732-873):
+    ModelNetDataset(npoints = 2 * NUM_POINT, class_choice = [category]) with augmentation, train_one_epoch_3d, an
+    evaluation epoch on the test split every 10 epochs and at the end, `model.ckpt` saved next to the log."""
+    from . import modelnet_dataset, tf_checkpoint
+    # every rank reads the same global batch (same seed) and keeps its own slice, like the towers' tf.slice (:241-251)
+    mk = lambda split: modelnet_dataset.ModelNetDataset(root=FLAGS.data_root, npoints=FLAGS.num_point * 2, split=split,
+                                                        normal_channel=False, batch_size=FLAGS.batch_size,
+                                                        class_choice=[FLAGS.category] if FLAGS.category else None,
+                                                        device=dev, seed=0)
+    TRAIN_DATASET, TEST_DATASET = mk('train'), mk('test')
+
+    def batches(ds, augment):
+        while ds.has_next_batch():
+            pcA, pcB, lab = ds.next_batch_device(FLAGS.num_point, augment=augment)
+            if pcA.shape[0] % world != 0:            # the reference pads the last batch with zeros (:736-739); drop it instead
+                continue
+            yield [train.shard(x, rank, world).contiguous() for x in (pcA, pcB, lab)]
+        ds.reset()
+
+    def eval_one_epoch():
+        from . import dpdist_and_aue as MODEL, tf_util
+        tot, cnt = 0.0, 0
+        with torch.no_grad():
+            for a, b, l in batches(TEST_DATASET, False):
+                with tf_util.use_store(tr.store):
+                    pred, _, _ = MODEL.get_model(a, b, False, **tr.kw)
+                tot += float((pred['pred_listAB'][:, :, 0, 0] - l).abs().mean())           # :840-852 loss_samples
+                cnt += 1
+        return tot / max(cnt, 1)
+
+    for epoch in range(FLAGS.max_epoch):
+        losses = []
+        for a, b, l in batches(TRAIN_DATASET, True):
+            noise = torch.randn_like(a) * FLAGS.add_noise if FLAGS.add_noise > 0 else 0
+            losses.append(tr.step(a, b, l, add_noise=noise))
+        mean_loss = float(torch.stack(losses).mean()) if losses else float('nan')
+        if world > 1:
+            t = torch.tensor([mean_loss], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+            mean_loss = float(t.item())
+        if rank == 0:
+            print(' ---- epoch: %03d ---- mean loss: %f' % (epoch + 1, mean_loss), flush=True)
+        if epoch % 10 == 0 or epoch == FLAGS.max_epoch - 1:                              # :354-357
+            ev = eval_one_epoch()
+            if rank == 0:
+                os.makedirs(FLAGS.log_dir, exist_ok=True)
+                path = tf_checkpoint.save_checkpoint(os.path.join(FLAGS.log_dir, 'model.ckpt'), tr.store.state_dict())
+                print('eval mean loss: %f   Model saved in file: %s' % (ev, path), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument('--num_gpus', type=int, default=1)
@@ -38,6 +91,13 @@ def main(argv=None):
     p.add_argument('--warmup', type=int, default=5)
     p.add_argument('--distinct_batches', type=int, default=4)
     p.add_argument('--log_every', type=int, default=10)
+    # real data (reference flags: --category chair, --max_epoch, --log_dir; train_multi_gpu_pc_compare_dist.py:41-69)
+    p.add_argument('--data_root', default='', help='ModelNet root with ground-truth files (dpdist_b200.dataset_sample_with_gt); '
+                                                   'empty = synthetic batches')
+    p.add_argument('--category', default='chair')
+    p.add_argument('--max_epoch', type=int, default=1)
+    p.add_argument('--log_dir', default='log/dpdist_b200')
+    p.add_argument('--cuda_graph', type=int, default=0, help='replay the captured training step (single GPU)')
     FLAGS = p.parse_args(argv)
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -50,7 +110,9 @@ def main(argv=None):
     sigma = FLAGS.sigma3dmfv * 0.0625                                       # :103
     tr = train.DPDistTrainer(dev, base_lr=FLAGS.learning_rate_dpdist, decay_step=FLAGS.decay_step,
                              decay_rate=FLAGS.decay_rate, Embedding_Size=FLAGS.embedding_size, k=int(FLAGS.K),
-                             sigma3dmfv=sigma, seed=1)
+                             sigma3dmfv=sigma, seed=1, cuda_graph=bool(FLAGS.cuda_graph))
+    if FLAGS.data_root:
+        return train_on_dataset(FLAGS, tr, dev, rank, world)
     batches = []
     for i in range(FLAGS.distinct_batches):
         if FLAGS.batch_size <= 64:

@@ -1,5 +1,7 @@
 """GPU tests of the data side: ground-truth distances and batch assembly + augmentation against the
 reference's numpy / scipy formulation restated in the oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -78,3 +80,35 @@ def test_data_entry_points_validate():
     assert lib.dpd_nearest_distance(None, 1, 4, x.data_ptr(), 4, x.data_ptr(), None, None) == -1
     assert lib.dpd_assemble_batch(x.data_ptr(), x.data_ptr(), 1, 3, 4, None, None, x.data_ptr(), x.data_ptr(), x.data_ptr(), None) == -1
     assert b"npoints" in lib.dpd_last_error()
+
+
+def test_generator_reader_and_trainer_on_a_tiny_dataset(tmp_path):
+    """dataset_sample_with_gt -> ModelNetDataset -> next_batch_device -> training driver, on a fake ModelNet tree."""
+    from test_dataset import make_tree
+    from dpdist_b200 import dataset_sample_with_gt as GEN, modelnet_dataset as MD, train_multi_gpu_pc_compare_dist as DRV, tf_checkpoint
+    make_tree(tmp_path, n_train=4, n_test=2, n_surface=600)
+    for f in tmp_path.rglob("*_dist_c_*"):          # keep only the raw shapes: the generator must produce the rest
+        f.unlink()
+    n = GEN.generate_points_with_gt(str(tmp_path), num_neg_points=500, cur_cls=["chair"], seed=0, verbose=False)
+    assert n == 6
+    assert GEN.generate_points_with_gt(str(tmp_path), num_neg_points=500, cur_cls=["chair"], verbose=False) == 0   # already there
+    base = str(tmp_path / "chair" / "chair_0000")
+    raw = np.loadtxt(base + ".txt", delimiter=",")[:, :3]
+    pos = np.loadtxt(base + "_dist_c_scaled.txt", delimiter=",")
+    assert np.allclose(pos, raw * 0.8, atol=1e-6)
+    negl = np.loadtxt(base + "_500_dist_c_neg_l.txt", delimiter=",")
+    want, _ = O.nearest_distance(pos, negl[:, :3])
+    assert negl.shape == (500, 4) and np.abs(negl[:, 3] - want).max() < 5e-6 and negl[:, 3].max() < 0.1
+    # the reader expects the 10^4-point file names; link them for this miniature
+    for f in list(tmp_path.rglob("*_500_dist_c_*")):
+        os.rename(f, str(f).replace("_500_", "_10000_"))
+    ds = MD.ModelNetDataset(root=str(tmp_path), npoints=128, split="train", batch_size=4, class_choice=["chair"], device=DEV, seed=3)
+    pcA, pcB, lab = ds.next_batch_device(64, augment=True)
+    assert pcA.shape == (4, 64, 3) and pcB.shape == (4, 64, 3) and lab.shape == (4, 64)
+    assert float(lab[:, :32].abs().max()) == 0.0 and float(lab[:, 32:48].max()) < 0.1 and float(lab[:, 48:].min()) > 0.0
+    # labels are distances to the (augmented) surface: rigid motion keeps them valid
+    d = D.nearest_distance(torch.cat([pcA, pcB[:, :32]], 1), pcB[:, 32:])
+    assert float((lab[:, 32:] - d).max()) < 1e-5      # a subsample of the surface (96 of 600 points) can only over-estimate
+    DRV.main(["--data_root", str(tmp_path), "--batch_size", "4", "--max_epoch", "2", "--log_dir", str(tmp_path / "log")])
+    ck = tf_checkpoint.list_variables(str(tmp_path / "log" / "model.ckpt"))
+    assert "pc_compare/dpdist_local/mapper_conv1/weights" in ck
