@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>   // header-only; resolves the tools library lazily, no-ops when no tool is attached
+#include <stdlib.h>
 
 namespace dpd {
 
@@ -52,8 +54,17 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
+// DPD_NVTX=1: every kernel launch of the library is wrapped in an NVTX range carrying its profile name, so that nsys /
+// ncu timelines show the three stages of the path (3DmFV, voxel assignment, head layers) by name
+static bool nvtx_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DPD_NVTX"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v != 0;
+}
+
 ProfScope::ProfScope(const char* name, cudaStream_t st) : name_(name), st_(st), e0_(nullptr), e1_(nullptr), on_(false) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (nvtx_on()) nvtxRangePushA(name);
   if (g_prof_on.load(std::memory_order_relaxed)) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     e0_ = get_event(); e1_ = get_event();
@@ -63,6 +74,7 @@ ProfScope::ProfScope(const char* name, cudaStream_t st) : name_(name), st_(st), 
 }
 
 ProfScope::~ProfScope() {
+  if (nvtx_on()) nvtxRangePop();
   if (on_) {
     cudaEventRecord(e1_, st_);
     std::lock_guard<std::mutex> lk(g_prof_mu);
