@@ -365,8 +365,10 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
   if (all || stage == DPD_BWD_L4) {
     if (is_tc(L.impl) && !tc_bwd && (rc = tc_merge_activations(*cfg, is_f16(L.impl), ws + W.tc, chunk, rows, ha, hb, st))) return rc;
     if ((rc = launch_row_active(d_grad_out, rows, active, st))) return rc;
+    unsigned* amax3 = nullptr;
+    if (tc_bwd && (rc = tc_backward_begin(*cfg, ws + W.tc, chunk, &amax3, st))) return rc;
     if ((rc = launch_out_backward(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
-                                  d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st))) return rc;
+                                  d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st, amax3))) return rc;
     if (d_gw4 && (rc = launch_reduce_out_partials(part4, OUT_BWD_CTAS, H, d_gw4, d_gb4, st))) return rc;
   }
   TnParams tp;

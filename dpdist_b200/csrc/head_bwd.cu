@@ -21,13 +21,15 @@ __global__ void row_active_kernel(const float* __restrict__ g, int M, int* __res
 __global__ void __launch_bounds__(256) out_backward_kernel(const float* __restrict__ h3, const float* __restrict__ w4,
                                                            const float* __restrict__ b4, const float* __restrict__ mask,
                                                            const float* __restrict__ grad_out, const int* __restrict__ active,
-                                                           float* __restrict__ dz3, float* __restrict__ partial4, int M, int H) {
+                                                           float* __restrict__ dz3, float* __restrict__ partial4, int M, int H,
+                                                           unsigned* __restrict__ absmax_bits) {
   extern __shared__ float red[];   // [8 warps][H*3 + 3]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = gridDim.x * 8;
   constexpr int MAXQ = 8;          // H <= 1024: up to 8 column quads per lane
   float gw[MAXQ][4][3];
   float gb[3] = {0.f, 0.f, 0.f};
+  float amax = 0.f;          // max |dZ3| written by this thread (feeds the tensor-core backward's operand scale)
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i)
 #pragma unroll
@@ -78,10 +80,16 @@ __global__ void __launch_bounds__(256) out_backward_kernel(const float* __restri
           gw[i][e][2] = fmaf(x[e], dz[2], gw[i][e][2]);
           const float d = dz[0] * __ldg(w4 + (n + e) * 3 + 0) + dz[1] * __ldg(w4 + (n + e) * 3 + 1) + dz[2] * __ldg(w4 + (n + e) * 3 + 2);
           o[e] = x[e] > 0.f ? d : 0.f;
+          amax = fmaxf(amax, fabsf(o[e]));
         }
         *reinterpret_cast<float4*>(dz3 + (size_t)row * H + n) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
+  }
+  if (absmax_bits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.f) atomicMax(absmax_bits, __float_as_uint(amax));
   }
   // CTA reduction in fixed warp order -> partial4[cta]
   float* mine = red + warp * (H * 3 + 3);
@@ -320,12 +328,13 @@ int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st
 }
 
 int launch_out_backward(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
-                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st) {
+                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st,
+                        unsigned* absmax_bits) {
   DPD_REQUIRE(H % 128 == 0 && H <= 1024, DPD_E_UNSUPPORTED, "head backward: H=%d must be a multiple of 128, <= 1024", H);
   const size_t smem = (size_t)8 * (H * 3 + 3) * sizeof(float);
   static PerDeviceOnce attr_once;
   if (attr_once.need()) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4)); }
-  DPD_LAUNCH("bwd_out_l4", st, out_backward_kernel<<<n_cta, 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3, partial4, M, H));
+  DPD_LAUNCH("bwd_out_l4", st, out_backward_kernel<<<n_cta, 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3, partial4, M, H, absmax_bits));
   DPD_CUDA_CHECK_LAUNCH("out_backward_kernel");
   return 0;
 }

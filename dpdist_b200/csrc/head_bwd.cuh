@@ -15,7 +15,8 @@ int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st
 // dZ3[r,:] = (sum_j dz4[r,j] W4[:,j]) * (H3[r,:] > 0),   dz4 = grad_out * mask * relu6'(z4) / 3
 // partial4[cta][H*3 + 3] accumulates H3^T dz4 and sum_r dz4 per CTA (reduced in fixed order later).
 int launch_out_backward(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
-                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st);
+                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st,
+                        unsigned* absmax_bits = nullptr);
 int launch_reduce_out_partials(const float* partial4, int n_cta, int H, float* gw4, float* gb4, cudaStream_t st);
 
 struct TnParams {

@@ -132,22 +132,6 @@ __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
-// |x|max over the ACTIVE 128-row blocks of x [rows, H] (inactive blocks hold stale data and are never read)
-__global__ void absmax_active_kernel(const float* __restrict__ x, int rows, int H, const int* __restrict__ active,
-                                     unsigned* __restrict__ out_bits) {
-  const int sub = blockIdx.x;                 // 32-row sub-block of a 128-row block
-  if (active && !active[sub >> 2]) return;
-  const size_t lo = (size_t)sub * 32 * H, hi = min((size_t)rows, (size_t)(sub + 1) * 32) * H;
-  float m = 0.f;
-  for (size_t i = lo + threadIdx.x * 4; i < hi; i += blockDim.x * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(x + i);
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
-}
-
 // (hi, lo) = fp16 split of x * scale for active 128-row blocks, zeros for inactive ones
 __global__ void split_f16_active_kernel(const float* __restrict__ x, int rows, int H, const int* __restrict__ active,
                                         const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -188,17 +172,21 @@ __global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, in
 // dX = dZ . W^T) AND transposed [H, Mp] (operand of dW = A^T . dZ); zeros for inactive 128-row blocks.
 __global__ void split_transpose_f16_kernel(const float* __restrict__ dz, int rows, int H, int Mp, const int* __restrict__ active,
                                            const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
-                                           __half* __restrict__ thi, __half* __restrict__ tlo, const int* __restrict__ extent) {
+                                           __half* __restrict__ thi, __half* __restrict__ tlo, const int* __restrict__ extent,
+                                           float* __restrict__ col_partial) {
   __shared__ __half th[64][66], tl[64][66];
+  __shared__ float csum[8][64];
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   if (extent && m0 >= *extent) return;       // past the last active block: neither product reads these rows
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const bool on = !active || active[m0 >> 7];
   const float s = *scale;
+  float cs0 = 0.f, cs1 = 0.f;               // column sums of this thread's 8 rows (bias gradient, fixed order)
   for (int r = ty; r < 64; r += 8) {
     const int m = m0 + r;
     float2 v = make_float2(0.f, 0.f);
     if (on && m < rows) v = *reinterpret_cast<const float2*>(dz + (size_t)m * H + c0 + 2 * tx);
+    cs0 += v.x; cs1 += v.y;
     __half h0, l0, h1, l1;
     split_half(v.x * s, h0, l0); split_half(v.y * s, h1, l1);
     if (m < rows) {
@@ -207,11 +195,38 @@ __global__ void split_transpose_f16_kernel(const float* __restrict__ dz, int row
     }
     th[r][2 * tx] = h0; th[r][2 * tx + 1] = h1; tl[r][2 * tx] = l0; tl[r][2 * tx + 1] = l1;
   }
+  csum[ty][2 * tx] = cs0; csum[ty][2 * tx + 1] = cs1;
   __syncthreads();
   for (int c = ty; c < 64; c += 8) {
     const size_t o = (size_t)(c0 + c) * Mp + m0 + 2 * tx;
     *reinterpret_cast<__half2*>(thi + o) = __halves2half2(th[2 * tx][c], th[2 * tx + 1][c]);
     *reinterpret_cast<__half2*>(tlo + o) = __halves2half2(tl[2 * tx][c], tl[2 * tx + 1][c]);
+  }
+  if (col_partial != nullptr && threadIdx.x < 64) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += csum[j][threadIdx.x];
+    col_partial[(size_t)blockIdx.x * H + c0 + threadIdx.x] = a;
+  }
+}
+
+// gb[c] = sum over the 64-row blocks below the active extent of col_partial[b][c].  CTA = 64 columns x 16 block lanes;
+// lane j sums blocks j, j+16, ... in order, then the 16 lane sums are added in order (deterministic).
+__global__ void __launch_bounds__(1024) colsum_blocks_final_kernel(const float* __restrict__ col_partial, const int* __restrict__ extent,
+                                                                   int H, float* __restrict__ gb) {
+  __shared__ float red[16][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + tx;
+  const int nb = (*extent + 63) / 64;
+  float a = 0.f;
+  for (int b = ty; b < nb; b += 16) a += col_partial[(size_t)b * H + c];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t += red[j][tx];
+    gb[c] = t;
   }
 }
 
@@ -220,30 +235,53 @@ __global__ void split_transpose_f16_kernel(const float* __restrict__ dz, int row
 __global__ void gather_transpose_f16_kernel(const GatherArgs g, int rows, int Mp, __half* __restrict__ pth,
                                             __half* __restrict__ ptl, const int* __restrict__ extent) {
   __shared__ __half th[64][66], tl[64][66];     // [k within block][row]
+  __shared__ long long row_base[64];            // element offset of the row's cloud in the FV tensor, -1 past the end
+  __shared__ int row_vox[64];                   // i0 | i1 << 8 | i2 << 16
+  __shared__ int lut[16];                       // per 4-element chunk of this K-block: tap (a0 | a1<<8 | a2<<16) | part << 24, -1 offsets, -2 zero
   const int m0 = blockIdx.x * 64, kb = blockIdx.y;
   if (extent && m0 >= *extent) return;
   const int G = g.G, Cc = g.C, kk = g.k, pb = (g.k - 1) >> 1, V = G * G * G, ech = g.E / 4;
   const __half* fv_hi = (const __half*)g.fv_hi; const __half* fv_lo = (const __half*)g.fv_lo;
   const __half* o4_hi = (const __half*)g.off4_hi; const __half* o4_lo = (const __half*)g.off4_lo;
+  if (threadIdx.x < 64) {          // the decode that does not depend on the K-block ...
+    const int m = m0 + threadIdx.x;
+    long long base = -1; int vox = 0;
+    if (m < rows) {
+      const int v = __ldg(g.idx + m);
+      base = ((g.row0 + m) / g.n_query) * (long long)V * Cc;
+      vox = (v / (G * G)) | (((v / G) % G) << 8) | ((v % G) << 16);
+    }
+    row_base[threadIdx.x] = base; row_vox[threadIdx.x] = vox;
+  } else if (threadIdx.x < 80) {   // ... and the one that does not depend on the row
+    const int q = kb * 16 + (threadIdx.x - 64);
+    int code = -2;
+    if (q < ech) {
+      const int e = q * 4, j = e / Cc, part = e - j * Cc;
+      code = (j / (kk * kk)) | (((j / kk) % kk) << 8) | ((j % kk) << 16) | (part << 24);
+    } else if (q == ech) {
+      code = -1;
+    }
+    lut[threadIdx.x - 64] = code;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
     const int r = i >> 4, chunk = i & 15;
-    const int m = m0 + r, q = kb * 16 + chunk;
+    const long long base = row_base[r];
+    const int code = lut[chunk];
     uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
-    if (m < rows) {
-      if (q < ech) {
-        const int e = q * 4, j = e / Cc, part = e - j * Cc;
-        const int a2 = j % kk, a1 = (j / kk) % kk, a0 = j / (kk * kk);
-        const int v = __ldg(g.idx + m);
-        const int n0 = v / (G * G) + a0 - pb, n1 = (v / G) % G + a1 - pb, n2 = v % G + a2 - pb;
+    if (base >= 0 && code != -2) {
+      if (code == -1) {
+        vh = *reinterpret_cast<const uint2*>(o4_hi + (size_t)(m0 + r) * 4);
+        vl = *reinterpret_cast<const uint2*>(o4_lo + (size_t)(m0 + r) * 4);
+      } else {
+        const int vox = row_vox[r];
+        const int n0 = (vox & 255) + (code & 255) - pb, n1 = ((vox >> 8) & 255) + ((code >> 8) & 255) - pb;
+        const int n2 = ((vox >> 16) & 255) + ((code >> 16) & 255) - pb;
         if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
-          const long long cloud = (g.row0 + m) / g.n_query;
-          const size_t el = (size_t)cloud * V * Cc + (size_t)((n0 * G + n1) * G + n2) * Cc + part;
+          const size_t el = (size_t)base + (size_t)((n0 * G + n1) * G + n2) * Cc + (code >> 24);
           vh = *reinterpret_cast<const uint2*>(fv_hi + el);
           vl = *reinterpret_cast<const uint2*>(fv_lo + el);
         }
-      } else if (q == ech) {
-        vh = *reinterpret_cast<const uint2*>(o4_hi + (size_t)m * 4);
-        vl = *reinterpret_cast<const uint2*>(o4_lo + (size_t)m * 4);
       }
     }
     const __half* ph = reinterpret_cast<const __half*>(&vh);
@@ -260,31 +298,6 @@ __global__ void gather_transpose_f16_kernel(const GatherArgs g, int rows, int Mp
   }
 }
 
-// bias gradients: column sums of dz over the active rows, two deterministic levels (32 row slices, then in order)
-constexpr int COLSUM_SLICES = 32;
-__global__ void colsum_partial_kernel(const float* __restrict__ dz, int rows, int H, const int* __restrict__ active,
-                                      float* __restrict__ partial) {
-  __shared__ float red[4][64];
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63), ty = threadIdx.x >> 6, sl = blockIdx.y;
-  const int nblk = (rows + 127) / 128;
-  float a = 0.f;
-  for (int blk = sl; blk < nblk; blk += COLSUM_SLICES) {
-    if (active && !active[blk]) continue;
-    const int r1 = min(rows, (blk + 1) * 128);
-    for (int r = blk * 128 + ty; r < r1; r += 4) a += dz[(size_t)r * H + c];
-  }
-  red[ty][threadIdx.x & 63] = a;
-  __syncthreads();
-  if (ty == 0) partial[(size_t)sl * H + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
-}
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int H, float* __restrict__ gb) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= H) return;
-  float a = 0.f;
-  for (int s = 0; s < COLSUM_SLICES; ++s) a += partial[(size_t)s * H + c];
-  gb[c] = a;
-}
-
 // rows covered by the active blocks: (index of the last active 128-row block + 1) * 128, clipped to `rows`
 __global__ void active_extent_kernel(const int* __restrict__ active, int nblk, int rows, int* __restrict__ out) {   // one warp
   int last = -1;
@@ -296,8 +309,9 @@ __global__ void active_extent_kernel(const int* __restrict__ active, int nblk, i
 
 // backward products: sc[0] = |dZ|max bits -> sc[1] = s_g, sc[2] = 1 / (s_g * *other_scale)
 // and sc[3] = 1 / (s_g * *act_scale) for the weight-gradient product
-__global__ void bwd_scales_kernel(float* __restrict__ sc, const float* __restrict__ other_scale, const float* __restrict__ act_scale) {   // one thread
-  const float m = __uint_as_float(reinterpret_cast<const unsigned*>(sc)[0]);
+__global__ void bwd_scales_kernel(float* __restrict__ sc, const float* __restrict__ other_scale, const float* __restrict__ act_scale,
+                                  const unsigned* __restrict__ amax_bits) {   // one thread
+  const float m = __uint_as_float(amax_bits ? *amax_bits : reinterpret_cast<const unsigned*>(sc)[0]);
   const float sg = m > 0.f ? pow2_floor_scale(m) : 1.0f;
   sc[1] = sg;
   sc[2] = other_scale ? 1.0f / (sg * *other_scale) : 0.f;
@@ -467,6 +481,7 @@ struct BwdExtras {
   int slices = 1;
   const int* k_limit = nullptr;
   long long slice_stride = 0;
+  unsigned* absmax_bits = nullptr;
   const char* name = nullptr;
 };
 
@@ -501,7 +516,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   if (bx) {
     DPD_REQUIRE(!gather && !split && part4 == nullptr, DPD_E_UNSUPPORTED, "tc gemm2: backward modes need the dense fp32-output kernel");
     ka.mode = bx->mode; ka.gate_hi = bx->gate_hi; ka.gate_lo = bx->gate_lo; ka.active = bx->active; ka.k_limit = bx->k_limit;
-    ka.slices = bx->slices; ka.slice_stride = bx->slice_stride;
+    ka.slices = bx->slices; ka.slice_stride = bx->slice_stride; ka.absmax_bits = bx->absmax_bits;
     // K-blocks per slice: a multiple of the promotion segment so that segments never straddle slices
     ka.kb_per_slice = round_up(ceil_div(K / 64, bx->slices > 1 ? bx->slices : 1), 4);
     tiles *= bx->slices > 1 ? bx->slices : 1;
@@ -604,7 +619,7 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
     w.pth = o; o += up256(rows * Kp1 * e); w.ptl = o; o += up256(rows * Kp1 * e);
     const size_t p1 = (size_t)TC_DW1_SLICES * Kp1 * c.H * 4, p2 = (size_t)TC_DW_SLICES * c.H * c.H * 4;
     w.part = o; o += up256(p1 > p2 ? p1 : p2);
-    w.cpart = o; o += up256((size_t)tc::COLSUM_SLICES * c.H * 4);
+    w.cpart = o; o += up256((rows / 64 + 1) * (size_t)c.H * 4);      // per-64-row-block column sums of dZ
     w.bsc = o; o += up256(64 * 4);
   }
   w.scales = o; o += up256(tc::S_COUNT * 4);
@@ -695,12 +710,13 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
   const float* w_scale = layer == 3 ? ps + tc::P_W3 : layer == 2 ? ps + tc::P_W2 : nullptr;
   __half* gh = (__half*)(ws + w.gh); __half* gl = (__half*)(ws + w.gl);
   __half* gth = (__half*)(ws + w.gth); __half* gtl = (__half*)(ws + w.gtl);
-  DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
-  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<ceil_div(rows, 32), 256, 0, st>>>(dz, rows, H, active, (unsigned*)bsc));
-  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, w_scale, act_scale));
+  // |dZ|max was left in the layer's slot by the kernel that produced dZ (layer-4 backward or the previous dX product)
+  unsigned* slots = (unsigned*)(bsc + 16);
+  float* cpart = (float*)(ws + w.cpart);
+  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, w_scale, act_scale, slots + layer));
   DPD_LAUNCH("bwd_scales", st, tc::active_extent_kernel<<<1, 32, 0, st>>>(active, nblk, rows, extent));
   DPD_LAUNCH("bwd_split_transpose", st, tc::split_transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(
-      dz, rows, H, Mp, active, bsc + 1, gh, gl, gth, gtl, extent));
+      dz, rows, H, Mp, active, bsc + 1, gh, gl, gth, gtl, extent, gw != nullptr ? cpart : nullptr));
   DPD_CUDA_CHECK_LAUNCH("tc_backward_layer prep");
   int rc;
   if (gw != nullptr) {
@@ -729,10 +745,8 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
     float* part = (float*)(ws + w.part);
     if ((rc = tc::launch2(false, ath, atl, Mo, Mp, gth, gtl, H, nullptr, part, nullptr, 0, bsc + 3, nullptr, nullptr, st, nullptr,
                           nullptr, &bx))) return rc;
-    // gb = column sums of dZ over the active rows
-    float* cpart = (float*)(ws + w.cpart);
-    DPD_LAUNCH("bwd_colsum", st, tc::colsum_partial_kernel<<<dim3(H / 64, tc::COLSUM_SLICES), 256, 0, st>>>(dz, rows, H, active, cpart));
-    DPD_LAUNCH("bwd_colsum", st, tc::colsum_final_kernel<<<ceil_div(H, 256), 256, 0, st>>>(cpart, H, gb));
+    // gb = column sums of dZ over the active rows: per-block partials came out of the split pass
+    DPD_LAUNCH("bwd_colsum", st, tc::colsum_blocks_final_kernel<<<H / 64, 1024, 0, st>>>(cpart, extent, H, gb));
     DPD_CUDA_CHECK_LAUNCH("tc_backward_layer colsum");
     if (layer == 1) rc = launch_reduce_partials(part, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices);
     else rc = launch_reduce_partials(part, nullptr, H, H, H, 0, 0, gw, nullptr, st, bx.slices);
@@ -740,7 +754,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
   }
   if (dz_next != nullptr) {
     tc::BwdExtras bx;
-    bx.mode = 1; bx.active = active;
+    bx.mode = 1; bx.active = active; bx.absmax_bits = slots + (layer - 1);
     bx.gate_hi = ws + (layer == 3 ? w.yh : w.xh); bx.gate_lo = ws + (layer == 3 ? w.yl : w.xl);
     if ((rc = tc::launch2(false, gh, gl, rows, H, blob + (layer == 3 ? b.w3nh : b.w2nh), blob + (layer == 3 ? b.w3nl : b.w2nl), H,
                           nullptr, dz_next, nullptr, 0, bsc + 2, nullptr, nullptr, st, nullptr, nullptr, &bx))) return rc;
@@ -749,6 +763,16 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
 }
 
 int tc_kp1(const dpd_head_config& c) { return kp1_of(c, true); }
+
+// |dZ|max slots of the tensor-core backward: zeroed at the start of a backward pass; slot 3 is filled by the layer-4
+// backward kernel, slots 2 and 1 by the dX products
+int tc_backward_begin(const dpd_head_config& c, void* tc_ws, size_t ws_rows, unsigned** slot3, cudaStream_t st) {
+  const TcWs w = tc_ws_layout(c, true, ws_rows);
+  float* bsc = (float*)((char*)tc_ws + w.bsc);
+  DPD_CUDA_CALL(cudaMemsetAsync(bsc + 16, 0, 16, st));
+  *slot3 = (unsigned*)(bsc + 16) + 3;
+  return 0;
+}
 
 // dX1 = dZ1 . W1p^T for the input-gradient path.  prepare: measure / scale / split dZ1 once; rows: one group of rows.
 int tc_backward_inputs_prepare(const dpd_head_config& c, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
@@ -759,9 +783,7 @@ int tc_backward_inputs_prepare(const dpd_head_config& c, const void* tc_blob, vo
   const int H = c.H, nblk = ceil_div(rows, 128);
   float* bsc = (float*)(ws + w.bsc);
   const float* ps = (const float*)((const char*)tc_blob + b.scales);
-  DPD_CUDA_CALL(cudaMemsetAsync(bsc, 0, 16, st));
-  DPD_LAUNCH("bwd_absmax", st, tc::absmax_active_kernel<<<ceil_div(rows, 32), 256, 0, st>>>(dz1, rows, H, active, (unsigned*)bsc));
-  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, ps + tc::P_W1, ps + tc::P_W1));
+  DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, ps + tc::P_W1, ps + tc::P_W1, (const unsigned*)(bsc + 16) + 1));
   DPD_LAUNCH("bwd_split", st, tc::split_f16_active_kernel<<<nblk, 256, 0, st>>>(
       dz1, rows, H, active, bsc + 1, (__half*)(ws + w.gh), (__half*)(ws + w.gl)));
   DPD_CUDA_CHECK_LAUNCH("tc_backward_inputs_prepare");

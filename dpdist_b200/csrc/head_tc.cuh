@@ -35,6 +35,8 @@ int tc_merge_activations(const dpd_head_config& c, bool f16, void* tc_ws, size_t
 
 // tensor-core backward (fp16x3, 2-CTA kernel, training configuration)
 bool tc_backward_supported(const dpd_head_config& c, bool f16);
+// start of a backward pass: resets the |dZ|max slots and returns the one the layer-4 backward kernel must fill
+int tc_backward_begin(const dpd_head_config& c, void* tc_ws, size_t ws_rows, unsigned** slot3, cudaStream_t st);
 // one layer (3, 2 or 1) of the backward pass: gw / gb (skipped when gw == nullptr) and, for layers 3 and 2, dz_next
 int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
                       const GatherDesc* g, const float* dz, float* dz_next, const int* active, float* gw, float* gb,

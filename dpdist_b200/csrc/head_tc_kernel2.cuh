@@ -394,6 +394,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           }
         }
       } else {
+        float tile_amax = 0.f;
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll
@@ -418,6 +419,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                                            __ldg(reinterpret_cast<const uint32_t*>((const __half*)args.gate_lo + o))) & 0x7fff7fffu;
                       if ((gb & 0xffffu) == 0) x0 = 0.f;
                       if ((gb >> 16) == 0) x1 = 0.f;
+                      tile_amax = fmaxf(tile_amax, fmaxf(fabsf(x0), fabsf(x1)));
                     }
                   }
                   *reinterpret_cast<float2*>((float*)args.out0 + (size_t)sl * (size_t)args.slice_stride + o) = make_float2(x0, x1);
@@ -425,6 +427,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               }
             }
           }
+        }
+        if (args.mode == 1 && args.absmax_bits != nullptr) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) tile_amax = fmaxf(tile_amax, __shfl_xor_sync(0xffffffffu, tile_amax, o));
+          if (lane == 0 && tile_amax > 0.f) atomicMax(args.absmax_bits, __float_as_uint(tile_amax));
         }
       }
     }
