@@ -173,3 +173,32 @@ def test_training_and_input_gradients_together():
         ref = t.grad
         err = float((store.vars[n].grad.cpu().double() - ref).abs().max())
         assert err <= 2e-4 * float(ref.abs().max()), n
+
+
+def test_anchor_gradients_match_the_golden_fixture():
+    """Config A of BASELINE.json against the committed fixture (tests/golden/anchor_A.npz, fp64 twin of the oracle): the
+    consumers' loss differentiated into both clouds, and the training loss into the variables."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "anchor_A.npz"))
+    var = O.unit_scale_variables(int(z["weight_seed"]))
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    a = torch.tensor(z["pcA"], device=DEV, requires_grad=True)
+    b = torch.tensor(z["pcB"], device=DEV, requires_grad=True)
+    with tf_util.use_store(store):
+        pred, _, _ = MODEL.get_model(a, b, False, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+    ((pred["pred_listAB"][..., 0].mean() + pred["pred_listBA"][..., 0].mean()) / 2).backward()
+    assert_grad_close(a.grad, z["grad_input1"], "golden d loss / d input1", frac=0.95)
+    assert_grad_close(b.grad, z["grad_input2"], "golden d loss / d input2", frac=0.95)
+    tf_util.clear_collections()
+    with tf_util.use_store(store):
+        pred, ep, _ = MODEL.get_model(a.detach(), b.detach(), True, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+        MODEL.get_loss(pred, ep, torch.tensor(z["labels"], device=DEV))
+    tf_util.get_collection("loss_samples")[-1].backward()
+    names = sorted(store.vars)
+    sums = np.array([float(store.vars[n].grad.double().abs().sum()) for n in names])
+    assert np.allclose(sums, z["grad_abs_sums"], rtol=2e-4), (sums, z["grad_abs_sums"])
+    w4 = store.vars[O.VAR_PREFIX + "mapper_conv4/weights"].grad.cpu().numpy()
+    assert np.abs(w4 - z["grad_w4"]).max() <= 2e-4 * np.abs(z["grad_w4"]).max()
+    b1 = store.vars[O.VAR_PREFIX + "mapper_conv1/biases"].grad.cpu().numpy()
+    assert np.abs(b1 - z["grad_b1"]).max() <= 2e-4 * np.abs(z["grad_b1"]).max()
