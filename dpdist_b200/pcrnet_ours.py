@@ -114,13 +114,19 @@ def compose(TRANSFORMATIONS, pose7):
 class IterativePCRNetOurs:
     """One trainer: `train_step(source, template)` = iterative_PCRNet_ours.py:407-471 for one batch."""
 
-    def __init__(self, dpdist, max_loops=8, learning_rate=0.001, train_single=False, device=None, seed=0):
+    def __init__(self, dpdist, max_loops=8, learning_rate=0.001, train_single=False, device=None, seed=0, cuda_graph=False):
         self.dpdist = dpdist
         self.device = torch.device(device) if device is not None else next(dpdist.parameters()).device
         torch.manual_seed(seed)
         self.net = PCRNet().to(self.device)
-        self.opt = torch.optim.Adam(self.net.parameters(), lr=learning_rate, eps=1e-8)       # TF AdamOptimizer defaults
+        # cuda_graph=True: the whole batch step (max_loops pose refinements, the DPDist loss forward and backward, Adam) is
+        # captured once per batch shape and replayed -- at batch 16 the step is otherwise bound by ~150 tiny launches
+        self.cuda_graph = bool(cuda_graph)
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=learning_rate, eps=1e-8,       # TF AdamOptimizer defaults
+                                    capturable=self.cuda_graph)
         self.max_loops, self.train_single = int(max_loops), bool(train_single)
+        self._side = torch.cuda.Stream(device=self.device) if self.cuda_graph else None
+        self._graph, self._eager_steps = None, 0
 
     def _predict(self, source, template):
         pose = self.net(source, template)
@@ -128,14 +134,40 @@ class IterativePCRNetOurs:
         return pose, transformation_quat_tensor(source, quat, pose[:, 0:3])
 
     def _trained_step(self, source, template):
-        self.opt.zero_grad(set_to_none=True)
         pose, moved = self._predict(source, template)
         loss = self.dpdist.loss(moved, template)                 # gradients reach the pose network through input1 only
-        loss.backward()
+        params = [p for p in self.net.parameters()]
+        # autograd.grad (no gradient accumulators): identical in eager mode, and safe inside a stream capture
+        for p, g in zip(params, torch.autograd.grad(loss, params)):
+            p.grad = g
         self.opt.step()
         return pose.detach(), loss.detach()
 
     def train_step(self, source, template):
+        if not self.cuda_graph:
+            return self._train_step(source, template)
+        if self._eager_steps < 3:                                # warm-up on the stream the capture will use
+            self._eager_steps += 1
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                out = self._train_step(source, template)
+            cur.wait_stream(self._side)
+            return out
+        gs = self._graph
+        if gs is None or gs["shape"] != tuple(source.shape):
+            gs = {"shape": tuple(source.shape), "src": source.clone(), "tpl": template.clone()}
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=self._side):
+                gs["out"] = self._train_step(gs["src"], gs["tpl"])
+            gs["graph"] = graph
+            self._graph = gs
+        gs["src"].copy_(source, non_blocking=True)
+        gs["tpl"].copy_(template, non_blocking=True)
+        gs["graph"].replay()
+        return gs["out"]
+
+    def _train_step(self, source, template):
         B = source.shape[0]
         T = torch.eye(4, device=self.device).repeat(B, 1, 1)
         self.net.train()
@@ -182,13 +214,14 @@ def main(argv=None):
     ap.add_argument("--max_epoch", type=int, default=2)
     ap.add_argument("--num_templates", type=int, default=64)
     ap.add_argument("--train_single", type=int, default=0)
+    ap.add_argument("--cuda_graph", type=int, default=0)
     ap.add_argument("--model_path", default="", help="DPDist checkpoint (TF V2 prefix or .npz); random init if empty")
     args = ap.parse_args(argv)
     dev = torch.device("cuda", 0)
     dpd = DPDistLoss(num_point=args.num_point, device=dev, seed=1)
     if args.model_path:
         dpd.restore(args.model_path)
-    tr = IterativePCRNetOurs(dpd, args.max_loops, args.learning_rate, bool(args.train_single), dev)
+    tr = IterativePCRNetOurs(dpd, args.max_loops, args.learning_rate, bool(args.train_single), dev, cuda_graph=bool(args.cuda_graph))
     rng = np.random.default_rng(0)
     templates = synthetic_templates(args.num_templates, args.num_point, seed=3)
     for epoch in range(args.max_epoch):

@@ -87,3 +87,26 @@ def test_pcrnet_step_trains_only_the_pose_network():
     assert_close(chk, moved, 1e-4, 1e-5, "accumulated transformation")
     T2, moved2 = tr.register(torch.tensor(src, device=DEV), torch.tensor(tpl, device=DEV))
     assert torch.isfinite(moved2).all()
+
+
+def test_pcrnet_graph_step_matches_eager():
+    """The captured PCRNet-ours batch step replays to the same pose-network weights as the eager one (dropout off)."""
+    var = O.unit_scale_variables(4)
+    rng = np.random.default_rng(0)
+    tpl = pcrnet_ours.synthetic_templates(16, 64, seed=1)
+    src = pcrnet_ours.apply_transformation(tpl, pcrnet_ours.generate_poses(16, rng))
+    s, t = torch.tensor(src, device=DEV), torch.tensor(tpl, device=DEV)
+    res = []
+    for graph in (False, True):
+        m = _loss_module(var)
+        tr = pcrnet_ours.IterativePCRNetOurs(m, max_loops=3, learning_rate=1e-3, device=DEV, seed=0, cuda_graph=graph)
+        tr.net.dp4.p = 0.0                                   # no dropout: the two runs must see the same network
+        # the same optimizer arithmetic in both runs (capturable Adam keeps its step count on the device)
+        tr.opt = torch.optim.Adam(tr.net.parameters(), lr=1e-3, eps=1e-8, capturable=True)
+        losses = [tr.train_step(s, t)[0].clone() for _ in range(6)]
+        torch.cuda.synchronize()
+        res.append((torch.stack(losses).cpu(), [p.detach().cpu().clone() for p in tr.net.parameters()]))
+    assert tr._graph is not None
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-4, atol=1e-7), (res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), float((a - b).abs().max())
