@@ -475,8 +475,7 @@ static bool fuse_l4() {
 // optional backward-pass behaviour of launch2 (see KernelArgs)
 struct BwdExtras {
   int mode = 0;
-  const void* gate_hi = nullptr;
-  const void* gate_lo = nullptr;
+  const uint4* relu_bits_in = nullptr;
   const int* active = nullptr;
   int slices = 1;
   const int* k_limit = nullptr;
@@ -488,7 +487,7 @@ struct BwdExtras {
 static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo, int N,
                    const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
                    const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr,
-                   const BwdExtras* bx = nullptr) {
+                   const BwdExtras* bx = nullptr, uint4* relu_bits_out = nullptr) {
   DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
   DPD_REQUIRE(!gather || K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -504,7 +503,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   KernelArgs ka;
   memset(&ka, 0, sizeof(ka));
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
-  ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4;
+  ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4; ka.relu_bits_out = relu_bits_out;
   if (g) {
     ka.g = *g;
     if (gather) {   // valid operand length E + 3; everything from there to K is zero padding
@@ -515,7 +514,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   int tiles = ceil_div(M, 2 * BM) * (N / BN);
   if (bx) {
     DPD_REQUIRE(!gather && !split && part4 == nullptr, DPD_E_UNSUPPORTED, "tc gemm2: backward modes need the dense fp32-output kernel");
-    ka.mode = bx->mode; ka.gate_hi = bx->gate_hi; ka.gate_lo = bx->gate_lo; ka.active = bx->active; ka.k_limit = bx->k_limit;
+    ka.mode = bx->mode; ka.relu_bits_in = bx->relu_bits_in; ka.active = bx->active; ka.k_limit = bx->k_limit;
     ka.slices = bx->slices; ka.slice_stride = bx->slice_stride; ka.absmax_bits = bx->absmax_bits;
     // K-blocks per slice: a multiple of the promotion segment so that segments never straddle slices
     ka.kb_per_slice = round_up(ceil_div(K / 64, bx->slices > 1 ? bx->slices : 1), 4);
@@ -530,9 +529,10 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
 // D[M,N] = relu(acc_scale * A[M,K] * B[N,K]^T + bias), operands pre-split (hi, lo); K % kb == 0, N % 256 == 0
 static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo,
                   int N, const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
-                  const GatherArgs* g, cudaStream_t st) {
+                  const GatherArgs* g, cudaStream_t st, uint4* relu_bits_out = nullptr) {
   if (f16 && use_2cta())
-    return launch2(gather, a_hi, a_lo, M, K, bt_hi, bt_lo, N, bias, out0, out1, split, acc_scale, out_scale, g, st);
+    return launch2(gather, a_hi, a_lo, M, K, bt_hi, bt_lo, N, bias, out0, out1, split, acc_scale, out_scale, g, st, nullptr, nullptr,
+                   nullptr, relu_bits_out);
   const int kb = f16 ? 64 : 32;
   DPD_REQUIRE(K % kb == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm: need K %% %d == 0, N %% 256 == 0 (K=%d N=%d)", kb, K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm: K=%d too large", K);
@@ -602,7 +602,7 @@ TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
 }
 constexpr int TC_DW_SLICES = 9;       // dW2 / dW3: 16 tiles x 9 slices = 144 work items on 74 clusters (1.95 waves)
 constexpr int TC_DW1_SLICES = 11;     // dW1: 40 tiles x 11 = 440 (5.95 waves)
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, gth, gtl, hth, htl, pth, ptl, part, cpart, bsc, scales, total; };
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, gth, gtl, hth, htl, pth, ptl, part, cpart, rb1, rb2, bsc, scales, total; };
 TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -611,7 +611,7 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
   w.yh = w.yl = o;
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
-  w.gh = w.gl = w.gth = w.gtl = w.hth = w.htl = w.pth = w.ptl = w.part = w.cpart = w.bsc = o;
+  w.gh = w.gl = w.gth = w.gtl = w.hth = w.htl = w.pth = w.ptl = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
   if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient (row-major and transposed), transposed
     const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);        // activations / patches, partials
     w.gh = o; o += act; w.gl = o; o += act; w.gth = o; o += act; w.gtl = o; o += act;
@@ -620,6 +620,9 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
     const size_t p1 = (size_t)TC_DW1_SLICES * Kp1 * c.H * 4, p2 = (size_t)TC_DW_SLICES * c.H * c.H * 4;
     w.part = o; o += up256(p1 > p2 ? p1 : p2);
     w.cpart = o; o += up256((rows / 64 + 1) * (size_t)c.H * 4);      // per-64-row-block column sums of dZ
+    // ReLU' bit masks of H1 / H2: one uint4 per (256x256 tile, CTA of the pair, epilogue warp, lane)
+    const size_t nbits = ((rows + 255) / 256) * (size_t)(c.H / tc::BN) * 2 * tc::NUM_EPI_WARPS * 32 * 16;
+    w.rb1 = o; o += up256(nbits); w.rb2 = o; o += up256(nbits);
     w.bsc = o; o += up256(64 * 4);
   }
   w.scales = o; o += up256(tc::S_COUNT * 4);
@@ -755,7 +758,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
   if (dz_next != nullptr) {
     tc::BwdExtras bx;
     bx.mode = 1; bx.active = active; bx.absmax_bits = slots + (layer - 1);
-    bx.gate_hi = ws + (layer == 3 ? w.yh : w.xh); bx.gate_lo = ws + (layer == 3 ? w.yl : w.xl);
+    bx.relu_bits_in = (const uint4*)(ws + (layer == 3 ? w.rb2 : w.rb1));
     if ((rc = tc::launch2(false, gh, gl, rows, H, blob + (layer == 3 ? b.w3nh : b.w2nh), blob + (layer == 3 ? b.w3nl : b.w2nl), H,
                           nullptr, dz_next, nullptr, 0, bsc + 2, nullptr, nullptr, st, nullptr, nullptr, &bx))) return rc;
   }
@@ -865,10 +868,11 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
         g.offset, mask, rows, sc + tc::S_A1, (__half*)(ws + w.o4h), (__half*)(ws + w.o4l)));
     DPD_CUDA_CHECK_LAUNCH("split_off4_f16_kernel");
     // layer 1: gathered A -> (xh, xl) scaled by sA2; layer 2 -> (yh, yl) scaled by sA3; layer 3 -> fp32
+    const bool bits = tc_train(c) && tc::use_2cta();    // ReLU' bit masks for the tensor-core backward
     if ((rc = tc::launch(true, true, nullptr, nullptr, rows, Kp1, blob + b.w1h, blob + b.w1l, H, b1, ws + w.xh, ws + w.xl, 1,
-                         sc + tc::S_ACC1, sc + tc::S_A2, &ga, st))) return rc;
+                         sc + tc::S_ACC1, sc + tc::S_A2, &ga, st, bits ? (uint4*)(ws + w.rb1) : nullptr))) return rc;
     if ((rc = tc::launch(false, true, ws + w.xh, ws + w.xl, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.yh, ws + w.yl, 1,
-                         sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st))) return rc;
+                         sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st, bits ? (uint4*)(ws + w.rb2) : nullptr))) return rc;
     if (fused_out != nullptr && tc::use_2cta() && tc::fuse_l4() && h3_out == nullptr) {
       // layer 3 with the output layer fused into its epilogue: H3 never reaches HBM.  `ha` (unused by this path)
       // holds the [rows, 2*H/256] float4 partials.

@@ -42,9 +42,12 @@ struct KernelArgs {
   const float* w4;         // [N,3] fp32 (reference layout of mapper_conv4/weights)
   float* part4;            // [M, 2*N/BN, 4]
   // ---- backward-pass extensions (2-CTA kernel, fp32 output only); all zero / nullptr in the forward pass ----
-  int mode;                // 0: relu(acc*scale + bias)   1: acc*scale where the gate is non-zero, else 0   2: acc*scale
-  const void* gate_hi;     // mode 1: (hi, lo) fp16 pair [M,N] of the forward activation; gate = (hi | lo) != 0, i.e. ReLU'
-  const void* gate_lo;
+  int mode;                // 0: relu(acc*scale + bias)   1: acc*scale where the gate bit is set, else 0   2: acc*scale
+  // ReLU' as one bit per output: written by the forward epilogue (split output, training) as a uint4 per thread, tile and
+  // epilogue warp, read back by the SAME thread of the dX product of the next layer (identical tile decomposition of
+  // [rows, N]), so the gate costs one coalesced 16-byte load instead of 128 scattered loads of the activation pair
+  uint4* relu_bits_out;    // forward: [tiles, 2 CTAs, 8 epilogue warps, 32 lanes]
+  const uint4* relu_bits_in;   // mode 1
   const int* active;       // optional per-128-row flags: a 256-row tile with both flags clear is skipped by every role
   int slices;              // split-K: work items = slices * tiles, item -> (slice, tile); 0 or 1 = no split
   int kb_per_slice;        // K-blocks per slice

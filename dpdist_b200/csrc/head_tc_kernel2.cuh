@@ -349,6 +349,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int ql = lane & 3;
         const int src_a = (lane & ~3) | (2 * (ql & 1)), src_b = src_a + 1;
         const bool upper = (ql >> 1) != 0;          // lanes 2,3 of the quad take the words of group j+1
+        uint32_t rb[4] = {0u, 0u, 0u, 0u};          // ReLU' bits of this thread's 128 outputs, bit index = index into sum[]
+        const bool want_bits = args.relu_bits_out != nullptr;
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll
@@ -368,6 +370,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                   const float2 bb = jj ? b1 : b0;
                   const float s0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f) * out_scale;
                   const float s1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f) * out_scale;
+                  if (want_bits) {
+                    const int vi = (rh * 2 + cg) * 32 + (2 * jp + jj) * 4 + u2 * 2;      // compile-time after unrolling
+                    rb[vi >> 5] |= (s0 > 0.f ? 1u : 0u) << (vi & 31);
+                    rb[vi >> 5] |= (s1 > 0.f ? 1u : 0u) << ((vi + 1) & 31);
+                  }
                   const __half2 hi = __floats2half2_rn(s0, s1);
                   const float2 hf = __half22float2(hi);
                   const __half2 lo = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
@@ -393,8 +400,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
           }
         }
+        if (want_bits)
+          args.relu_bits_out[(((size_t)t * 2 + rank) * NUM_EPI_WARPS + e) * 32 + lane] = make_uint4(rb[0], rb[1], rb[2], rb[3]);
       } else {
         float tile_amax = 0.f;
+        uint4 gbits = make_uint4(0u, 0u, 0u, 0u);
+        if (args.mode == 1) gbits = __ldg(args.relu_bits_in + (((size_t)t * 2 + rank) * NUM_EPI_WARPS + e) * 32 + lane);
+        const uint32_t gw[4] = {gbits.x, gbits.y, gbits.z, gbits.w};
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll
@@ -414,11 +426,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                     x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f); x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
                   } else {
                     x0 = sp[0] * acc_scale; x1 = sp[1] * acc_scale;
-                    if (args.mode == 1) {      // ReLU' of the forward activation: non-zero (hi | lo), sign bits ignored
-                      const uint32_t gb = (__ldg(reinterpret_cast<const uint32_t*>((const __half*)args.gate_hi + o)) |
-                                           __ldg(reinterpret_cast<const uint32_t*>((const __half*)args.gate_lo + o))) & 0x7fff7fffu;
-                      if ((gb & 0xffffu) == 0) x0 = 0.f;
-                      if ((gb >> 16) == 0) x1 = 0.f;
+                    if (args.mode == 1) {      // ReLU' of the forward activation, one bit per output (relu_bits_in)
+                      const int vi = (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
+                      if (((gw[vi >> 5] >> (vi & 31)) & 1u) == 0) x0 = 0.f;
+                      if (((gw[vi >> 5] >> ((vi + 1) & 31)) & 1u) == 0) x1 = 0.f;
                       tile_amax = fmaxf(tile_amax, fmaxf(fabsf(x0), fabsf(x1)));
                     }
                   }
