@@ -67,6 +67,18 @@ def get_model(pcA, pcB,
                 embedding_A, embedding_B = embedding_A.materialize(), embedding_B.materialize()
             return ({'pred_listAB': out[0], 'pred_listBA': out[1]}, {},
                     {'embedding_A': embedding_A, 'embedding_B': embedding_B})
+        inputs_need = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (pcA, pcB, add_noise))
+        if FUSED_INFERENCE and not inputs_need and NUM_DIMS == 3 and conv_version == 1 and not bn:
+            # training step of DPDist itself (the clouds are data): still one library call for 3DmFV + head, with an
+            # autograd node for the 8 variables
+            fv, out, C = dpdist.model_forward_train(torch.cat([pcA_noise, pcB], 0), torch.cat([pcB, pcA], 0), n_gaussians,
+                                                    sigma3dmfv, full_fv, k, localSNmlp, reuse=reuse)
+            out = out.view(2, B, pcA.shape[1], 1, 3)
+            embedding_A, embedding_B = dpdist.LocalPatches(fv[:B], k), dpdist.LocalPatches(fv[B:], k)
+            if materialize_embeddings:
+                embedding_A, embedding_B = embedding_A.materialize(), embedding_B.materialize()
+            return ({'pred_listAB': out[0], 'pred_listBA': out[1]}, {},
+                    {'embedding_A': embedding_A, 'embedding_B': embedding_B})
         # one launch encodes both clouds of every pair: rows [A | B]
         emb = dpdist.get_3dmfv_tf(torch.cat([pcA_noise, pcB], 0), n_gaussians=n_gaussians,
                                   flatten=flatten, full_fv=full_fv,

@@ -315,12 +315,18 @@ class _HeadFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        return _head_backward(ctx, grad_out)
+
+
+def _head_backward(ctx, grad_out, n_leading=5):
+    """Shared backward of the head nodes: (grad fv, grad query, None x (n_leading - 2), *weight grads)."""
+    if True:
         cache, cfg, fv = ctx.cache, ctx.cfg, ctx.fv
         if cache.generation != ctx.generation:
             raise RuntimeError("the activations of this forward were overwritten by a later DPDist call; call backward() first")
         lib = _lib.load()
         grad_out = grad_out.contiguous().float()
-        need_w = ctx.needs_input_grad[5:]
+        need_w = ctx.needs_input_grad[n_leading:]
         # a layer's weight and bias gradients come out of one product: compute both if either is asked for
         need_layer = [bool(need_w[2 * i] or need_w[2 * i + 1]) for i in range(4)]
         grads = [torch.empty(s, device=fv.device, dtype=torch.float32) if need_layer[i // 2] else None
@@ -343,8 +349,59 @@ class _HeadFunction(torch.autograd.Function):
                                                   _ptr(cache.ws), cache.ws.numel(), _stream())
                 _lib.check(rc, "dpd_head_backward_inputs")
         wg = tuple(g if need_w[i] else None for i, g in enumerate(grads))
-        return (grad_fv if ctx.needs_input_grad[0] else None, grad_query if ctx.needs_input_grad[1] else None,
-                None, None, None) + wg
+        return (grad_fv if ctx.needs_input_grad[0] else None, grad_query if ctx.needs_input_grad[1] else None) + \
+            (None,) * (n_leading - 2) + wg
+
+
+class _ModelTrainFunction(torch.autograd.Function):
+    """3DmFV + head in ONE library call (dpd_model_forward with DPD_HEAD_TRAIN) as an autograd node for the 8 variables:
+    the training step of a DPDist whose inputs are data (no gradient into the clouds).  Saves the separate |fv|max and
+    (hi, lo) split passes of the staged path; the backward is the head's."""
+
+    @staticmethod
+    def forward(ctx, points, query, n_gaussians, sigma, full_fv, k, mlp_h, impl, *weights):
+        lib = _lib.load()
+        n_clouds, N, _ = points.shape
+        G, l = _fv_grid(n_gaussians, 3)
+        V, Cc = G ** 3, FV_CHANNELS[bool(full_fv)]
+        Ct = _centers_tensor(V, 3, points.device)
+        _, cl, lo, hi = Ct._dpd_tables
+        ws_list = [_check_cuda(w.detach(), "variable") for w in weights]
+        cfg = _lib.HeadConfig(n_clouds, query.shape[1], G, Cc, int(k), int(mlp_h), impl | _lib.HEAD_TRAIN)
+        fv = torch.empty((n_clouds, V, Cc), device=points.device, dtype=torch.float32)
+        out = torch.empty((n_clouds, query.shape[1], 3), device=points.device, dtype=torch.float32)
+        with torch.cuda.device(points.device):
+            cache = _PACKED.setdefault((points.device, cfg.flags), _PackedHead())
+            blob = cache.get(lib, cfg, list(weights), ws_list)
+            ws = cache.workspace(lib, cfg, points.device)
+            rc = lib.dpd_model_forward(ctypes.byref(cfg), _ptr(points), N, float(sigma), _lib.fptr(l), _ptr(query),
+                                       _lib.fptr(cl), _lib.fptr(lo), _lib.fptr(hi), _ptr(blob), _ptr(fv), _ptr(out), None,
+                                       _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "dpd_model_forward")
+        cache.generation = getattr(cache, "generation", 0) + 1
+        ctx.fv, ctx.cfg, ctx.cache, ctx.generation = fv, cfg, cache, cache.generation
+        ctx.shapes = [tuple(w.shape) for w in weights]
+        ctx.inputs_need = False
+        ctx.query_shape = tuple(query.shape)
+        ctx.mark_non_differentiable(fv)
+        return out, fv
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_fv):
+        return _head_backward(ctx, grad_out, n_leading=8)
+
+
+def model_forward_train(points, query, n_gaussians, sigma, full_fv, k, mlp, reuse=None, impl=None):
+    """model_forward with gradients w.r.t. the 8 variables (`points` / `query` are data): -> (fv, out, C)."""
+    points = _check_cuda(points, "points")
+    query = _check_cuda(query, "query")
+    _check_head_options(k, 1, 3, False, 'relu', mlp)
+    G, _ = _fv_grid(n_gaussians, 3)
+    Cc = FV_CHANNELS[bool(full_fv)]
+    weights = _head_variables(Cc * k ** 3, 3, mlp, reuse)
+    flags = HEAD_IMPL if impl is None else impl
+    out, fv = _ModelTrainFunction.apply(points, query, n_gaussians, sigma, full_fv, k, mlp[0], flags, *weights)
+    return fv, out, _centers_tensor(G ** 3, 3, points.device)
 
 
 def head_forward(fv, query, C, weights, k, impl=None, return_idx=False):
