@@ -165,7 +165,7 @@ class IterativePCRNetOurs:
         gs["src"].copy_(source, non_blocking=True)
         gs["tpl"].copy_(template, non_blocking=True)
         gs["graph"].replay()
-        return gs["out"]
+        return tuple(t.clone() for t in gs["out"])     # the graph's output buffers are overwritten by the next replay
 
     def _train_step(self, source, template):
         B = source.shape[0]

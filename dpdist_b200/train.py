@@ -144,7 +144,7 @@ class DPDistTrainer:
         gs["b"].copy_(pcB, non_blocking=True)
         gs["l"].copy_(labels_AB, non_blocking=True)
         gs["graph"].replay()
-        return gs["loss"]
+        return gs["loss"].clone()        # the graph's own output buffer is overwritten by the next replay
 
     def step(self, pcA, pcB, labels_AB, add_noise=0):
         distributed_now = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
