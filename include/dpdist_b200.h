@@ -155,7 +155,11 @@ int dpd_model_forward(const dpd_head_config* cfg, const float* d_points, int n_p
  *   d_gw1 [3+k^3*C, H] (reference row order, offset rows first), d_gw2/3 [H,H], d_gw4 [H,3], d_gb* biases
  * stage = DPD_BWD_ALL, or DPD_BWD_L4, L3, L2, L1 in that order (each writes only its layer's gradients).
  * A NULL d_gw<i> skips that layer's weight / bias gradient (frozen DPDist used as a loss): the chain of
- * activation gradients is still propagated for dpd_head_backward_inputs.                                  */
+ * activation gradients is still propagated for dpd_head_backward_inputs.
+ * With the fp16x3 tensor-core head (the default) every product of the backward pass runs on the tensor cores as well
+ * (dX = dZ.W^T with the ReLU' bit masks the forward left in the workspace, dW = A^T.dZ split over the active rows);
+ * the stages must then be issued in order starting with DPD_BWD_L4 (it resets the per-layer |dZ|max slots).
+ * Deterministic: all reductions run in a fixed order.                                                      */
 int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, const void* d_packed,
                       const float* d_grad_out, int stage, float* d_gw1, float* d_gb1, float* d_gw2,
                       float* d_gb2, float* d_gw3, float* d_gb3, float* d_gw4, float* d_gb4,
