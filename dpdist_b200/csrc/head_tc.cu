@@ -873,12 +873,13 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
                          sc + tc::S_ACC1, sc + tc::S_A2, &ga, st, bits ? (uint4*)(ws + w.rb1) : nullptr))) return rc;
     if ((rc = tc::launch(false, true, ws + w.xh, ws + w.xl, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.yh, ws + w.yl, 1,
                          sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st, bits ? (uint4*)(ws + w.rb2) : nullptr))) return rc;
-    if (fused_out != nullptr && tc::use_2cta() && tc::fuse_l4() && h3_out == nullptr) {
-      // layer 3 with the output layer fused into its epilogue: H3 never reaches HBM.  `ha` (unused by this path)
-      // holds the [rows, 2*H/256] float4 partials.
+    if (fused_out != nullptr && tc::use_2cta() && tc::fuse_l4()) {
+      // layer 3 with the output layer fused into its epilogue.  Inference: H3 never reaches HBM.  Training (h3_out set):
+      // the fp32 activations are stored as well, for the backward pass.  `ha` (not read by this path; the SIMT backward
+      // refills it later) holds the [rows, 2*H/256] float4 partials.
       const int nslots = 2 * (H / tc::BN);
       float* part4 = ha;
-      if ((rc = tc::launch2(false, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, nullptr, nullptr, 0,
+      if ((rc = tc::launch2(false, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, h3_out, nullptr, 0,
                             sc + tc::S_ACC3, nullptr, nullptr, st, w4, part4))) return rc;
       DPD_LAUNCH("head_out_finish", st, tc::head_out_finish_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
           (const float4*)part4, nslots, b4, mask, fused_out, rows));

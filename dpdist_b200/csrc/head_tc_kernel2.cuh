@@ -315,6 +315,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               for (int u2 = 0; u2 < 2; ++u2) {
                 const float* sp = sum + (rh * 2 + cg) * 32 + j * 4 + u2 * 2;
                 const float x0 = fmaxf(fmaf(sp[0], acc_scale, bb.x), 0.f), x1 = fmaxf(fmaf(sp[1], acc_scale, bb.y), 0.f);
+                if (args.out0 != nullptr) {      // training: the fp32 activations are kept for the backward pass as well
+                  const int row = row_base + q * 32 + rh * 16 + (lane >> 2) + 8 * u2;
+                  if (row < args.M) *reinterpret_cast<float2*>((float*)args.out0 + (size_t)row * args.N + col) = make_float2(x0, x1);
+                }
                 float* q3 = pr[rh * 2 + u2];
                 q3[0] = fmaf(x1, wb.y, fmaf(x0, wa.x, q3[0]));
                 q3[1] = fmaf(x1, wc.x, fmaf(x0, wa.y, q3[1]));
