@@ -150,31 +150,12 @@ __global__ void split_f16_active_kernel(const float* __restrict__ x, int rows, i
   }
 }
 
-// out[c][m] = in[m][c] for an fp16 matrix in [rows, H] (row stride H) -> out [H, Mp]; 64x64 tiles through shared memory
-__global__ void transpose_f16_kernel(const __half* __restrict__ in, int rows, int H, int Mp, __half* __restrict__ out,
-                                     const int* __restrict__ extent) {
-  __shared__ __half tile[64][66];
-  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-  if (extent && m0 >= *extent) return;       // rows past the active extent are never read (k_limit of the dW product)
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: 32 x 8
-  for (int r = ty; r < 64; r += 8) {
-    const int m = m0 + r;
-    __half2 v = __floats2half2_rn(0.f, 0.f);
-    if (m < rows) v = *reinterpret_cast<const __half2*>(in + (size_t)m * H + c0 + 2 * tx);
-    tile[r][2 * tx] = __low2half(v); tile[r][2 * tx + 1] = __high2half(v);
-  }
-  __syncthreads();
-  for (int c = ty; c < 64; c += 8)
-    *reinterpret_cast<__half2*>(out + (size_t)(c0 + c) * Mp + m0 + 2 * tx) = __halves2half2(tile[2 * tx][c], tile[2 * tx + 1][c]);
-}
-
-// One pass over the upstream gradient dz [rows, H] (fp32): the scaled fp16 (hi, lo) pair row-major (operand of
-// dX = dZ . W^T) AND transposed [H, Mp] (operand of dW = A^T . dZ); zeros for inactive 128-row blocks.
-__global__ void split_transpose_f16_kernel(const float* __restrict__ dz, int rows, int H, int Mp, const int* __restrict__ active,
-                                           const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
-                                           __half* __restrict__ thi, __half* __restrict__ tlo, const int* __restrict__ extent,
-                                           float* __restrict__ col_partial) {
-  __shared__ __half th[64][66], tl[64][66];
+// One pass over the upstream gradient dz [rows, H] (fp32): the scaled fp16 (hi, lo) pair (operand of both products of
+// the layer: dX = dZ . W^T and, MN-major, dW = A^T . dZ), zeros for inactive 128-row blocks, and the per-64-row-block
+// column sums that make up the bias gradient.
+__global__ void split_colsum_f16_kernel(const float* __restrict__ dz, int rows, int H, const int* __restrict__ active,
+                                        const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                        const int* __restrict__ extent, float* __restrict__ col_partial) {
   __shared__ float csum[8][64];
   const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   if (extent && m0 >= *extent) return;       // past the last active block: neither product reads these rows
@@ -193,16 +174,11 @@ __global__ void split_transpose_f16_kernel(const float* __restrict__ dz, int row
       *reinterpret_cast<__half2*>(hi + (size_t)m * H + c0 + 2 * tx) = __halves2half2(h0, h1);
       *reinterpret_cast<__half2*>(lo + (size_t)m * H + c0 + 2 * tx) = __halves2half2(l0, l1);
     }
-    th[r][2 * tx] = h0; th[r][2 * tx + 1] = h1; tl[r][2 * tx] = l0; tl[r][2 * tx + 1] = l1;
   }
+  if (col_partial == nullptr) return;
   csum[ty][2 * tx] = cs0; csum[ty][2 * tx + 1] = cs1;
   __syncthreads();
-  for (int c = ty; c < 64; c += 8) {
-    const size_t o = (size_t)(c0 + c) * Mp + m0 + 2 * tx;
-    *reinterpret_cast<__half2*>(thi + o) = __halves2half2(th[2 * tx][c], th[2 * tx + 1][c]);
-    *reinterpret_cast<__half2*>(tlo + o) = __halves2half2(tl[2 * tx][c], tl[2 * tx + 1][c]);
-  }
-  if (col_partial != nullptr && threadIdx.x < 64) {
+  if (threadIdx.x < 64) {
     float a = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) a += csum[j][threadIdx.x];
@@ -230,16 +206,16 @@ __global__ void __launch_bounds__(1024) colsum_blocks_final_kernel(const float* 
   }
 }
 
-// Transposed layer-1 operand: pt[kk][m] = element kk of the virtual row m = [patch | offset | 0] (same decode as the
-// forward gather producers), from the scaled fp16 FV tensor and offsets.  Block = 64 rows x one 64-element K-block.
-__global__ void gather_transpose_f16_kernel(const GatherArgs g, int rows, int Mp, __half* __restrict__ pth,
-                                            __half* __restrict__ ptl, const int* __restrict__ extent) {
-  __shared__ __half th[64][66], tl[64][66];     // [k within block][row]
+// Materialised layer-1 operand for the weight-gradient product: pa[m][kk] = element kk of the virtual row
+// m = [patch | offset | 0] (same decode as the forward gather producers), from the scaled fp16 FV tensor and offsets,
+// row-major [rows, Kp1] -- the MN-major A operand of dW1 = A^T . dZ1.  Block = 64 rows x one 64-element K-block.
+__global__ void gather_rows_f16_kernel(const GatherArgs g, int rows, int Kp1, __half* __restrict__ pah,
+                                       __half* __restrict__ pal, const int* __restrict__ extent) {
   __shared__ long long row_base[64];            // element offset of the row's cloud in the FV tensor, -1 past the end
   __shared__ int row_vox[64];                   // i0 | i1 << 8 | i2 << 16
   __shared__ int lut[16];                       // per 4-element chunk of this K-block: tap (a0 | a1<<8 | a2<<16) | part << 24, -1 offsets, -2 zero
   const int m0 = blockIdx.x * 64, kb = blockIdx.y;
-  if (extent && m0 >= *extent) return;
+  if (extent && m0 >= *extent) return;          // rows past the active extent are never read (k_limit of the dW product)
   const int G = g.G, Cc = g.C, kk = g.k, pb = (g.k - 1) >> 1, V = G * G * G, ech = g.E / 4;
   const __half* fv_hi = (const __half*)g.fv_hi; const __half* fv_lo = (const __half*)g.fv_lo;
   const __half* o4_hi = (const __half*)g.off4_hi; const __half* o4_lo = (const __half*)g.off4_lo;
@@ -266,35 +242,26 @@ __global__ void gather_transpose_f16_kernel(const GatherArgs g, int rows, int Mp
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
     const int r = i >> 4, chunk = i & 15;
+    if (m0 + r >= rows) continue;
     const long long base = row_base[r];
     const int code = lut[chunk];
     uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
-    if (base >= 0 && code != -2) {
-      if (code == -1) {
-        vh = *reinterpret_cast<const uint2*>(o4_hi + (size_t)(m0 + r) * 4);
-        vl = *reinterpret_cast<const uint2*>(o4_lo + (size_t)(m0 + r) * 4);
-      } else {
-        const int vox = row_vox[r];
-        const int n0 = (vox & 255) + (code & 255) - pb, n1 = ((vox >> 8) & 255) + ((code >> 8) & 255) - pb;
-        const int n2 = ((vox >> 16) & 255) + ((code >> 16) & 255) - pb;
-        if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
-          const size_t el = (size_t)base + (size_t)((n0 * G + n1) * G + n2) * Cc + (code >> 24);
-          vh = *reinterpret_cast<const uint2*>(fv_hi + el);
-          vl = *reinterpret_cast<const uint2*>(fv_lo + el);
-        }
+    if (code == -1) {
+      vh = *reinterpret_cast<const uint2*>(o4_hi + (size_t)(m0 + r) * 4);
+      vl = *reinterpret_cast<const uint2*>(o4_lo + (size_t)(m0 + r) * 4);
+    } else if (code != -2) {
+      const int vox = row_vox[r];
+      const int n0 = (vox & 255) + (code & 255) - pb, n1 = ((vox >> 8) & 255) + ((code >> 8) & 255) - pb;
+      const int n2 = ((vox >> 16) & 255) + ((code >> 16) & 255) - pb;
+      if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
+        const size_t el = (size_t)base + (size_t)((n0 * G + n1) * G + n2) * Cc + (code >> 24);
+        vh = *reinterpret_cast<const uint2*>(fv_hi + el);
+        vl = *reinterpret_cast<const uint2*>(fv_lo + el);
       }
     }
-    const __half* ph = reinterpret_cast<const __half*>(&vh);
-    const __half* pl = reinterpret_cast<const __half*>(&vl);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { th[chunk * 4 + e][r] = ph[e]; tl[chunk * 4 + e][r] = pl[e]; }
-  }
-  __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int c = ty; c < 64; c += 8) {
-    const size_t o = (size_t)(kb * 64 + c) * Mp + m0 + 2 * tx;
-    *reinterpret_cast<__half2*>(pth + o) = __halves2half2(th[c][2 * tx], th[c][2 * tx + 1]);
-    *reinterpret_cast<__half2*>(ptl + o) = __halves2half2(tl[c][2 * tx], tl[c][2 * tx + 1]);
+    const size_t o = (size_t)(m0 + r) * Kp1 + kb * 64 + chunk * 4;     // 16 lanes x 8 B = one 128-byte row segment
+    *reinterpret_cast<uint2*>(pah + o) = vh;
+    *reinterpret_cast<uint2*>(pal + o) = vl;
   }
 }
 
@@ -481,6 +448,8 @@ struct BwdExtras {
   const int* k_limit = nullptr;
   long long slice_stride = 0;
   unsigned* absmax_bits = nullptr;
+  int mn_major = 0;          // A [K, M] and B [K, N] row-major (K = reduction): D = A^T . B
+  unsigned long long mn_rows = 0;   // valid rows of A and B in that case
   const char* name = nullptr;
 };
 
@@ -492,13 +461,23 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   DPD_REQUIRE(!gather || K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_tmap(&tb_hi, bt_hi, true, N, K, BN / 2))) return rc;
-  if ((rc = make_tmap(&tb_lo, bt_lo, true, N, K, BN / 2))) return rc;
-  if (!gather) {
-    if ((rc = make_tmap(&ta_hi, a_hi, true, M, K, BM))) return rc;
-    if ((rc = make_tmap(&ta_lo, a_lo, true, M, K, BM))) return rc;
+  if (bx && bx->mn_major) {
+    // operands as stored: A [K rows, M columns], B [K rows, N columns]; boxes of 64 columns x 64 reduction rows.
+    // K here is the VALID row count of both arrays (rows beyond it are never read: TMA fills zeros)
+    DPD_REQUIRE(!gather && M % 64 == 0, DPD_E_UNSUPPORTED, "tc gemm2 (MN-major): M %% 64 != 0");
+    if ((rc = make_tmap(&tb_hi, bt_hi, true, bx->mn_rows, N, 64))) return rc;
+    if ((rc = make_tmap(&tb_lo, bt_lo, true, bx->mn_rows, N, 64))) return rc;
+    if ((rc = make_tmap(&ta_hi, a_hi, true, bx->mn_rows, M, 64))) return rc;
+    if ((rc = make_tmap(&ta_lo, a_lo, true, bx->mn_rows, M, 64))) return rc;
   } else {
-    ta_hi = tb_hi; ta_lo = tb_lo;
+    if ((rc = make_tmap(&tb_hi, bt_hi, true, N, K, BN / 2))) return rc;
+    if ((rc = make_tmap(&tb_lo, bt_lo, true, N, K, BN / 2))) return rc;
+    if (!gather) {
+      if ((rc = make_tmap(&ta_hi, a_hi, true, M, K, BM))) return rc;
+      if ((rc = make_tmap(&ta_lo, a_lo, true, M, K, BM))) return rc;
+    } else {
+      ta_hi = tb_hi; ta_lo = tb_lo;
+    }
   }
   KernelArgs ka;
   memset(&ka, 0, sizeof(ka));
@@ -515,7 +494,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   if (bx) {
     DPD_REQUIRE(!gather && !split && part4 == nullptr, DPD_E_UNSUPPORTED, "tc gemm2: backward modes need the dense fp32-output kernel");
     ka.mode = bx->mode; ka.relu_bits_in = bx->relu_bits_in; ka.active = bx->active; ka.k_limit = bx->k_limit;
-    ka.slices = bx->slices; ka.slice_stride = bx->slice_stride; ka.absmax_bits = bx->absmax_bits;
+    ka.slices = bx->slices; ka.slice_stride = bx->slice_stride; ka.absmax_bits = bx->absmax_bits; ka.mn_major = bx->mn_major;
     // K-blocks per slice: a multiple of the promotion segment so that segments never straddle slices
     ka.kb_per_slice = round_up(ceil_div(K / 64, bx->slices > 1 ? bx->slices : 1), 4);
     tiles *= bx->slices > 1 ? bx->slices : 1;
@@ -602,7 +581,7 @@ TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
 }
 constexpr int TC_DW_SLICES = 9;       // dW2 / dW3: 16 tiles x 9 slices = 144 work items on 74 clusters (1.95 waves)
 constexpr int TC_DW1_SLICES = 11;     // dW1: 40 tiles x 11 = 440 (5.95 waves)
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, gth, gtl, hth, htl, pth, ptl, part, cpart, rb1, rb2, bsc, scales, total; };
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, pah, pal, part, cpart, rb1, rb2, bsc, scales, total; };
 TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -611,12 +590,11 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
   w.yh = w.yl = o;
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
-  w.gh = w.gl = w.gth = w.gtl = w.hth = w.htl = w.pth = w.ptl = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
-  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient (row-major and transposed), transposed
-    const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);        // activations / patches, partials
-    w.gh = o; o += act; w.gl = o; o += act; w.gth = o; o += act; w.gtl = o; o += act;
-    w.hth = o; o += act; w.htl = o; o += act;
-    w.pth = o; o += up256(rows * Kp1 * e); w.ptl = o; o += up256(rows * Kp1 * e);
+  w.gh = w.gl = w.pah = w.pal = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
+  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, the materialised layer-1 operand, partials
+    const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);
+    w.gh = o; o += act; w.gl = o; o += act;
+    w.pah = o; o += up256(rows * Kp1 * e); w.pal = o; o += up256(rows * Kp1 * e);
     const size_t p1 = (size_t)TC_DW1_SLICES * Kp1 * c.H * 4, p2 = (size_t)TC_DW_SLICES * c.H * c.H * 4;
     w.part = o; o += up256(p1 > p2 ? p1 : p2);
     w.cpart = o; o += up256((rows / 64 + 1) * (size_t)c.H * 4);      // per-64-row-block column sums of dZ
@@ -691,10 +669,11 @@ bool tc_backward_supported(const dpd_head_config& c, bool f16) { return f16 && t
 // One layer of the backward pass on the tensor cores (fp16x3, 2-CTA kernel), layer = 3, 2 or 1:
 //   gw = A^T . dZ   with A = H2 (layer 3), H1 (layer 2) or the gathered layer-1 operand (layer 1); gb = column sums of dZ
 //   dz_next = (dZ . W^T) * ReLU'(A)                                              (layers 3 and 2 only)
-// dZ (fp32) is measured over its active row blocks, scaled by a power of two and split once into fp16 (hi, lo) pairs,
-// row-major for the dX product and transposed for the dW product.  Both products run through the forward GEMM kernel:
-// dX with B = W as stored (K-major for this product) and the ReLU' gate in the epilogue; dW as A^T[k, m] . dZ^T[n, m]
-// over the row axis, split into slices of the active extent whose fp32 partials are summed in a fixed order.
+// dZ (fp32) is scaled by a power of two (its |.|max was recorded by the kernel that produced it) and split once into an
+// fp16 (hi, lo) pair [rows, H].  Both products run through the forward GEMM kernel: dX with B = W as stored (K-major for
+// this product) and the ReLU' bit-mask gate in the epilogue; dW with MN-major operands, i.e. A and dZ exactly as stored
+// ([rows, features], the row axis being the reduction), split into slices of the active extent whose fp32 partials are
+// summed in a fixed order.  No operand is ever transposed.
 int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, void* tc_ws, size_t ws_rows, int rows,
                       const GatherDesc* g, const float* dz, float* dz_next, const int* active, float* gw, float* gb,
                       cudaStream_t st) {
@@ -705,48 +684,43 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
   const int H = c.H, Kp1 = kp1_of(c, true);
   const int Mp = round_up(rows, 128);
   const int nblk = ceil_div(rows, 128);
-  float* bsc = (float*)(ws + w.bsc);      // [0] |dZ|max bits  [1] s_g  [2] 1/(s_g s_W)  [3] 1/(s_g s_A)  [8] active extent (int)
+  float* bsc = (float*)(ws + w.bsc);      // [0] -  [1] s_g  [2] 1/(s_g s_W)  [3] 1/(s_g s_A)  [8] active extent (int)  [16..19] |dZ|max slots
   int* extent = (int*)(bsc + 8);
   const float* ps = (const float*)(blob + b.scales);
   const float* sc = (const float*)(ws + w.scales);
   const float* act_scale = sc + (layer == 3 ? tc::S_A3 : layer == 2 ? tc::S_A2 : tc::S_A1);
   const float* w_scale = layer == 3 ? ps + tc::P_W3 : layer == 2 ? ps + tc::P_W2 : nullptr;
   __half* gh = (__half*)(ws + w.gh); __half* gl = (__half*)(ws + w.gl);
-  __half* gth = (__half*)(ws + w.gth); __half* gtl = (__half*)(ws + w.gtl);
-  // |dZ|max was left in the layer's slot by the kernel that produced dZ (layer-4 backward or the previous dX product)
   unsigned* slots = (unsigned*)(bsc + 16);
   float* cpart = (float*)(ws + w.cpart);
   DPD_LAUNCH("bwd_scales", st, tc::bwd_scales_kernel<<<1, 1, 0, st>>>(bsc, w_scale, act_scale, slots + layer));
   DPD_LAUNCH("bwd_scales", st, tc::active_extent_kernel<<<1, 32, 0, st>>>(active, nblk, rows, extent));
-  DPD_LAUNCH("bwd_split_transpose", st, tc::split_transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(
-      dz, rows, H, Mp, active, bsc + 1, gh, gl, gth, gtl, extent, gw != nullptr ? cpart : nullptr));
+  DPD_LAUNCH("bwd_split", st, tc::split_colsum_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(
+      dz, rows, H, active, bsc + 1, gh, gl, extent, gw != nullptr ? cpart : nullptr));
   DPD_CUDA_CHECK_LAUNCH("tc_backward_layer prep");
   int rc;
   if (gw != nullptr) {
-    const __half* ath; const __half* atl;
+    const __half* ah; const __half* al;
     int Mo;       // rows of the weight gradient in kernel order
     if (layer == 1) {
       tc::GatherArgs ga;
       ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g->idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g->row0;
       ga.n_query = g->n_query; ga.G = g->G; ga.C = g->C; ga.k = g->k; ga.E = g->E;
-      DPD_LAUNCH("bwd_gather_transpose", st, tc::gather_transpose_f16_kernel<<<dim3(Mp / 64, Kp1 / 64), 256, 0, st>>>(
-          ga, rows, Mp, (__half*)(ws + w.pth), (__half*)(ws + w.ptl), extent));
-      ath = (const __half*)(ws + w.pth); atl = (const __half*)(ws + w.ptl); Mo = Kp1;
+      DPD_LAUNCH("bwd_gather_rows", st, tc::gather_rows_f16_kernel<<<dim3(Mp / 64, Kp1 / 64), 256, 0, st>>>(
+          ga, rows, Kp1, (__half*)(ws + w.pah), (__half*)(ws + w.pal), extent));
+      DPD_CUDA_CHECK_LAUNCH("gather_rows_f16_kernel");
+      ah = (const __half*)(ws + w.pah); al = (const __half*)(ws + w.pal); Mo = Kp1;
     } else {
-      const __half* sh = (const __half*)(ws + (layer == 3 ? w.yh : w.xh));
-      const __half* sl = (const __half*)(ws + (layer == 3 ? w.yl : w.xl));
-      DPD_LAUNCH("bwd_transpose", st, tc::transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(sh, rows, H, Mp, (__half*)(ws + w.hth), extent));
-      DPD_LAUNCH("bwd_transpose", st, tc::transpose_f16_kernel<<<dim3(Mp / 64, H / 64), 256, 0, st>>>(sl, rows, H, Mp, (__half*)(ws + w.htl), extent));
-      ath = (const __half*)(ws + w.hth); atl = (const __half*)(ws + w.htl); Mo = H;
+      ah = (const __half*)(ws + (layer == 3 ? w.yh : w.xh)); al = (const __half*)(ws + (layer == 3 ? w.yl : w.xl)); Mo = H;
     }
-    DPD_CUDA_CHECK_LAUNCH("tc_backward_layer transposes");
     tc::BwdExtras bx;
+    bx.mn_major = 1; bx.mn_rows = (unsigned long long)rows;
     // at most the configured number of slices, at least 8 K-blocks (512 rows) per slice: small batches need few partials
     const int max_slices = layer == 1 ? TC_DW1_SLICES : TC_DW_SLICES;
     const int by_rows = Mp / (64 * 8) > 0 ? Mp / (64 * 8) : 1;
     bx.mode = 2; bx.slices = by_rows < max_slices ? by_rows : max_slices; bx.k_limit = extent; bx.slice_stride = (long long)Mo * H;
     float* part = (float*)(ws + w.part);
-    if ((rc = tc::launch2(false, ath, atl, Mo, Mp, gth, gtl, H, nullptr, part, nullptr, 0, bsc + 3, nullptr, nullptr, st, nullptr,
+    if ((rc = tc::launch2(false, ah, al, Mo, Mp, gh, gl, H, nullptr, part, nullptr, 0, bsc + 3, nullptr, nullptr, st, nullptr,
                           nullptr, &bx))) return rc;
     // gb = column sums of dZ over the active rows: per-block partials came out of the split pass
     DPD_LAUNCH("bwd_colsum", st, tc::colsum_blocks_final_kernel<<<H / 64, 1024, 0, st>>>(cpart, extent, H, gb));

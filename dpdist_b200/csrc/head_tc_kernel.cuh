@@ -53,6 +53,8 @@ struct KernelArgs {
   int kb_per_slice;        // K-blocks per slice
   const int* k_limit;      // optional device scalar: valid K extent in elements (K-blocks beyond it are not visited)
   long long slice_stride;  // elements between the fp32 outputs of consecutive slices
+  int mn_major;            // dense 2-CTA kernel: A and B are [reduction, M] / [reduction, N] row-major arrays (MN-major operands):
+                           // the weight-gradient products A^T . B straight from the activations and gradients as stored
   unsigned* absmax_bits;   // mode 1: atomicMax of the bit pattern of max |output| (non-negative floats order like their bits),
                            // so that the next layer's operand scale needs no extra pass over the gradient
   int last_ks;             // 2-CTA kernel: K-steps (16 elements) of the LAST K-block that hold data; 0 = all four.  The padded

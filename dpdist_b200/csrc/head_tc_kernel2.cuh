@@ -178,11 +178,23 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           mbar_wait(&ctl->empty[s], ph ^ 1);
           const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
-          tma_load_2d_cg2(stage_ptr(s, 2), &tm_b_hi, lbar, kb * KB_ELEMS, brow0);
-          tma_load_2d_cg2(stage_ptr(s, 3), &tm_b_lo, lbar, kb * KB_ELEMS, brow0);
-          if (!GATHER) {
-            tma_load_2d_cg2(stage_ptr(s, 0), &tm_a_hi, lbar, kb * KB_ELEMS, row0);
-            tma_load_2d_cg2(stage_ptr(s, 1), &tm_a_lo, lbar, kb * KB_ELEMS, row0);
+          if (!GATHER && args.mn_major) {
+            // MN-major operands: boxes of [64 M (or N) elements x 64 reduction rows]; this CTA's 128 M rows and its
+            // 128 N columns are two such groups each (8 KB apart in the tile)
+#pragma unroll
+            for (int gI = 0; gI < 2; ++gI) {
+              tma_load_2d_cg2(stage_ptr(s, 2) + gI * 8192, &tm_b_hi, lbar, brow0 + gI * 64, kb * KB_ELEMS);
+              tma_load_2d_cg2(stage_ptr(s, 3) + gI * 8192, &tm_b_lo, lbar, brow0 + gI * 64, kb * KB_ELEMS);
+              tma_load_2d_cg2(stage_ptr(s, 0) + gI * 8192, &tm_a_hi, lbar, row0 + gI * 64, kb * KB_ELEMS);
+              tma_load_2d_cg2(stage_ptr(s, 1) + gI * 8192, &tm_a_lo, lbar, row0 + gI * 64, kb * KB_ELEMS);
+            }
+          } else {
+            tma_load_2d_cg2(stage_ptr(s, 2), &tm_b_hi, lbar, kb * KB_ELEMS, brow0);
+            tma_load_2d_cg2(stage_ptr(s, 3), &tm_b_lo, lbar, kb * KB_ELEMS, brow0);
+            if (!GATHER) {
+              tma_load_2d_cg2(stage_ptr(s, 0), &tm_a_hi, lbar, kb * KB_ELEMS, row0);
+              tma_load_2d_cg2(stage_ptr(s, 1), &tm_a_lo, lbar, kb * KB_ELEMS, row0);
+            }
           }
           if (++s == STAGES2) { s = 0; ph ^= 1; }
         }
@@ -204,18 +216,22 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait_cluster(&ctl->full[s], ph);
             tc_fence_after();
-            const uint64_t ah = make_desc_sw128(smem_u32(stage_ptr(s, 0)));
-            const uint64_t al = make_desc_sw128(smem_u32(stage_ptr(s, 1)));
-            const uint64_t bh = make_desc_sw128(smem_u32(stage_ptr(s, 2)));
-            const uint64_t bl = make_desc_sw128(smem_u32(stage_ptr(s, 3)));
+            const bool mn = !GATHER && args.mn_major;
+            const uint64_t ah = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 0)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 0)));
+            const uint64_t al = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 1)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 1)));
+            const uint64_t bh = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 2)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 2)));
+            const uint64_t bl = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 3)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 3)));
+            // K-major: a K step of 16 elements is 32 bytes along the row; MN-major: 16 reduction rows of 128 bytes
+            const uint64_t kstep = mn ? (uint64_t)(16 * 128 >> 4) : (uint64_t)2;
+            const uint32_t idesc = IDESC_F16_M256 | (mn ? (3u << 15) : 0u);      // a_major, b_major = MN
             const int nks = (kb == args.num_kb - 1 && args.last_ks > 0) ? args.last_ks : 4;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               if (ks >= nks) break;
-              const uint64_t o = (uint64_t)(ks * 2);
-              umma_f16_cg2(d_tmem, al + o, bh + o, IDESC_F16_M256, accumulate);
-              umma_f16_cg2(d_tmem, ah + o, bl + o, IDESC_F16_M256, 1);
-              umma_f16_cg2(d_tmem, ah + o, bh + o, IDESC_F16_M256, 1);
+              const uint64_t o = (uint64_t)ks * kstep;
+              umma_f16_cg2(d_tmem, al + o, bh + o, idesc, accumulate);
+              umma_f16_cg2(d_tmem, ah + o, bl + o, idesc, 1);
+              umma_f16_cg2(d_tmem, ah + o, bh + o, idesc, 1);
               accumulate = 1;
             }
             umma_commit_cg2_mcast(&ctl->empty[s]);

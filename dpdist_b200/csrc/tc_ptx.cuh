@@ -130,6 +130,20 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, SWIZZLE_128B descriptor: the operand tile is stored as rows of the REDUCTION index, each row 128 bytes =
+// 64 consecutive M (or N) elements -- which is what a TMA box [64 elements x rows] of a row-major [reduction, M] array
+// gives.  Canonical layout (cute::UMMA, units of 16 B): ((8,n),(8,k)) : ((1,LBO),(8,SBO)): LBO = distance between
+// 64-element M/N groups, SBO = distance between groups of 8 reduction rows (1024 B when the rows are contiguous).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A/B format [7,10),[10,13): F16=0, TF32=2,
 // A,B K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
