@@ -18,13 +18,18 @@ __global__ void row_active_kernel(const float* __restrict__ g, int M, int* __res
 }
 
 // One warp per row, grid-stride over rows; per-lane accumulators for H3^T dz4 (lane owns columns 4*lane + 128*i).
+// W4 is staged once per CTA in shared memory, transposed to [3][H] so that a lane's four columns are one conflict-free
+// LDS.128 (read straight from global memory the 192 strided scalar loads per row were the whole cost of this kernel).
 __global__ void __launch_bounds__(256) out_backward_kernel(const float* __restrict__ h3, const float* __restrict__ w4,
                                                            const float* __restrict__ b4, const float* __restrict__ mask,
                                                            const float* __restrict__ grad_out, const int* __restrict__ active,
                                                            float* __restrict__ dz3, float* __restrict__ partial4, int M, int H,
                                                            unsigned* __restrict__ absmax_bits) {
-  extern __shared__ float red[];   // [8 warps][H*3 + 3]
+  extern __shared__ __align__(16) float red[];   // [8 warps][H*3 + 3] for the final reduction, then [3][H] W4^T
+  float* w4t = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red + 8 * (H * 3 + 3)) + 15) & ~(uintptr_t)15);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < H * 3; i += blockDim.x) w4t[(i % 3) * H + i / 3] = w4[i];
+  __syncthreads();
   const int nw = gridDim.x * 8;
   constexpr int MAXQ = 8;          // H <= 1024: up to 8 column quads per lane
   float gw[MAXQ][4][3];
@@ -45,13 +50,11 @@ __global__ void __launch_bounds__(256) out_backward_kernel(const float* __restri
       if (i < nq) {
         const int n = i * 128 + lane * 4;
         hv[i] = *reinterpret_cast<const float4*>(hr + n);
-        const float x[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          s0 = fmaf(x[e], __ldg(w4 + (n + e) * 3 + 0), s0);
-          s1 = fmaf(x[e], __ldg(w4 + (n + e) * 3 + 1), s1);
-          s2 = fmaf(x[e], __ldg(w4 + (n + e) * 3 + 2), s2);
-        }
+        const float4 wa = *reinterpret_cast<const float4*>(w4t + n), wb = *reinterpret_cast<const float4*>(w4t + H + n);
+        const float4 wc = *reinterpret_cast<const float4*>(w4t + 2 * H + n);
+        s0 = fmaf(hv[i].x, wa.x, fmaf(hv[i].y, wa.y, fmaf(hv[i].z, wa.z, fmaf(hv[i].w, wa.w, s0))));
+        s1 = fmaf(hv[i].x, wb.x, fmaf(hv[i].y, wb.y, fmaf(hv[i].z, wb.z, fmaf(hv[i].w, wb.w, s1))));
+        s2 = fmaf(hv[i].x, wc.x, fmaf(hv[i].y, wc.y, fmaf(hv[i].z, wc.z, fmaf(hv[i].w, wc.w, s2))));
       }
     }
 #pragma unroll
@@ -72,13 +75,16 @@ __global__ void __launch_bounds__(256) out_backward_kernel(const float* __restri
       if (i < nq) {
         const int n = i * 128 + lane * 4;
         const float x[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
+        const float4 wa = *reinterpret_cast<const float4*>(w4t + n), wb = *reinterpret_cast<const float4*>(w4t + H + n);
+        const float4 wc = *reinterpret_cast<const float4*>(w4t + 2 * H + n);
+        const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w}, w2[4] = {wc.x, wc.y, wc.z, wc.w};
         float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           gw[i][e][0] = fmaf(x[e], dz[0], gw[i][e][0]);
           gw[i][e][1] = fmaf(x[e], dz[1], gw[i][e][1]);
           gw[i][e][2] = fmaf(x[e], dz[2], gw[i][e][2]);
-          const float d = dz[0] * __ldg(w4 + (n + e) * 3 + 0) + dz[1] * __ldg(w4 + (n + e) * 3 + 1) + dz[2] * __ldg(w4 + (n + e) * 3 + 2);
+          const float d = dz[0] * w0[e] + dz[1] * w1[e] + dz[2] * w2[e];
           o[e] = x[e] > 0.f ? d : 0.f;
           amax = fmaxf(amax, fabsf(o[e]));
         }
@@ -331,9 +337,9 @@ int launch_out_backward(const float* h3, const float* w4, const float* b4, const
                         const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st,
                         unsigned* absmax_bits) {
   DPD_REQUIRE(H % 128 == 0 && H <= 1024, DPD_E_UNSUPPORTED, "head backward: H=%d must be a multiple of 128, <= 1024", H);
-  const size_t smem = (size_t)8 * (H * 3 + 3) * sizeof(float);
+  const size_t smem = (size_t)8 * (H * 3 + 3) * sizeof(float) + (size_t)H * 3 * sizeof(float) + 32;   // + W4^T [3][H]
   static PerDeviceOnce attr_once;
-  if (attr_once.need()) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4)); }
+  if (attr_once.need()) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4 + 1024 * 3 * 4 + 32)); }
   DPD_LAUNCH("bwd_out_l4", st, out_backward_kernel<<<n_cta, 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3, partial4, M, H, absmax_bits));
   DPD_CUDA_CHECK_LAUNCH("out_backward_kernel");
   return 0;
