@@ -206,63 +206,24 @@ __global__ void __launch_bounds__(1024) colsum_blocks_final_kernel(const float* 
   }
 }
 
-// Materialised layer-1 operand for the weight-gradient product: pa[m][kk] = element kk of the virtual row
-// m = [patch | offset | 0] (same decode as the forward gather producers), from the scaled fp16 FV tensor and offsets,
-// row-major [rows, Kp1] -- the MN-major A operand of dW1 = A^T . dZ1.  Block = 64 rows x one 64-element K-block.
-__global__ void gather_rows_f16_kernel(const GatherArgs g, int rows, int Kp1, __half* __restrict__ pah,
-                                       __half* __restrict__ pal, const int* __restrict__ extent) {
-  __shared__ long long row_base[64];            // element offset of the row's cloud in the FV tensor, -1 past the end
-  __shared__ int row_vox[64];                   // i0 | i1 << 8 | i2 << 16
-  __shared__ int lut[16];                       // per 4-element chunk of this K-block: tap (a0 | a1<<8 | a2<<16) | part << 24, -1 offsets, -2 zero
-  const int m0 = blockIdx.x * 64, kb = blockIdx.y;
-  if (extent && m0 >= *extent) return;          // rows past the active extent are never read (k_limit of the dW product)
-  const int G = g.G, Cc = g.C, kk = g.k, pb = (g.k - 1) >> 1, V = G * G * G, ech = g.E / 4;
-  const __half* fv_hi = (const __half*)g.fv_hi; const __half* fv_lo = (const __half*)g.fv_lo;
-  const __half* o4_hi = (const __half*)g.off4_hi; const __half* o4_lo = (const __half*)g.off4_lo;
-  if (threadIdx.x < 64) {          // the decode that does not depend on the K-block ...
-    const int m = m0 + threadIdx.x;
-    long long base = -1; int vox = 0;
-    if (m < rows) {
-      const int v = __ldg(g.idx + m);
-      base = ((g.row0 + m) / g.n_query) * (long long)V * Cc;
-      vox = (v / (G * G)) | (((v / G) % G) << 8) | ((v % G) << 16);
-    }
-    row_base[threadIdx.x] = base; row_vox[threadIdx.x] = vox;
-  } else if (threadIdx.x < 80) {   // ... and the one that does not depend on the row
-    const int q = kb * 16 + (threadIdx.x - 64);
-    int code = -2;
-    if (q < ech) {
-      const int e = q * 4, j = e / Cc, part = e - j * Cc;
-      code = (j / (kk * kk)) | (((j / kk) % kk) << 8) | ((j % kk) << 16) | (part << 24);
-    } else if (q == ech) {
-      code = -1;
-    }
-    lut[threadIdx.x - 64] = code;
+// Per query row: {element offset of its own voxel record in the FV tensor (or -1 past the end), validity bits of the k
+// taps per axis (bit a: i0 + a - pb in range, bit 8 + a: i1, bit 16 + a: i2)} -- what the forward gather producers
+// compute per tile, prepared once per backward pass for the gather producers of the dW1 product.
+__global__ void rowinfo_kernel(const int32_t* __restrict__ idx, long long row0, int n_query, int G, int Cc, int k, int rows,
+                               int2* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const int V = G * G * G, pb = (k - 1) >> 1;
+  const long long cloud = (row0 + m) / n_query;
+  const int v = idx[m];
+  const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
+  uint32_t mk = 0;
+  for (int a = 0; a < k; ++a) {
+    mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
+    mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
+    mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
-    const int r = i >> 4, chunk = i & 15;
-    if (m0 + r >= rows) continue;
-    const long long base = row_base[r];
-    const int code = lut[chunk];
-    uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
-    if (code == -1) {
-      vh = *reinterpret_cast<const uint2*>(o4_hi + (size_t)(m0 + r) * 4);
-      vl = *reinterpret_cast<const uint2*>(o4_lo + (size_t)(m0 + r) * 4);
-    } else if (code != -2) {
-      const int vox = row_vox[r];
-      const int n0 = (vox & 255) + (code & 255) - pb, n1 = ((vox >> 8) & 255) + ((code >> 8) & 255) - pb;
-      const int n2 = ((vox >> 16) & 255) + ((code >> 16) & 255) - pb;
-      if ((unsigned)n0 < (unsigned)G && (unsigned)n1 < (unsigned)G && (unsigned)n2 < (unsigned)G) {
-        const size_t el = (size_t)base + (size_t)((n0 * G + n1) * G + n2) * Cc + (code >> 24);
-        vh = *reinterpret_cast<const uint2*>(fv_hi + el);
-        vl = *reinterpret_cast<const uint2*>(fv_lo + el);
-      }
-    }
-    const size_t o = (size_t)(m0 + r) * Kp1 + kb * 64 + chunk * 4;     // 16 lanes x 8 B = one 128-byte row segment
-    *reinterpret_cast<uint2*>(pah + o) = vh;
-    *reinterpret_cast<uint2*>(pal + o) = vl;
-  }
+  out[m] = make_int2((int)(cloud * V * Cc) + v * Cc, (int)mk);
 }
 
 // rows covered by the active blocks: (index of the last active 128-row block + 1) * 128, clipped to `rows`
@@ -419,7 +380,7 @@ static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const C
   if (attr_once.need()) {
     DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
   }
-  DPD_LAUNCH(GATHER ? "tc_gemm2_gather_l1_f16" : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
+  DPD_LAUNCH(GATHER ? (ka.mn_major ? "tc_gemm2_bwd_dw1_gather_f16" : "tc_gemm2_gather_l1_f16") : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
              tc_gemm2_kernel<GATHER><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
   DPD_CUDA_CHECK_LAUNCH("tc_gemm2_kernel");
   return 0;
@@ -448,6 +409,8 @@ struct BwdExtras {
   const int* k_limit = nullptr;
   long long slice_stride = 0;
   unsigned* absmax_bits = nullptr;
+  const int2* rowinfo = nullptr;    // gather + mn_major (dW1): per-row gather info, see rowinfo_kernel
+  int lut_chunks = 0;
   int mn_major = 0;          // A [K, M] and B [K, N] row-major (K = reduction): D = A^T . B
   unsigned long long mn_rows = 0;   // valid rows of A and B in that case
   const char* name = nullptr;
@@ -458,17 +421,22 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
                    const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr,
                    const BwdExtras* bx = nullptr, uint4* relu_bits_out = nullptr) {
   DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
-  DPD_REQUIRE(!gather || K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: K=%d too large", K);
+  DPD_REQUIRE(!gather || (bx && bx->mn_major ? bx->lut_chunks : K / 4) <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: operand row too long");
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if (bx && bx->mn_major) {
     // operands as stored: A [K rows, M columns], B [K rows, N columns]; boxes of 64 columns x 64 reduction rows.
-    // K here is the VALID row count of both arrays (rows beyond it are never read: TMA fills zeros)
-    DPD_REQUIRE(!gather && M % 64 == 0, DPD_E_UNSUPPORTED, "tc gemm2 (MN-major): M %% 64 != 0");
+    // K here is the VALID row count of both arrays (rows beyond it are never read: TMA fills zeros).  With `gather`
+    // the A operand is assembled by the gather warps instead (dW1).
+    DPD_REQUIRE(M % 64 == 0, DPD_E_UNSUPPORTED, "tc gemm2 (MN-major): M %% 64 != 0");
     if ((rc = make_tmap(&tb_hi, bt_hi, true, bx->mn_rows, N, 64))) return rc;
     if ((rc = make_tmap(&tb_lo, bt_lo, true, bx->mn_rows, N, 64))) return rc;
-    if ((rc = make_tmap(&ta_hi, a_hi, true, bx->mn_rows, M, 64))) return rc;
-    if ((rc = make_tmap(&ta_lo, a_lo, true, bx->mn_rows, M, 64))) return rc;
+    if (!gather) {
+      if ((rc = make_tmap(&ta_hi, a_hi, true, bx->mn_rows, M, 64))) return rc;
+      if ((rc = make_tmap(&ta_lo, a_lo, true, bx->mn_rows, M, 64))) return rc;
+    } else {
+      ta_hi = tb_hi; ta_lo = tb_lo;
+    }
   } else {
     if ((rc = make_tmap(&tb_hi, bt_hi, true, N, K, BN / 2))) return rc;
     if ((rc = make_tmap(&tb_lo, bt_lo, true, N, K, BN / 2))) return rc;
@@ -483,16 +451,19 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   memset(&ka, 0, sizeof(ka));
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
   ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4; ka.relu_bits_out = relu_bits_out;
+  const bool gather_mn = gather && bx && bx->mn_major;
   if (g) {
     ka.g = *g;
-    if (gather) {   // valid operand length E + 3; everything from there to K is zero padding
+    if (gather && !gather_mn) {   // valid operand length E + 3; everything from there to K is zero padding
       const int tail = g->E + 3 - (K - 64);
       ka.last_ks = tail >= 64 ? 0 : (tail <= 0 ? 1 : ceil_div(tail, 16));
     }
   }
   int tiles = ceil_div(M, 2 * BM) * (N / BN);
   if (bx) {
-    DPD_REQUIRE(!gather && !split && part4 == nullptr, DPD_E_UNSUPPORTED, "tc gemm2: backward modes need the dense fp32-output kernel");
+    DPD_REQUIRE((!gather || gather_mn) && !split && part4 == nullptr, DPD_E_UNSUPPORTED,
+                "tc gemm2: backward modes need the fp32-output kernel (gather only with MN-major operands)");
+    ka.rowinfo = bx->rowinfo; ka.lut_chunks = bx->lut_chunks; ka.g_rows = (int)bx->mn_rows;
     ka.mode = bx->mode; ka.relu_bits_in = bx->relu_bits_in; ka.active = bx->active; ka.k_limit = bx->k_limit;
     ka.slices = bx->slices; ka.slice_stride = bx->slice_stride; ka.absmax_bits = bx->absmax_bits; ka.mn_major = bx->mn_major;
     // K-blocks per slice: a multiple of the promotion segment so that segments never straddle slices
@@ -500,7 +471,8 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
     tiles *= bx->slices > 1 ? bx->slices : 1;
   }
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + (gather ? 2 * (size_t)(K / 4) * sizeof(uint32_t) : 0);
+  const size_t lut_entries = gather ? (gather_mn ? (size_t)bx->lut_chunks : (size_t)(K / 4)) : 0;
+  const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + 2 * lut_entries * sizeof(uint32_t);
   return gather ? launch2_t<true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st)
                 : launch2_t<false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st);
 }
@@ -581,7 +553,7 @@ TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
 }
 constexpr int TC_DW_SLICES = 9;       // dW2 / dW3: 16 tiles x 9 slices = 144 work items on 74 clusters (1.95 waves)
 constexpr int TC_DW1_SLICES = 11;     // dW1: 40 tiles x 11 = 440 (5.95 waves)
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, pah, pal, part, cpart, rb1, rb2, bsc, scales, total; };
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, rinfo, part, cpart, rb1, rb2, bsc, scales, total; };
 TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -590,11 +562,11 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
   w.yh = w.yl = o;
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
-  w.gh = w.gl = w.pah = w.pal = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
-  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, the materialised layer-1 operand, partials
+  w.gh = w.gl = w.rinfo = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
+  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, per-row gather info, partials
     const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);
     w.gh = o; o += act; w.gl = o; o += act;
-    w.pah = o; o += up256(rows * Kp1 * e); w.pal = o; o += up256(rows * Kp1 * e);
+    w.rinfo = o; o += up256(rows * 8);
     const size_t p1 = (size_t)TC_DW1_SLICES * Kp1 * c.H * 4, p2 = (size_t)TC_DW_SLICES * c.H * c.H * 4;
     w.part = o; o += up256(p1 > p2 ? p1 : p2);
     w.cpart = o; o += up256((rows / 64 + 1) * (size_t)c.H * 4);      // per-64-row-block column sums of dZ
@@ -706,10 +678,22 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
       tc::GatherArgs ga;
       ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g->idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g->row0;
       ga.n_query = g->n_query; ga.G = g->G; ga.C = g->C; ga.k = g->k; ga.E = g->E;
-      DPD_LAUNCH("bwd_gather_rows", st, tc::gather_rows_f16_kernel<<<dim3(Mp / 64, Kp1 / 64), 256, 0, st>>>(
-          ga, rows, Kp1, (__half*)(ws + w.pah), (__half*)(ws + w.pal), extent));
-      DPD_CUDA_CHECK_LAUNCH("gather_rows_f16_kernel");
-      ah = (const __half*)(ws + w.pah); al = (const __half*)(ws + w.pal); Mo = Kp1;
+      // the gather warps of the GEMM kernel assemble the MN-major A tiles on the fly: nothing is materialised
+      int2* rinfo = (int2*)(ws + w.rinfo);
+      DPD_LAUNCH("bwd_rowinfo", st, tc::rowinfo_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
+          g->idx, g->row0, g->n_query, g->G, g->C, g->k, rows, rinfo));
+      DPD_CUDA_CHECK_LAUNCH("rowinfo_kernel");
+      tc::BwdExtras bx;
+      bx.mn_major = 1; bx.mn_rows = (unsigned long long)rows; bx.rowinfo = rinfo; bx.lut_chunks = Kp1 / 4;
+      const int by_rows1 = Mp / (64 * 8) > 0 ? Mp / (64 * 8) : 1;
+      bx.mode = 2; bx.slices = by_rows1 < TC_DW1_SLICES ? by_rows1 : TC_DW1_SLICES; bx.k_limit = extent;
+      bx.slice_stride = (long long)Kp1 * H;
+      float* part1 = (float*)(ws + w.part);
+      if ((rc = tc::launch2(true, nullptr, nullptr, Kp1, Mp, gh, gl, H, nullptr, part1, nullptr, 0, bsc + 3, nullptr, &ga, st,
+                            nullptr, nullptr, &bx))) return rc;
+      DPD_LAUNCH("bwd_colsum", st, tc::colsum_blocks_final_kernel<<<H / 64, 1024, 0, st>>>(cpart, extent, H, gb));
+      DPD_CUDA_CHECK_LAUNCH("tc_backward_layer colsum");
+      return launch_reduce_partials(part1, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices);
     } else {
       ah = (const __half*)(ws + (layer == 3 ? w.yh : w.xh)); al = (const __half*)(ws + (layer == 3 ? w.yl : w.xl)); Mo = H;
     }

@@ -53,7 +53,12 @@ struct KernelArgs {
   int kb_per_slice;        // K-blocks per slice
   const int* k_limit;      // optional device scalar: valid K extent in elements (K-blocks beyond it are not visited)
   long long slice_stride;  // elements between the fp32 outputs of consecutive slices
-  int mn_major;            // dense 2-CTA kernel: A and B are [reduction, M] / [reduction, N] row-major arrays (MN-major operands):
+  // gather kernel in MN-major mode (dW1 = patches^T . dZ1): per-row {FV element offset or -1, tap validity mask} prepared
+  // by rowinfo_kernel, number of 4-element chunks of the operand row, number of valid rows
+  const int2* rowinfo;
+  int lut_chunks;
+  int g_rows;
+  int mn_major;            // 2-CTA kernel: A and B are [reduction, M] / [reduction, N] row-major arrays (MN-major operands):
                            // the weight-gradient products A^T . B straight from the activations and gradients as stored
   unsigned* absmax_bits;   // mode 1: atomicMax of the bit pattern of max |output| (non-negative floats order like their bits),
                            // so that the next layer's operand scale needs no extra pass over the gradient

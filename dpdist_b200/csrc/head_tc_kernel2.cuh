@@ -138,7 +138,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
   if (warp == 2) tmem_alloc_cg2(&ctl->tmem_base, TMEM_COLS);
   if (GATHER) {
-    const int nchunks = args.num_kb * CHUNKS;
+    const int nchunks = args.mn_major ? args.lut_chunks : args.num_kb * CHUNKS;
     const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4, Gg = args.g.G, pbb = (args.g.k - 1) >> 1;
     int32_t* lutd = (int32_t*)(lut + nchunks);
     for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
@@ -178,15 +178,17 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           mbar_wait(&ctl->empty[s], ph ^ 1);
           const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
-          if (!GATHER && args.mn_major) {
+          if (args.mn_major) {
             // MN-major operands: boxes of [64 M (or N) elements x 64 reduction rows]; this CTA's 128 M rows and its
-            // 128 N columns are two such groups each (8 KB apart in the tile)
+            // 128 N columns are two such groups each (8 KB apart in the tile).  GATHER: A comes from the gather warps.
 #pragma unroll
             for (int gI = 0; gI < 2; ++gI) {
               tma_load_2d_cg2(stage_ptr(s, 2) + gI * 8192, &tm_b_hi, lbar, brow0 + gI * 64, kb * KB_ELEMS);
               tma_load_2d_cg2(stage_ptr(s, 3) + gI * 8192, &tm_b_lo, lbar, brow0 + gI * 64, kb * KB_ELEMS);
-              tma_load_2d_cg2(stage_ptr(s, 0) + gI * 8192, &tm_a_hi, lbar, row0 + gI * 64, kb * KB_ELEMS);
-              tma_load_2d_cg2(stage_ptr(s, 1) + gI * 8192, &tm_a_lo, lbar, row0 + gI * 64, kb * KB_ELEMS);
+              if (!GATHER) {
+                tma_load_2d_cg2(stage_ptr(s, 0) + gI * 8192, &tm_a_hi, lbar, row0 + gI * 64, kb * KB_ELEMS);
+                tma_load_2d_cg2(stage_ptr(s, 1) + gI * 8192, &tm_a_lo, lbar, row0 + gI * 64, kb * KB_ELEMS);
+              }
             }
           } else {
             tma_load_2d_cg2(stage_ptr(s, 2), &tm_b_hi, lbar, kb * KB_ELEMS, brow0);
@@ -216,7 +218,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait_cluster(&ctl->full[s], ph);
             tc_fence_after();
-            const bool mn = !GATHER && args.mn_major;
+            const bool mn = args.mn_major != 0;
             const uint64_t ah = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 0)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 0)));
             const uint64_t al = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 1)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 1)));
             const uint64_t bh = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 2)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 2)));
@@ -478,8 +480,60 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int V = G * G * G;
     const uint8_t* fv_hi = (const uint8_t*)g.fv_hi; const uint8_t* fv_lo = (const uint8_t*)g.fv_lo;
     const uint8_t* o4_hi = (const uint8_t*)g.off4_hi; const uint8_t* o4_lo = (const uint8_t*)g.off4_lo;
-    const uint32_t lut_s = smem_u32(lut), lutd_s = lut_s + (uint32_t)(args.num_kb * CHUNKS) * 4u;
+    const uint32_t lut_s = smem_u32(lut), lutd_s = lut_s + (uint32_t)((args.mn_major ? args.lut_chunks : args.num_kb * CHUNKS)) * 4u;
     int s = 0; uint32_t ph = 0;
+    if (args.mn_major) {
+      // dW1 = patches^T . dZ1: the tile's M range is a range of operand elements, fixed per tile, so this thread's
+      // 4-element chunk (tap, channel quad) is decoded once per tile; what changes per stage are the 64 reduction rows,
+      // whose {FV offset, tap validity} come precomputed (rowinfo).  Tile layout = MN-major: group (64 elements) major,
+      // then reduction row (128 bytes), 16-byte units XOR-swizzled with the row.
+      const int chunk32 = p & 31, sub = p >> 5;                 // 32 chunk columns (2 groups x 16) x 4 row lanes
+      const uint32_t c16 = (uint32_t)((chunk32 & 15) >> 1);
+      const uint32_t dst0 = (uint32_t)((chunk32 >> 4) * 8192 + (chunk32 & 1) * 8);
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int t = w % num_tiles, sl = w / num_tiles;
+        const int mt = t / num_n_tiles;
+        const int q = (mt * 2 * BM + (int)rank * BM) / 4 + chunk32;
+        uint32_t code = LUT_ZERO; int32_t delta = 0;
+        if (q < args.lut_chunks) {
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)q * 4u));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)q * 4u));
+        }
+        const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
+        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          int2 ri[16];
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int m = kb * KB_ELEMS + it * 4 + sub;
+            ri[it] = (m < args.g_rows) ? __ldg(args.rowinfo + m) : make_int2(-1, 0);
+          }
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int r = it * 4 + sub;
+            const uint32_t dst = dst0 + (uint32_t)(r * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            if (code < LUT_OFFS) {
+              const uint32_t mk = (uint32_t)ri[it].y;
+              const uint32_t ok = (ri[it].x >= 0 ? 1u : 0u) & (mk >> s0) & (mk >> s1) & (mk >> s2) & 1u;
+              const size_t el = ok ? (size_t)(ri[it].x + delta) : 0;
+              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+              cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
+              cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
+            } else {
+              const bool ok = (code == LUT_OFFS) && ri[it].x >= 0;
+              const size_t m = ok ? (size_t)(kb * KB_ELEMS + r) : 0;
+              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+              cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
+              cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
+            }
+          }
+          cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
+    } else
     for (int w = cluster_id; w < num_items; w += num_clusters) {
       const int t = w % num_tiles;
       const int mt = t / num_n_tiles;
