@@ -12,7 +12,6 @@ namespace {
 
 constexpr size_t ALIGN = 256;
 constexpr int MAX_CHUNK_ROWS = 1 << 18;
-constexpr int OUT_BWD_CTAS = 296;
 
 struct HeadLayout {
   int impl;      // DPD_HEAD_SIMT or DPD_HEAD_TC (resolved)
@@ -115,7 +114,7 @@ WsLayout make_ws(const dpd_head_config& c, const HeadLayout& L, size_t rows) {
     W.active = o; o += up((rows / 128 + 1) * 4);
     W.part = o; o += up((size_t)BWD_SLICES * L.Kp1 * H * 4);
     W.part_bias = o; o += up((size_t)BWD_SLICES * H * 4);
-    W.part4 = o; o += up((size_t)OUT_BWD_CTAS * (H * 3 + 3) * 4);
+    W.part4 = o; o += up((rows / 64 + 1) * (H * 3 + 3) * 4);       // one record per 64-row block
     W.dx1 = o;
     if (L.input_grad) {
       const size_t ld = is_tc(L.impl) && is_f16(L.impl) && tc_kp1(c) > L.Kp1 ? (size_t)tc_kp1(c) : (size_t)L.Kp1;   // tensor-core dX1: ld 2560
@@ -367,9 +366,9 @@ extern "C" int dpd_head_backward(const dpd_head_config* cfg, const float* d_fv, 
     if ((rc = launch_row_active(d_grad_out, rows, active, st))) return rc;
     unsigned* amax3 = nullptr;
     if (tc_bwd && (rc = tc_backward_begin(*cfg, ws + W.tc, chunk, &amax3, st))) return rc;
-    if ((rc = launch_out_backward(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
-                                  d_grad_out, active, g0, part4, OUT_BWD_CTAS, rows, H, st, amax3))) return rc;
-    if (d_gw4 && (rc = launch_reduce_out_partials(part4, OUT_BWD_CTAS, H, d_gw4, d_gb4, st))) return rc;
+    if ((rc = launch_out_backward_blocks(hc, (const float*)(pk + L.w4), (const float*)(pk + L.b4), (const float*)(ws + W.mask),
+                                         d_grad_out, active, g0, part4, rows, H, st, amax3))) return rc;
+    if (d_gw4 && (rc = launch_reduce_out_blocks(part4, active, rows, H, d_gw4, d_gb4, st))) return rc;
   }
   TnParams tp;
   tp.M = rows; tp.N = H; tp.active = active; tp.partial = part; tp.partial_bias = part_bias; tp.lda = H;

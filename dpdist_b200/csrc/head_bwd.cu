@@ -17,44 +17,38 @@ __global__ void row_active_kernel(const float* __restrict__ g, int M, int* __res
   if (threadIdx.x == 0) active[b] = any;
 }
 
-// One warp per row, grid-stride over rows; per-lane accumulators for H3^T dz4 (lane owns columns 4*lane + 128*i).
-// W4 is staged once per CTA in shared memory, transposed to [3][H] so that a lane's four columns are one conflict-free
-// LDS.128 (read straight from global memory the 192 strided scalar loads per row were the whole cost of this kernel).
-__global__ void __launch_bounds__(256) out_backward_kernel(const float* __restrict__ h3, const float* __restrict__ w4,
-                                                           const float* __restrict__ b4, const float* __restrict__ mask,
-                                                           const float* __restrict__ grad_out, const int* __restrict__ active,
-                                                           float* __restrict__ dz3, float* __restrict__ partial4, int M, int H,
-                                                           unsigned* __restrict__ absmax_bits) {
-  extern __shared__ __align__(16) float red[];   // [8 warps][H*3 + 3] for the final reduction, then [3][H] W4^T
-  float* w4t = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(red + 8 * (H * 3 + 3)) + 15) & ~(uintptr_t)15);
+// Two-phase block formulation of the layer-4 backward (H <= 1024, H % 4 == 0): one 256-thread CTA per 64 rows.
+//   phase 1  warp-per-row dot products z = H3[r,:] . W4 + b4 -> dz4[r][3] (relu6' and the in-cube mask applied) in smem
+//   phase 2  thread-per-4-columns over the CTA's 64 rows (H3 re-read from L1 / L2): dZ3[r, c] = (dz4[r] . W4[c]) * (H3 > 0),
+//            weight-gradient partials H3[:, c]^T dz4 in 12 registers, |dZ3|max
+// Partials: one (3H + 3) record per CTA (weights, then the 3 bias sums), reduced in block order afterwards.
+__global__ void __launch_bounds__(256) out_backward_block_kernel(const float* __restrict__ h3, const float* __restrict__ w4,
+                                                                 const float* __restrict__ b4, const float* __restrict__ mask,
+                                                                 const float* __restrict__ grad_out, const int* __restrict__ active,
+                                                                 float* __restrict__ dz3, float* __restrict__ partial4, int M, int H,
+                                                                 unsigned* __restrict__ absmax_bits) {
+  extern __shared__ __align__(16) float sm[];    // W4^T [3][H] | dz4 [64][4]
+  float* w4t = sm;
+  float* dz4 = sm + 3 * H;
+  const int blk = blockIdx.x;                    // 64-row block; two of them per `active` flag
+  if (!active[blk >> 1]) return;
+  const int r0 = blk * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < H * 3; i += blockDim.x) w4t[(i % 3) * H + i / 3] = w4[i];
   __syncthreads();
-  const int nw = gridDim.x * 8;
-  constexpr int MAXQ = 8;          // H <= 1024: up to 8 column quads per lane
-  float gw[MAXQ][4][3];
-  float gb[3] = {0.f, 0.f, 0.f};
-  float amax = 0.f;          // max |dZ3| written by this thread (feeds the tensor-core backward's operand scale)
-#pragma unroll
-  for (int i = 0; i < MAXQ; ++i)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) gw[i][e][0] = gw[i][e][1] = gw[i][e][2] = 0.f;
-  const int nq = H / 128;
-  for (int row = blockIdx.x * 8 + warp; row < M; row += nw) {
-    if (!active[row >> 7]) continue;
-    const float* hr = h3 + (size_t)row * H;
-    float4 hv[MAXQ];
+  // ---- phase 1
+  for (int rr = warp; rr < 64; rr += 8) {
+    const int row = r0 + rr;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXQ; ++i) {
-      if (i < nq) {
-        const int n = i * 128 + lane * 4;
-        hv[i] = *reinterpret_cast<const float4*>(hr + n);
+    if (row < M) {
+      const float* hr = h3 + (size_t)row * H;
+      for (int n = lane * 4; n < H; n += 128) {
+        const float4 x = *reinterpret_cast<const float4*>(hr + n);
         const float4 wa = *reinterpret_cast<const float4*>(w4t + n), wb = *reinterpret_cast<const float4*>(w4t + H + n);
         const float4 wc = *reinterpret_cast<const float4*>(w4t + 2 * H + n);
-        s0 = fmaf(hv[i].x, wa.x, fmaf(hv[i].y, wa.y, fmaf(hv[i].z, wa.z, fmaf(hv[i].w, wa.w, s0))));
-        s1 = fmaf(hv[i].x, wb.x, fmaf(hv[i].y, wb.y, fmaf(hv[i].z, wb.z, fmaf(hv[i].w, wb.w, s1))));
-        s2 = fmaf(hv[i].x, wc.x, fmaf(hv[i].y, wc.y, fmaf(hv[i].z, wc.z, fmaf(hv[i].w, wc.w, s2))));
+        s0 = fmaf(x.x, wa.x, fmaf(x.y, wa.y, fmaf(x.z, wa.z, fmaf(x.w, wa.w, s0))));
+        s1 = fmaf(x.x, wb.x, fmaf(x.y, wb.y, fmaf(x.z, wb.z, fmaf(x.w, wb.w, s1))));
+        s2 = fmaf(x.x, wc.x, fmaf(x.y, wc.y, fmaf(x.z, wc.z, fmaf(x.w, wc.w, s2))));
       }
     }
 #pragma unroll
@@ -63,68 +57,80 @@ __global__ void __launch_bounds__(256) out_backward_kernel(const float* __restri
       s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    const float z[3] = {s0 + b4[0], s1 + b4[1], s2 + b4[2]};
-    const float mk = mask[row];
-    float dz[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)   // d/dz [relu6(z)/3 * mask]; TF-semantics relu6 grad = 1 on 0 < z < 6
-      dz[j] = (z[j] > 0.f && z[j] < 6.f) ? grad_out[(size_t)row * 3 + j] * mk * (1.0f / 3.0f) : 0.f;
-    gb[0] += dz[0]; gb[1] += dz[1]; gb[2] += dz[2];
-#pragma unroll
-    for (int i = 0; i < MAXQ; ++i) {
-      if (i < nq) {
-        const int n = i * 128 + lane * 4;
-        const float x[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
-        const float4 wa = *reinterpret_cast<const float4*>(w4t + n), wb = *reinterpret_cast<const float4*>(w4t + H + n);
-        const float4 wc = *reinterpret_cast<const float4*>(w4t + 2 * H + n);
-        const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w}, w2[4] = {wc.x, wc.y, wc.z, wc.w};
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          gw[i][e][0] = fmaf(x[e], dz[0], gw[i][e][0]);
-          gw[i][e][1] = fmaf(x[e], dz[1], gw[i][e][1]);
-          gw[i][e][2] = fmaf(x[e], dz[2], gw[i][e][2]);
-          const float d = dz[0] * w0[e] + dz[1] * w1[e] + dz[2] * w2[e];
-          o[e] = x[e] > 0.f ? d : 0.f;
-          amax = fmaxf(amax, fabsf(o[e]));
-        }
-        *reinterpret_cast<float4*>(dz3 + (size_t)row * H + n) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lane < 3) {
+      float d = 0.f;
+      if (row < M) {
+        const float z = (lane == 0 ? s0 : lane == 1 ? s1 : s2) + b4[lane];
+        // d/dz [relu6(z)/3 * mask]; TF-semantics relu6 grad = 1 on 0 < z < 6
+        d = (z > 0.f && z < 6.f) ? grad_out[(size_t)row * 3 + lane] * mask[row] * (1.0f / 3.0f) : 0.f;
       }
+      dz4[rr * 4 + lane] = d;
     }
+  }
+  __syncthreads();
+  // ---- phase 2
+  const int n = threadIdx.x * 4;
+  float gw[4][3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) gw[e][0] = gw[e][1] = gw[e][2] = 0.f;
+  float amax = 0.f;
+  if (n < H) {
+    const float4 wa = *reinterpret_cast<const float4*>(w4t + n), wb = *reinterpret_cast<const float4*>(w4t + H + n);
+    const float4 wc = *reinterpret_cast<const float4*>(w4t + 2 * H + n);
+    const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w}, w2[4] = {wc.x, wc.y, wc.z, wc.w};
+    const int nr = min(64, M - r0);
+    for (int rr = 0; rr < nr; ++rr) {
+      const float d0 = dz4[rr * 4 + 0], d1 = dz4[rr * 4 + 1], d2 = dz4[rr * 4 + 2];
+      const float4 xv = *reinterpret_cast<const float4*>(h3 + (size_t)(r0 + rr) * H + n);
+      const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        gw[e][0] = fmaf(x[e], d0, gw[e][0]);
+        gw[e][1] = fmaf(x[e], d1, gw[e][1]);
+        gw[e][2] = fmaf(x[e], d2, gw[e][2]);
+        const float d = d0 * w0[e] + d1 * w1[e] + d2 * w2[e];
+        o[e] = x[e] > 0.f ? d : 0.f;
+        amax = fmaxf(amax, fabsf(o[e]));
+      }
+      *reinterpret_cast<float4*>(dz3 + (size_t)(r0 + rr) * H + n) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    float* dst = partial4 + (size_t)blk * (H * 3 + 3) + (size_t)n * 3;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dst[e * 3 + 0] = gw[e][0]; dst[e * 3 + 1] = gw[e][1]; dst[e * 3 + 2] = gw[e][2]; }
+  }
+  if (threadIdx.x < 3) {      // bias gradient of this block
+    float a = 0.f;
+    for (int rr = 0; rr < 64; ++rr) a += dz4[rr * 4 + threadIdx.x];
+    partial4[(size_t)blk * (H * 3 + 3) + H * 3 + threadIdx.x] = a;
   }
   if (absmax_bits != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if (lane == 0 && amax > 0.f) atomicMax(absmax_bits, __float_as_uint(amax));
   }
-  // CTA reduction in fixed warp order -> partial4[cta]
-  float* mine = red + warp * (H * 3 + 3);
-#pragma unroll
-  for (int i = 0; i < MAXQ; ++i)
-    if (i < nq)
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) mine[(i * 128 + lane * 4 + e) * 3 + j] = gw[i][e][j];
-  // every lane saw every active row of its warp: gb is identical across lanes
-  if (lane == 0) { mine[H * 3 + 0] = gb[0]; mine[H * 3 + 1] = gb[1]; mine[H * 3 + 2] = gb[2]; }
-  __syncthreads();
-  float* dst = partial4 + (size_t)blockIdx.x * (H * 3 + 3);
-  for (int i = threadIdx.x; i < H * 3 + 3; i += blockDim.x) {
-    float a = 0.f;
-    for (int w = 0; w < 8; ++w) a += red[w * (H * 3 + 3) + i];
-    dst[i] = a;
-  }
 }
 
-__global__ void reduce_out_partials_kernel(const float* __restrict__ partial4, int n_cta, int H, float* __restrict__ gw4,
-                                           float* __restrict__ gb4) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= H * 3 + 3) return;
+// gw4 / gb4 = sum over the active 64-row blocks of their partial records; 16 lanes per element sum blocks j, j+16, ...
+// in order, the lane sums are then added in order (deterministic)
+__global__ void __launch_bounds__(1024) reduce_out_blocks_kernel(const float* __restrict__ partial4, const int* __restrict__ active,
+                                                                 int nblk64, int H, float* __restrict__ gw4, float* __restrict__ gb4) {
+  __shared__ float red[16][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + tx, total = H * 3 + 3;
   float a = 0.f;
-  for (int c = 0; c < n_cta; ++c) a += partial4[(size_t)c * (H * 3 + 3) + i];
-  if (i < H * 3) gw4[i] = a;
-  else gb4[i - H * 3] = a;
+  if (i < total)
+    for (int b = ty; b < nblk64; b += 16)
+      if (active[b >> 1]) a += partial4[(size_t)b * total + i];
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t += red[j][tx];
+    if (i < H * 3) gw4[i] = t;
+    else gb4[i - H * 3] = t;
+  }
 }
 
 // partial[s][k][n] = sum over the 128-row blocks b == s (mod BWD_SLICES) of A[m,k] * B[m,n]
@@ -333,21 +339,21 @@ int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st
   return 0;
 }
 
-int launch_out_backward(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
-                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st,
-                        unsigned* absmax_bits) {
-  DPD_REQUIRE(H % 128 == 0 && H <= 1024, DPD_E_UNSUPPORTED, "head backward: H=%d must be a multiple of 128, <= 1024", H);
-  const size_t smem = (size_t)8 * (H * 3 + 3) * sizeof(float) + (size_t)H * 3 * sizeof(float) + 32;   // + W4^T [3][H]
-  static PerDeviceOnce attr_once;
-  if (attr_once.need()) { DPD_CUDA_CALL(cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1024 * 3 + 3) * 4 + 1024 * 3 * 4 + 32)); }
-  DPD_LAUNCH("bwd_out_l4", st, out_backward_kernel<<<n_cta, 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3, partial4, M, H, absmax_bits));
-  DPD_CUDA_CHECK_LAUNCH("out_backward_kernel");
+int launch_out_backward_blocks(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
+                               const int* active, float* dz3, float* partial4, int M, int H, cudaStream_t st,
+                               unsigned* absmax_bits) {
+  DPD_REQUIRE(H % 4 == 0 && H <= 1024, DPD_E_UNSUPPORTED, "head backward: H=%d must be a multiple of 4, <= 1024", H);
+  const size_t smem = ((size_t)3 * H + 64 * 4) * sizeof(float);
+  DPD_LAUNCH("bwd_out_l4", st, out_backward_block_kernel<<<ceil_div(M, 64), 256, smem, st>>>(h3, w4, b4, mask, grad_out, active, dz3,
+                                                                                             partial4, M, H, absmax_bits));
+  DPD_CUDA_CHECK_LAUNCH("out_backward_block_kernel");
   return 0;
 }
 
-int launch_reduce_out_partials(const float* partial4, int n_cta, int H, float* gw4, float* gb4, cudaStream_t st) {
-  DPD_LAUNCH("bwd_reduce_l4", st, reduce_out_partials_kernel<<<ceil_div(H * 3 + 3, 256), 256, 0, st>>>(partial4, n_cta, H, gw4, gb4));
-  DPD_CUDA_CHECK_LAUNCH("reduce_out_partials_kernel");
+int launch_reduce_out_blocks(const float* partial4, const int* active, int M, int H, float* gw4, float* gb4, cudaStream_t st) {
+  DPD_LAUNCH("bwd_reduce_l4", st, reduce_out_blocks_kernel<<<ceil_div(H * 3 + 3, 64), 1024, 0, st>>>(partial4, active, ceil_div(M, 64), H,
+                                                                                                   gw4, gb4));
+  DPD_CUDA_CHECK_LAUNCH("reduce_out_blocks_kernel");
   return 0;
 }
 

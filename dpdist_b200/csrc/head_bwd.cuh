@@ -12,12 +12,14 @@ constexpr int BWD_SLICES = 8;   // split of the row (reduction) axis of the weig
 // gradient is identically zero (the whole B->A half in DPDist training, :967) are skipped everywhere.
 int launch_row_active(const float* grad_out, int M, int* active, cudaStream_t st);
 
-// dZ3[r,:] = (sum_j dz4[r,j] W4[:,j]) * (H3[r,:] > 0),   dz4 = grad_out * mask * relu6'(z4) / 3
-// partial4[cta][H*3 + 3] accumulates H3^T dz4 and sum_r dz4 per CTA (reduced in fixed order later).
-int launch_out_backward(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
-                        const int* active, float* dz3, float* partial4, int n_cta, int M, int H, cudaStream_t st,
-                        unsigned* absmax_bits = nullptr);
-int launch_reduce_out_partials(const float* partial4, int n_cta, int H, float* gw4, float* gb4, cudaStream_t st);
+// dZ3[r,:] = (sum_j dz4[r,j] W4[:,j]) * (H3[r,:] > 0),   dz4 = grad_out * mask * relu6'(z4) / 3,
+// gw4 = H3^T dz4, gb4 = sum_r dz4.
+// Block formulation (one CTA per 64 rows, two phases): partial4 holds one (3H + 3) record per 64-row
+// block; launch_reduce_out_blocks sums the records of the active blocks in a fixed order.
+int launch_out_backward_blocks(const float* h3, const float* w4, const float* b4, const float* mask, const float* grad_out,
+                               const int* active, float* dz3, float* partial4, int M, int H, cudaStream_t st,
+                               unsigned* absmax_bits = nullptr);
+int launch_reduce_out_blocks(const float* partial4, const int* active, int M, int H, float* gw4, float* gb4, cudaStream_t st);
 
 struct TnParams {
   const float* A;      // dense [M, lda] (ignored when gathering)
