@@ -53,6 +53,34 @@ def test_invalid_arguments_are_rejected_before_any_launch():
     assert b"H=1000" in lib.dpd_last_error()
 
 
+def test_backward_and_data_entry_points_validate_flags_and_pointers():
+    lib = _lib.load()
+    p = ctypes.c_void_p(256)
+    c = np.zeros(8, np.float32)
+    # input gradients need DPD_HEAD_TRAIN | DPD_HEAD_INPUT_GRAD; the latter alone is rejected by every head entry point
+    cfg = _lib.HeadConfig(2, 64, 8, 20, 5, 1024, _lib.HEAD_TRAIN)
+    assert lib.dpd_head_backward_inputs(ctypes.byref(cfg), p, p, p, p, 1 << 20, None) == -1
+    assert b"DPD_HEAD_INPUT_GRAD" in lib.dpd_last_error()
+    bad = _lib.HeadConfig(2, 64, 8, 20, 5, 1024, _lib.HEAD_INPUT_GRAD)
+    assert lib.dpd_head_workspace_bytes(ctypes.byref(bad)) == 0 and b"DPD_HEAD_TRAIN" in lib.dpd_last_error()
+    # backward without the training flag, bad stage
+    inf = _lib.HeadConfig(2, 64, 8, 20, 5, 1024, 0)
+    assert lib.dpd_head_backward(ctypes.byref(inf), p, p, p, 0, *([p] * 8), p, 1 << 20, None) == -1
+    assert lib.dpd_head_backward(ctypes.byref(cfg), p, p, p, 9, *([p] * 8), p, 1 << 20, None) == -1
+    # training keeps every activation: more rows than one chunk is refused, not silently chunked
+    big = _lib.HeadConfig(8192, 64, 8, 20, 5, 1024, _lib.HEAD_TRAIN)
+    assert lib.dpd_head_backward(ctypes.byref(big), p, p, p, 0, *([p] * 8), p, 1 << 20, None) == -3
+    # training workspace: the flag costs memory, the input-gradient flag a little more
+    w0 = lib.dpd_head_workspace_bytes(ctypes.byref(inf))
+    w1 = lib.dpd_head_workspace_bytes(ctypes.byref(cfg))
+    w2 = lib.dpd_head_workspace_bytes(ctypes.byref(_lib.HeadConfig(2, 64, 8, 20, 5, 1024, _lib.HEAD_TRAIN | _lib.HEAD_INPUT_GRAD)))
+    assert 0 < w0 < w1 < w2
+    assert lib.dpd_fv_backward(p, 1, 4, 8, _lib.fptr(c), 0.0, 1, 0, p, p, None) == -1          # sigma
+    assert lib.dpd_adam_step_dev(p, p, p, p, 16, None, 0.9, 0.999, 1e-8, None) == -1
+    want = 1e-4 * (1 - 0.999) ** 0.5 / (1 - 0.9)
+    assert abs(lib.dpd_adam_lr_t(1e-4, 0.9, 0.999, 1) - want) < 1e-4 * want          # float32 arguments
+
+
 def test_head_sizes_are_consistent():
     lib = _lib.load()
     for flags in (_lib.HEAD_AUTO, _lib.HEAD_SIMT):
