@@ -8,6 +8,7 @@
 //
 // fv_generic_kernel: any G <= 16, any N, full or small FV.  One CTA per cloud.
 #include "fv.cuh"
+#include <stdlib.h>
 
 namespace dpd {
 
@@ -153,7 +154,10 @@ __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p
 
 int fv_forward_dispatch(const FvParams& p, cudaStream_t st, bool* split_done) {
   if (split_done) *split_done = false;
-  int r = fv_forward_optimized(p, st);
+  // DPD_FV_IMPL=old selects the previous one-role G = 8 kernel (A/B timing); default is the warp-specialised one
+  const char* impl_env = getenv("DPD_FV_IMPL");
+  const bool use_old = impl_env && !strcmp(impl_env, "old");
+  int r = use_old ? fv_forward_optimized(p, st) : fv_forward_ws(p, st);
   if (r <= 0) {
     if (r == 0 && split_done) *split_done = p.fv_hi != nullptr && !p.flatten;
     return r;

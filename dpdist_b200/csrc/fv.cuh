@@ -37,6 +37,10 @@ inline void fill_fv_params(FvParams& p, const float* points, int n_clouds, int n
 // fv_g8.cu: specialised kernel for G = 8, full FV.  Returns 1 if the configuration is not covered.
 int fv_forward_optimized(const FvParams& p, cudaStream_t stream);
 
+// fv_ws.cu: warp-specialised kernel for G = 8, full FV (builder / accumulator / finaliser roles, bulk-copy staging).
+// Returns 1 if the configuration is not covered.
+int fv_forward_ws(const FvParams& p, cudaStream_t stream);
+
 // fv.cu: validated dispatch used by dpd_fv_forward and dpd_model_forward.  *split_done tells whether the kernel
 // that ran also produced fv_hi / fv_lo (only the G = 8 kernel does; otherwise the caller splits afterwards).
 int fv_forward_dispatch(const FvParams& p, cudaStream_t stream, bool* split_done);

@@ -242,7 +242,10 @@ class _PackedHead:
         self.ws = None
 
     def get(self, lib, cfg, weights, ws_list):
-        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags) + tuple((w.data_ptr(), w._version) for w in weights)
+        # weights_generation: bumped by whoever updates the variables behind autograd's back (the trainer's flat Adam
+        # launch, CUDA-graph replays), which the tensors' own version counters do not see
+        key = (cfg.G, cfg.C, cfg.k, cfg.H, cfg.flags, getattr(tf_util.default_store(), "weights_generation", 0)) + \
+            tuple((w.data_ptr(), w._version) for w in weights)
         if key != self.key:
             nbytes = lib.dpd_head_packed_bytes(ctypes.byref(cfg))
             if nbytes == 0:
@@ -293,9 +296,12 @@ def _head_call(fv, query, tables, weights, k, flags, idx=None):
     return out, cfg, cache
 
 
-# called as hook(layer_index 4..1, [weight_grad, bias_grad]) as soon as a layer's gradients are complete,
-# so a data-parallel trainer can start that layer's all-reduce while the next layer is computed
-GRAD_READY_HOOK = None
+def _grad_sink():
+    """The gradient sink of the store in use, if a trainer installed one (train._GradSink): the head's backward then
+    writes the variables' gradients into the trainer's flat buffer and reports every finished layer (4..1), so the
+    data-parallel exchange of a layer can start while the next one is computed.  Captured at forward time - the
+    backward runs on autograd's thread, where the store stack of the caller is not visible."""
+    return getattr(tf_util.default_store(), "grad_sink", None)
 
 
 class _HeadFunction(torch.autograd.Function):
@@ -311,6 +317,7 @@ class _HeadFunction(torch.autograd.Function):
         ctx.fv, ctx.cfg, ctx.cache, ctx.generation = fv.detach(), cfg, cache, cache.generation
         ctx.shapes = [tuple(w.shape) for w in weights]
         ctx.query_shape = tuple(query.shape)
+        ctx.sink = _grad_sink()
         return out
 
     @staticmethod
@@ -329,8 +336,12 @@ def _head_backward(ctx, grad_out, n_leading=5):
         need_w = ctx.needs_input_grad[n_leading:]
         # a layer's weight and bias gradients come out of one product: compute both if either is asked for
         need_layer = [bool(need_w[2 * i] or need_w[2 * i + 1]) for i in range(4)]
-        grads = [torch.empty(s, device=fv.device, dtype=torch.float32) if need_layer[i // 2] else None
-                 for i, s in enumerate(ctx.shapes)]
+        sink = getattr(ctx, "sink", None) if all(need_layer) else None
+        if sink is not None:
+            grads = list(sink.buffers(ctx.shapes))
+        else:
+            grads = [torch.empty(s, device=fv.device, dtype=torch.float32) if need_layer[i // 2] else None
+                     for i, s in enumerate(ctx.shapes)]
         ptrs = [_ptr(g) if g is not None else None for g in grads]
         grad_fv = grad_query = None
         with torch.cuda.device(fv.device):
@@ -340,8 +351,8 @@ def _head_backward(ctx, grad_out, n_leading=5):
                 rc = lib.dpd_head_backward(ctypes.byref(cfg), _ptr(fv), _ptr(cache.blob), _ptr(grad_out), stage, *ptrs,
                                            _ptr(cache.ws), cache.ws.numel(), _stream())
                 _lib.check(rc, "dpd_head_backward")
-                if GRAD_READY_HOOK is not None and need_layer[layer - 1]:
-                    GRAD_READY_HOOK(layer, grads[2 * (layer - 1):2 * layer])
+                if sink is not None:
+                    sink.ready(layer)
             if ctx.inputs_need:
                 grad_fv = torch.empty_like(fv)
                 grad_query = torch.empty(ctx.query_shape, device=fv.device, dtype=torch.float32)
@@ -381,6 +392,7 @@ class _ModelTrainFunction(torch.autograd.Function):
         cache.generation = getattr(cache, "generation", 0) + 1
         ctx.fv, ctx.cfg, ctx.cache, ctx.generation = fv, cfg, cache, cache.generation
         ctx.shapes = [tuple(w.shape) for w in weights]
+        ctx.sink = _grad_sink()
         ctx.inputs_need = False
         ctx.query_shape = tuple(query.shape)
         ctx.mark_non_differentiable(fv)
@@ -471,23 +483,24 @@ def _head_variables(E, NUM_DIMS, mlp, reuse, bn=False):
     return [w1, b1, w2, b2, w3, b3, w4, b4]
 
 
-_BN_FOLDED = {}
-
-
 def _fold_batch_norm(weights, bns):
     """Inference-mode batch norm (is_training False: moving statistics, utils/tf_util.py:221-224) is a per-channel affine
     map after conv + bias, so it folds into the layer:  W' = W * s,  b' = (b - mean) * s + beta,  s = gamma / sqrt(var + eps).
-    The folded tensors are cached on the versions of the inputs (the packed-weight cache keys on them in turn)."""
+    The folded tensors are cached on the store that owns the variables, keyed on the versions of the inputs (the
+    packed-weight cache keys on them in turn)."""
+    store = tf_util.default_store()
+    folded = store.__dict__.setdefault("_bn_folded", {})
+    gen = getattr(store, "weights_generation", 0)
     out = []
     for i, (beta, gamma, mean, var) in enumerate(bns):
         w, b = weights[2 * i], weights[2 * i + 1]
-        key = tuple((t.data_ptr(), t._version) for t in (w, b, beta, gamma, mean, var))
-        hit = _BN_FOLDED.get(i)
+        key = (gen,) + tuple((t.data_ptr(), t._version) for t in (w, b, beta, gamma, mean, var))
+        hit = folded.get(i)
         if hit is None or hit[0] != key:
             with torch.no_grad():
                 s = gamma * torch.rsqrt(var + tf_util.BN_EPSILON)
                 hit = (key, (w.detach() * s).contiguous(), ((b.detach() - mean) * s + beta).contiguous(), (w, b, beta, gamma, mean, var))
-            _BN_FOLDED[i] = hit
+            folded[i] = hit
         out += [hit[1], hit[2]]
     return out
 

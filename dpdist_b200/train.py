@@ -69,25 +69,92 @@ def average_gradients(grads, group=None):
     return works
 
 
+class FlatState:
+    """The trainable variables of one tower re-homed into ONE flat fp32 buffer, with gradient and Adam-moment buffers of
+    the same layout.  The parameters stay the same `torch.nn.Parameter` objects (the VariableStore, checkpoints and the
+    TF names are untouched); only their storage moves.
+
+    Layout = the order in which the backward pass finishes the layers: bucket 0 = every variable of layers 4, 3, 2 (and
+    any variable that is not a layer-1 conv variable), bucket 1 = mapper_conv1/{weights,biases}.  So the data-parallel
+    exchange (`average_gradients`, :936-974) is at most two all-reduces per step, the first one in flight while the
+    largest product (dW1, 10.25 MB of the 18.67 MB) is still being computed, and Adam is one launch over the buffer.
+    Every segment starts on a 256-byte boundary; the padding stays zero (zero gradient -> zero Adam update)."""
+    ALIGN = 64      # floats
+
+    def __init__(self, named_params):
+        names = list(named_params.keys())
+        last = [n for n in names if "/mapper_conv1/" in n and not "/bn/" in n]
+        first = [n for n in reversed(names) if n not in last]       # layer 4 first, as the backward produces them
+        self.order = first + last
+        dev = named_params[names[0]].device
+        offs, off = {}, 0
+        for n in self.order:
+            offs[n] = off
+            off += -(-named_params[n].numel() // self.ALIGN) * self.ALIGN
+            if n == first[-1]:
+                self.split = off
+        self.total = off
+        self.param = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.param)
+        self.m = torch.zeros_like(self.param)
+        self.v = torch.zeros_like(self.param)
+        self.grad_view, self.params = {}, {}
+        with torch.no_grad():
+            for n in self.order:
+                p = named_params[n]
+                view = self.param[offs[n]:offs[n] + p.numel()].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view                                       # same Parameter object, storage inside the flat buffer
+                self.grad_view[n] = self.grad[offs[n]:offs[n] + p.numel()].view(p.shape)
+                self.params[n] = p
+        self.offs = offs
+        self.buckets = [(0, self.split), (self.split, self.total)] if last and first else [(0, self.total)]
+
+    def offset(self, name):
+        return self.offs[name]
+
+
+class _GradSink:
+    """What the head's backward writes into when a trainer is driving it: gradient buffers it does not allocate itself,
+    and a callback per finished layer.  Travels on the VariableStore (`store.grad_sink`), is captured by the autograd
+    node at forward time and used by its backward - no process-wide state, several trainers can coexist."""
+
+    def __init__(self, flat, head_names, on_ready):
+        self.views = [flat.grad_view[n] for n in head_names]       # [w1, b1, w2, b2, w3, b3, w4, b4]
+        self.on_ready = on_ready
+
+    def buffers(self, shapes):
+        if [tuple(v.shape) for v in self.views] != [tuple(s) for s in shapes]:
+            raise ValueError("gradient sink does not match the head's variables")
+        return self.views
+
+    def ready(self, layer):
+        self.on_ready(layer)
+
+
 class DPDistTrainer:
     """One rank of the DPDist trainer.  `step(pcA, pcB, labels_AB)` takes this rank's slice of the global
     batch as CUDA tensors and performs forward, loss_samples (:260-262), backward, gradient averaging and
     the Adam update; returns the local loss_samples as a tensor (no host sync)."""
 
+    HEAD = ["pc_compare/dpdist_local/mapper_conv%d/%s" % (l, w) for l in (1, 2, 3, 4) for w in ("weights", "biases")]
+
     def __init__(self, device, base_lr=0.0001, decay_step=300 * 512, decay_rate=0.5, seed=1, store=None,
                  Embedding_Size=512, k=5, sigma3dmfv=0.125, mlp=(1024, 1024, 1024), overlap_allreduce=True,
-                 cuda_graph=False):
+                 cuda_graph=False, group=None):
         self.device = torch.device(device)
         self.store = store if store is not None else tf_util.VariableStore(device=self.device, seed=seed)
         self.base_lr, self.decay_step, self.decay_rate = base_lr, decay_step, decay_rate
         self.kw = dict(bn=0, Embedding_Size=Embedding_Size, k=k, sigma3dmfv=sigma3dmfv, localSNmlp=list(mlp))
         self.batch = 0                      # the 'batch' global step variable (:201)
-        self.m, self.v = {}, {}
         self.overlap = overlap_allreduce
-        self._works = []
-        # cuda_graph=True (single process): after three eager steps the whole step (forward, backward, Adam) is captured
-        # once per input shape and replayed; only the Adam rate scalar and the inputs are rewritten per step.  For the
-        # reference's launch-bound batch of 16 pairs.
+        self.group = group
+        self.flat = None
+        self._works, self._reduced = [], set()
+        self._lr_t = torch.zeros(1, device=self.device)
+        # cuda_graph=True: after three eager steps the whole step (forward, backward, gradient all-reduce, Adam) is
+        # captured once per input shape and replayed; only the Adam rate scalar and the inputs are rewritten per step.
+        # For the reference's launch-bound batch of 16 pairs, on one GPU or sharded over several (NCCL inside the graph).
         self.cuda_graph = bool(cuda_graph)
         self._graph = None
         self._eager_steps = 0
@@ -96,59 +163,143 @@ class DPDistTrainer:
         # default stream wait on it
         self._side = torch.cuda.Stream(device=self.device) if self.cuda_graph else None
 
+    # ---- state -------------------------------------------------------------------------------------------------------
     def variables(self):
         return self.store.trainable_variables("pc_compare")
 
-    def _on_grad_ready(self, layer, grads):
-        # per-layer all-reduce on NCCL's stream, overlapping the remaining backward kernels
-        self._works += average_gradients(grads)
+    def _named(self):
+        return {n: v for n, v in self.store.vars.items() if v.requires_grad and n.startswith("pc_compare")}
 
-    def _graph_step(self, pcA, pcB, labels_AB):
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    def _create_variables(self):
+        """tf.get_variable at graph-build time: the head's variables exist before the first step."""
+        mlp = self.kw["localSNmlp"]
+        G, _ = dpdist_util._fv_grid(self.kw["Embedding_Size"], 3)
+        with tf_util.use_store(self.store), tf_util.variable_scope('pc_compare'):
+            dpdist_util._head_variables(dpdist_util.FV_CHANNELS[True] * self.kw["k"] ** 3, 3, mlp, None)
+
+    def _ensure_flat(self):
+        named = self._named()
+        if not all(n in named for n in self.HEAD):
+            self._create_variables()
+            named = self._named()
+        f = self.flat
+        if f is None or set(named) != set(f.params) or any(named[n] is not f.params[n] for n in named):
+            self.flat = FlatState(named)
+            if f is not None:                   # variables were added (e.g. batch norm): keep the moments of the old ones
+                for n, p in f.params.items():
+                    if named.get(n) is p:
+                        for new, old in ((self.flat.m, f.m), (self.flat.v, f.v)):
+                            new[self.flat.offset(n):][:p.numel()] = old[f.offset(n):][:p.numel()]
+            self._weights_changed()
+        return self.flat
+
+    @property
+    def m(self):
+        """{id(param): first-moment view} (for callers that inspect the optimizer state)."""
+        f = self._ensure_flat()
+        return {id(p): f.m[f.offset(n):][:p.numel()].view(p.shape) for n, p in f.params.items()}
+
+    @property
+    def v(self):
+        f = self._ensure_flat()
+        return {id(p): f.v[f.offset(n):][:p.numel()].view(p.shape) for n, p in f.params.items()}
+
+    # ---- one step ----------------------------------------------------------------------------------------------------
+    def _reduce_bucket(self, i):
+        lo, hi = self.flat.buckets[i]
+        self._works += average_gradients([self.flat.grad[lo:hi]], self.group)
+        self._reduced.add(i)
+
+    def _on_layer_ready(self, layer):
+        # called from the head's backward as soon as a layer's gradients are complete (4, 3, 2, 1): the first bucket goes
+        # out while dW1 is still being computed, on NCCL's own stream
+        if not self.overlap or self._world() == 1 or len(self.flat.buckets) < 2:
+            return
+        if layer == 2:
+            self._reduce_bucket(0)
+        elif layer == 1:
+            self._reduce_bucket(1)
+
+    def _forward_backward_update(self, pcA, pcB, labels_AB, add_noise):
+        flat = self._ensure_flat()
+        tf_util.clear_collections()
+        head_ok = all(n in flat.grad_view for n in self.HEAD)
+        self.store.grad_sink = _GradSink(flat, self.HEAD, self._on_layer_ready) if head_ok else None
+        self._works, self._reduced = [], set()
+        try:
+            with tf_util.use_store(self.store):
+                pred, end_points, _ = MODEL.get_model(pcA, pcB, True, add_noise=add_noise, **self.kw)
+                MODEL.get_loss(pred, end_points, labels_AB)
+            loss = tf_util.get_collection("loss_samples")[-1]      # total_loss_samples (:262-263)
+            names = list(flat.params.keys())
+            # autograd.grad, not backward(): no AccumulateGrad nodes (they would clone the buffers the all-reduce is
+            # running on, and their streams would invalidate a graph capture)
+            grads = torch.autograd.grad(loss, [flat.params[n] for n in names], allow_unused=True)
+        finally:
+            self.store.grad_sink = None
+        with torch.no_grad():
+            for n, g in zip(names, grads):
+                view = flat.grad_view[n]
+                if g is None:
+                    view.zero_()
+                elif g.data_ptr() != view.data_ptr():               # a variable outside the head's sink (batch norm, ...)
+                    if self._reduced:
+                        raise RuntimeError("gradient of %s was not written into the trainer's buffer" % n)
+                    view.copy_(g)
+        if self._world() > 1:
+            for i in range(len(flat.buckets)):
+                if i not in self._reduced:
+                    self._reduce_bucket(i)
+            for w in self._works:
+                w.wait()                                            # stream-ordered: the compute stream waits, not the host
+        self._works = []
+        self._adam(flat)
+        return loss.detach()
+
+    def _adam(self, flat):
+        """One TF-semantics Adam launch over the whole flat buffer; the bias-corrected rate is read from device memory."""
         lib = _lib.load()
-        gs = self._graph
-        if gs is None or gs["shape"] != tuple(pcA.shape):
-            params = self.variables()
-            gs = {"shape": tuple(pcA.shape), "a": pcA.clone(), "b": pcB.clone(), "l": labels_AB.clone(),
-                  "lr_t": torch.zeros(1, device=self.device), "params": params}
-            for p in params:
-                if id(p) not in self.m:
-                    self.m[id(p)] = torch.zeros_like(p)
-                    self.v[id(p)] = torch.zeros_like(p)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=self._side):
-                tf_util.clear_collections()
-                with tf_util.use_store(self.store):
-                    pred, end_points, _ = MODEL.get_model(gs["a"], gs["b"], True, **self.kw)
-                    MODEL.get_loss(pred, end_points, gs["l"])
-                loss = tf_util.get_collection("loss_samples")[-1]
-                # autograd.grad, not backward(): no AccumulateGrad nodes, whose streams (the default stream of the eager
-                # steps) would make the legacy stream wait on the capturing one and invalidate the capture
-                grads = torch.autograd.grad(loss, params)
-                gs["grads"] = grads
-                stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-                with torch.no_grad():
-                    for p, g in zip(params, grads):
-                        rc = lib.dpd_adam_step_dev(p.data_ptr(), g.data_ptr(), self.m[id(p)].data_ptr(),
-                                                   self.v[id(p)].data_ptr(), p.numel(), gs["lr_t"].data_ptr(),
-                                                   ADAM_BETA1, ADAM_BETA2, ADAM_EPS, stream)
-                        _lib.check(rc, "dpd_adam_step_dev")
-                        p.add_(0)
-                gs["loss"] = loss.detach()
-            gs["graph"] = graph
-            self._graph = gs
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = lib.dpd_adam_step_dev(flat.param.data_ptr(), flat.grad.data_ptr(), flat.m.data_ptr(), flat.v.data_ptr(),
+                                   flat.total, self._lr_t.data_ptr(), ADAM_BETA1, ADAM_BETA2, ADAM_EPS, stream)
+        _lib.check(rc, "dpd_adam_step_dev")
+
+    def _set_rate(self):
         self.batch += 1
         lr = get_learning_rate(self.batch - 1, self.base_lr, self.decay_step, self.decay_rate)
         # pageable source: the runtime stages it before returning, so the host may run ahead of the device safely
-        gs["lr_t"].copy_(torch.tensor([lib.dpd_adam_lr_t(lr, ADAM_BETA1, ADAM_BETA2, self.batch)]))
+        self._lr_t.copy_(torch.tensor([_lib.load().dpd_adam_lr_t(lr, ADAM_BETA1, ADAM_BETA2, self.batch)]))
+
+    def _weights_changed(self):
+        # the packed-weight caches key on this counter (the flat Adam launch does not touch the tensors' version counters)
+        self.store.weights_generation = getattr(self.store, "weights_generation", 0) + 1
+
+    def _graph_step(self, pcA, pcB, labels_AB):
+        gs = self._graph
+        if gs is None or gs["shape"] != tuple(pcA.shape):
+            self._ensure_flat()
+            gs = {"shape": tuple(pcA.shape), "a": pcA.clone(), "b": pcB.clone(), "l": labels_AB.clone()}
+            graph = torch.cuda.CUDAGraph()
+            self._weights_changed()              # the capture starts with a weight re-pack, so every replay does
+            with torch.cuda.graph(graph, stream=self._side):
+                gs["loss"] = self._forward_backward_update(gs["a"], gs["b"], gs["l"], 0)
+            gs["graph"] = graph
+            self._graph = gs
+        self._set_rate()
         gs["a"].copy_(pcA, non_blocking=True)
         gs["b"].copy_(pcB, non_blocking=True)
         gs["l"].copy_(labels_AB, non_blocking=True)
         gs["graph"].replay()
+        self._weights_changed()
         return gs["loss"].clone()        # the graph's own output buffer is overwritten by the next replay
 
     def step(self, pcA, pcB, labels_AB, add_noise=0):
-        distributed_now = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if self.cuda_graph and not distributed_now and not torch.is_tensor(add_noise) and add_noise == 0:
+        if self.cuda_graph and not torch.is_tensor(add_noise) and add_noise == 0:
             if self._eager_steps >= 3:
                 return self._graph_step(pcA, pcB, labels_AB)
             self._eager_steps += 1
@@ -161,38 +312,23 @@ class DPDistTrainer:
         return self._eager_step(pcA, pcB, labels_AB, add_noise)
 
     def _eager_step(self, pcA, pcB, labels_AB, add_noise=0):
-        lib = _lib.load()
-        tf_util.clear_collections()
-        with tf_util.use_store(self.store):
-            pred, end_points, _ = MODEL.get_model(pcA, pcB, True, add_noise=add_noise, **self.kw)
-            MODEL.get_loss(pred, end_points, labels_AB)
-        loss = tf_util.get_collection("loss_samples")[-1]      # total_loss_samples (:262-263)
-        params = self.variables()
-        for p in params:
-            p.grad = None
-        self._works = []
-        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        dpdist_util.GRAD_READY_HOOK = self._on_grad_ready if (self.overlap and distributed) else None
-        try:
-            loss.backward()
-        finally:
-            dpdist_util.GRAD_READY_HOOK = None
-        grads = [p.grad for p in params]
-        if distributed and not self.overlap:
-            self._works = average_gradients(grads)
-        for w in self._works:
-            w.wait()
-        self.batch += 1
-        lr = get_learning_rate(self.batch - 1, self.base_lr, self.decay_step, self.decay_rate)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        with torch.no_grad():
-            for p, g in zip(params, grads):
-                key = id(p)
-                if key not in self.m:
-                    self.m[key] = torch.zeros_like(p)
-                    self.v[key] = torch.zeros_like(p)
-                rc = lib.dpd_adam_step(p.data_ptr(), g.data_ptr(), self.m[key].data_ptr(), self.v[key].data_ptr(),
-                                       p.numel(), lr, ADAM_BETA1, ADAM_BETA2, ADAM_EPS, self.batch, stream)
-                _lib.check(rc, "dpd_adam_step")
-                p.add_(0)      # bump the tensor version: the packed-weight cache keys on it
-        return loss.detach()
+        self._set_rate()
+        loss = self._forward_backward_update(pcA, pcB, labels_AB, add_noise)
+        self._weights_changed()
+        return loss
+
+    def weights_checksum(self):
+        """Order-independent 64-bit checksum of the parameter bits (sum of the words as integers): equal on every rank
+        iff the ranks hold bit-identical weights."""
+        f = self._ensure_flat()
+        return f.param.view(torch.int32).to(torch.int64).sum()
+
+    def ranks_consistent(self):
+        """True iff every rank of the group holds bit-identical weights (one all-reduce of the checksum)."""
+        if self._world() == 1:
+            return True
+        c = self.weights_checksum().reshape(1)
+        lo, hi = c.clone(), c.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        return bool((lo == hi).item())
