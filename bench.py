@@ -48,6 +48,20 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel):
+    """(bytes per launch, source) of `kernel` from profiles/ncu_traffic.json: {kernel: {"bytes": dram read + write of one
+    launch, "source": "<ncu report / command / commit>"}}, written by tools/ncu_traffic.py from an `ncu --set full`
+    capture of `python bench.py`; (None, reason) if the kernel is not in it."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        e = d[kernel]
+        return float(e["bytes"]), e.get("source", "profiles/ncu_traffic.json")
+    except (OSError, KeyError, ValueError):
+        return None, "no ncu capture of this kernel under profiles/ (ncu_traffic.json)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -134,7 +148,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import dpdist_oracle as O
-    pairs = 32          # one step = 32 pairs = 4096 evals of the same workload
+    # one step = the whole configs[1] batch (1024 pairs = 131072 evals), evaluated in chunks of 8 pairs because the
+    # literal patch tensor of the reference is 5.12 MB per cloud (10.5 GB for the batch).  About 2 s per step on 16 cores.
+    pairs = CFG["pairs_per_gpu"]
+    if os.environ.get("DPD_BENCH_REF_PAIRS"):
+        pairs = int(os.environ["DPD_BENCH_REF_PAIRS"])
     var = O.init_variables(seed=1)
     for _ in range(args.warmup):
         cpu_reference_rate(pairs, 8, variables=var)
@@ -149,7 +167,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] sample: %d pairs/step, N=NP=64, G=8 (512 Gaussians), k=5, MLP 1024x3" % pairs,
+        "config": {"workload": "configs[1]: batch=%d synthetic pairs per step, N=NP=64, G=8 (512 Gaussians), k=5, MLP 1024x3, forward-only" % pairs,
+                   "evals_per_step": pairs * 2 * CFG["NP"],
                    "note": "CPU restatement of the reference TF1 graph (oracle/dpdist_oracle.py, torch CPU, literal tiles and patch tensor); TF1 not installable here"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d steps x %d pairs (%d evals)" % (args.steps, pairs, evals)},
@@ -280,6 +299,16 @@ def run_ours(args, rank, world, local_rank):
 
     ms, launches, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
     value = evals_per_step_rank * world * args.steps / (ms * 1e-3)
+    # The same step for >= 2 s: K = 20 steps last 60 ms, a burst at the boost clock; under sustained load the part settles
+    # at its power cap.  Both are reported; `value` stays the contract's "exactly K steps".
+    ss_steps = max(args.steps, int(np.ceil(2000.0 / max(ms / args.steps, 1e-3))))
+    if dist is not None:
+        t = torch.tensor([ss_steps], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ss_steps = int(t.item())
+    ms_ss, _, clocks_ss = timed(step_resident, ss_steps, 0, sample_clocks=True)
+    steady_state = {"value": evals_per_step_rank * world * ss_steps / (ms_ss * 1e-3), "unit": UNIT, "steps": ss_steps,
+                    "ms_per_step": ms_ss / ss_steps, "seconds": ms_ss * 1e-3, "clocks": clocks_ss}
     ms_e2e_sync, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     e2e_sync_value = evals_per_step_rank * world * args.steps / (ms_e2e_sync * 1e-3)
     ms_e2e, _, _ = timed(step_e2e_pipelined, args.steps, max(3, args.warmup // 2))
@@ -288,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
     # per-kernel device times, measured live with CUDA events on the launching stream
     lib.dpd_profile_enable(1)
     _lib.profile_read(reset=True)
-    psteps = min(args.steps, 10)
+    psteps = max(args.steps, 50)
     for i in range(psteps):
         step_resident(i)
     torch.cuda.synchronize()
@@ -312,21 +341,22 @@ def run_ours(args, rank, world, local_rank):
         ach = fl / per_launch_s / 1e12
         # the kernel is timed inside a long step -> sustained peak
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture of this
-        # very command (profiles/ncu_r1_summary.md, round-1 end state): layer 1 = 97 + 487 MB, layer 2 = 541 + 498 MB
-        traffic = {"tc_gemm2_gather_l1_f16": 584.0e6, "tc_gemm2_dense_f16": 1039.0e6, "tc_gemm2_dense_l3_l4_f16": 559.3e6}.get(dom)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch cannot be measured inside this run (it needs ncu's
+        # replay); it is read from the committed capture of this command on the current kernels, or null
+        traffic, traffic_src = ncu_traffic(dom)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": "ncu --set full, profiles/ncu_r1_summary.md (bytes per launch)",
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "tensor_work_frac": 3 * ach / peak, "peak_source": peaks["source"] + ", dense bf16 sustained; the fp32-accurate fp16x3 split issues 3 tensor "
                     "passes per algorithmic flop, so frac <= 0.333 (DESIGN.md 4.2)", "tensor_passes_per_flop": 3, "share_of_step": kernels[dom]["share"]}
     fvk = [k for k in kernels if k.startswith("fv")]
     if fvk:
         s = kernels[fvk[0]]["ms_per_launch"] * 1e-3
         ach = 2 * CFG["pairs_per_gpu"] * FV_BYTES_PER_CLOUD / s / 1e9
+        fv_traffic, fv_traffic_src = ncu_traffic(fvk[0])
         fv_kernel = {"kernel": fvk[0], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / peaks["hbm_gbs"], "traffic": 110.0e6,
-                     "note": "nominally HBM-bound; in practice bound by fp32 issue slots and the half-rate ALU pipe (FMNMX3): "
-                             "all-pairs ceiling = 43 % of the HBM peak (DESIGN.md 4.1)", "clouds_per_launch": 2 * CFG["pairs_per_gpu"],
+                     "frac": ach / peaks["hbm_gbs"], "traffic": fv_traffic, "traffic_source": fv_traffic_src,
+                     "note": "nominally HBM-bound; in practice bound by fp32 / max-min issue slots of the all-pairs loop "
+                             "(DESIGN.md 4.1)", "clouds_per_launch": 2 * CFG["pairs_per_gpu"],
                      "bytes_per_cloud": FV_BYTES_PER_CLOUD, "peak_source": peaks["source"]}
 
     # steady-state 3DmFV bandwidth: 16384 clouds per launch (8 x the in-step launch) so launch and tail
@@ -352,34 +382,122 @@ def run_ours(args, rank, world, local_rank):
         fv_kernel["steady_state"] = fv_large
         del big
 
-    # BASELINE configs[2] (training loop) beside the headline: forward + tensor-core backward + per-layer gradient
-    # all-reduce + Adam on 1024 synthetic pairs per GPU.  Informational; never allowed to break the bench line.
-    train_info = None
-    try:
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def event_time(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return max_over_ranks(t0.elapsed_time(t1) / n)
+
+    def guarded(fn):
+        """Sub-records are informational and must never break the bench line."""
+        try:
+            return fn()
+        except Exception as e:      # noqa: BLE001
+            torch.cuda.synchronize()
+            return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    # BASELINE configs[2] (training loop) beside the headline: forward + tensor-core backward + two-bucket gradient
+    # all-reduce + one Adam launch on 1024 synthetic pairs per GPU (weak scaling).
+    def run_train():
         from dpdist_b200 import train as TR, synthetic
         trainer = TR.DPDistTrainer(dev, seed=1)
         pa, pb, lab = synthetic.uniform_batch(2 + 1000 * rank, CFG["pairs_per_gpu"], CFG["N"])
         ta, tb, tl = (torch.tensor(x, device=dev) for x in (pa, pb, lab))
-        for _ in range(3):
-            trainer.step(ta, tb, tl)
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tsteps = 10
-        t0.record()
-        for _ in range(tsteps):
-            trainer.step(ta, tb, tl)
-        t1.record()
-        torch.cuda.synchronize()
-        tms = t0.elapsed_time(t1) / tsteps
-        if dist is not None:
-            tt = torch.tensor([tms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            tms = float(tt.item())
-        train_info = {"workload": "configs[2]: DPDist training step, %d pairs per GPU, Adam, gradient all-reduce" % CFG["pairs_per_gpu"],
-                      "ms_per_step": tms, "pairs_per_s": CFG["pairs_per_gpu"] * world / (tms * 1e-3), "steps": tsteps}
-        del trainer, ta, tb, tl
-    except Exception as e:      # noqa: BLE001
-        train_info = {"error": "%s: %s" % (type(e).__name__, e)}
+        tsteps = 30
+        tms = event_time(lambda: trainer.step(ta, tb, tl), tsteps, 3)
+        return {"workload": "configs[2]: DPDist training step, %d pairs per GPU, Adam, gradient all-reduce (2 buckets)" % CFG["pairs_per_gpu"],
+                "ms_per_step": tms, "pairs_per_s": CFG["pairs_per_gpu"] * world / (tms * 1e-3), "steps": tsteps,
+                # every rank must hold bit-identical weights after the averaged updates (:936-974)
+                "ranks_consistent": bool(trainer.ranks_consistent())}
+
+    # The reference's own training configuration (global batch 16, train...py:57) sharded over the ranks: strong
+    # scaling of a launch-bound step, eager and as one captured CUDA graph (NCCL all-reduce inside the graph).
+    def run_strong16():
+        from dpdist_b200 import train as TR, synthetic
+        if 16 % world != 0:
+            return {"skipped": "16 pairs do not divide over %d ranks" % world}
+        pa, pb, lab = synthetic.chair_batch(7, 16, CFG["N"])
+        mine = [torch.tensor(np.ascontiguousarray(TR.shard(x, rank, world)), device=dev) for x in (pa, pb, lab)]
+        out = {"workload": "configs[2] at the reference batch: 16 pairs global (%d per GPU), N=NP=64" % (16 // world), "scaling": "strong"}
+        for name, graph in (("eager", False), ("cuda_graph", True)):
+            trainer = TR.DPDistTrainer(dev, seed=1, cuda_graph=graph)
+            ms_ = event_time(lambda: trainer.step(*mine), 50, 8)
+            out[name] = {"ms_per_step": ms_, "pairs_per_s": 16 / (ms_ * 1e-3), "ranks_consistent": bool(trainer.ranks_consistent()),
+                         "captured": trainer._graph is not None}
+        return out
+
+    # BASELINE configs[4] (stress): 4096 pairs, N = NP = 512 over the ranks (strong scaling), forward only, swept over
+    # the Gaussian grid G and the patch edge k as SURVEY 8(d) asks.
+    def run_stress():
+        from dpdist_b200 import synthetic
+        total_pairs, Np = 4096, 512
+        if os.environ.get("DPD_BENCH_STRESS_PAIRS"):
+            total_pairs = int(os.environ["DPD_BENCH_STRESS_PAIRS"])
+        if total_pairs % world != 0:
+            return {"skipped": "%d pairs do not divide over %d ranks" % (total_pairs, world)}
+        pairs = total_pairs // world
+        g = torch.Generator(device="cpu").manual_seed(11 + rank)
+        sa = (torch.rand((pairs, Np, 3), generator=g) * 1.6 - 0.8).to(dev)
+        sb = (torch.rand((pairs, Np, 3), generator=g) * 1.6 - 0.8).to(dev)
+        out = {"workload": "configs[4]: %d pairs global (%d per GPU), N=NP=%d, forward-only" % (total_pairs, pairs, Np),
+               "scaling": "strong", "sweep": []}
+        for G, k in ((8, 5), (8, 3), (5, 5), (5, 3)):
+            st = tf_util.VariableStore(device=dev, seed=1)
+            kw2 = dict(bn=0, Embedding_Size=G ** 3, k=k, sigma3dmfv=1.0 / G, localSNmlp=[CFG["H"]] * 3)
+
+            def one():
+                with tf_util.use_store(st):
+                    return MODEL.get_model(sa, sb, False, **kw2)[0]
+            ms_ = event_time(one, 3, 1)
+            evals = 2 * total_pairs * Np
+            flops = 2 * ((3 + CFG["C"] * k ** 3) * CFG["H"] + 2 * CFG["H"] ** 2 + 3 * CFG["H"])
+            out["sweep"].append({"G": G, "k": k, "sigma": 1.0 / G, "ms_per_batch": ms_, "evals_per_s": evals / (ms_ * 1e-3),
+                                 "tflops_algorithmic": evals * flops / (ms_ * 1e-3) / 1e12})
+            del st
+        return out
+
+    # BASELINE configs[3]: PCRNet trained with the DPDist loss (iterative_PCRNet_ours.py), batch 16, 8 pose refinements,
+    # single GPU by specification: every rank would run the same thing, so rank 0's figure is reported.
+    def run_pcrnet():
+        from dpdist_b200 import pcrnet_ours as P
+        from dpdist_b200.dpdist_loss import DPDistLoss
+        out = {"workload": "configs[3]: PCRNet-ours training step, batch 16 x 64 points, 8 refinements, DPDist loss fwd + bwd into input1"}
+        tpl = torch.tensor(P.synthetic_templates(16, 64, seed=3), device=dev)
+        rng = np.random.default_rng(0)
+        src = torch.tensor(P.apply_transformation(tpl.cpu().numpy(), P.generate_poses(16, rng)), device=dev)
+        for name, graph in (("eager", False), ("cuda_graph", True)):
+            dpd = DPDistLoss(num_point=64, device=dev, seed=1)
+            tr = P.IterativePCRNetOurs(dpd, 8, 0.001, False, dev, cuda_graph=graph)
+            for _ in range(5):
+                tr.train_step(src, tpl)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(20):
+                loss = tr.train_step(src, tpl)[0]
+            t1.record()
+            torch.cuda.synchronize()
+            out[name] = {"ms_per_step": t0.elapsed_time(t1) / 20, "loss": float(loss)}
+        return out
+
+    train_info = guarded(run_train)
+    configs = {"strong_scaling_batch16": guarded(run_strong16), "stress": guarded(run_stress)}
+    if rank == 0:
+        configs["pcrnet_ours"] = guarded(run_pcrnet)
+    barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("DPD_BENCH_NO_CPU"):
@@ -409,10 +527,12 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": 2 * CFG["pairs_per_gpu"] * CFG["NP"] * 3 * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "steady_state": steady_state,
             "roofline": roofline,
             "fv_kernel": fv_kernel,
             "kernels": kernels,
             "train": train_info,
+            "configs": configs,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

@@ -393,6 +393,15 @@ static bool use_2cta() {
   return v != 0;
 }
 
+// DPD_TC_GATHER_LDG=1 assembles the layer-1 operand through registers (LDG.64 x 2 -> STS.128) instead of cp.async.  Measured
+// on B200 (profiles/ncu_r2_summary.md): 2.17 ms per launch against 1.69 ms -- the full-width shared-memory stores do not
+// pay for the load latency a register path exposes (one K-block in flight per thread instead of three).  Off by default.
+static bool gather_ldg() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DPD_TC_GATHER_LDG"); v = e ? (atoi(e) != 0) : 0; }
+  return v != 0;
+}
+
 // DPD_TC_FUSE_L4=0 keeps the separate output-layer kernel (A/B measurements)
 static bool fuse_l4() {
   static int v = -1;
@@ -452,6 +461,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
   ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4; ka.relu_bits_out = relu_bits_out;
   const bool gather_mn = gather && bx && bx->mn_major;
+  ka.gather_ldg = (gather && !gather_mn && gather_ldg()) ? 1 : 0;
   if (g) {
     ka.g = *g;
     if (gather && !gather_mn) {   // valid operand length E + 3; everything from there to K is zero padding

@@ -64,6 +64,9 @@ struct KernelArgs {
                            // so that the next layer's operand scale needs no extra pass over the gradient
   int last_ks;             // 2-CTA kernel: K-steps (16 elements) of the LAST K-block that hold data; 0 = all four.  The padded
                            // tail of the layer-1 operand (2503 -> 2560) is zero on both sides: its MMAs are not issued.
+  int gather_ldg;          // 2-CTA gather kernel, K-major operand: assemble the A tile through registers (LDG.64 x 2 ->
+                           // STS.128, full 128-byte shared-memory wavefronts) instead of 8-byte cp.async, whose data lands
+                           // sector by sector (about 3.8 x the ideal number of write wavefronts, profiles/ncu_r1_summary.md)
   GatherArgs g;
 };
 

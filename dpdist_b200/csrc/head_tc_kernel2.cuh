@@ -533,6 +533,85 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           if (++s == STAGES2) { s = 0; ph ^= 1; }
         }
       }
+    } else if (args.gather_ldg) {
+      // Register path: thread (rl = p / 8, u = p % 8) fills the 16-byte unit u of rows it*16 + rl, it = 0..7, of every
+      // K-block: two 8-byte loads (the two 4-element chunks of the unit; a chunk never straddles a tap) and one STS.128.
+      // A quarter warp writes the eight units of one 128-byte row: full-width, conflict-free shared-memory wavefronts.
+      constexpr int NIT2 = 8;
+      const int rl = p >> 3, u = p & 7;
+      for (int w = cluster_id; w < num_items; w += num_clusters) {
+        const int t = w % num_tiles;
+        const int mt = t / num_n_tiles;
+        if (item_skipped(mt)) continue;
+        const int row_base = mt * 2 * BM + (int)rank * BM;
+        int32_t rel[NIT2];
+        uint32_t rmsk[NIT2];
+#pragma unroll
+        for (int it = 0; it < NIT2; ++it) {
+          const int m = row_base + it * 16 + rl;
+          rel[it] = -1; rmsk[it] = 0;
+          if (m < args.M) {
+            const long long cloud = (g.row0 + m) / g.n_query;
+            const int v = __ldg(g.idx + m);
+            rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
+            const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
+            uint32_t mk = 0;
+            for (int a = 0; a < g.k; ++a) {
+              mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
+              mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
+              mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
+            }
+            rmsk[it] = mk;
+          }
+        }
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          uint32_t code[2]; int32_t delta[2];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code[hf]) : "r"(lut_s + (uint32_t)(kb * CHUNKS + 2 * u + hf) * 4u));
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta[hf]) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + 2 * u + hf) * 4u));
+          }
+          uint2 vh[NIT2][2], vl[NIT2][2];
+#pragma unroll
+          for (int it = 0; it < NIT2; ++it) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint32_t c = code[hf];
+              const uint8_t *sh, *sl;
+              bool ok;
+              if (c < LUT_OFFS) {
+                const uint32_t s0 = c & 255u, s1 = 8u + ((c >> 8) & 255u), s2 = 16u + ((c >> 16) & 255u);
+                ok = ((rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u) != 0;
+                const size_t el = ok ? (size_t)(rel[it] + delta[hf]) : 0;
+                sh = fv_hi + el * ELEM; sl = fv_lo + el * ELEM;
+              } else {
+                ok = (c == LUT_OFFS) && rel[it] >= 0;
+                const size_t m = ok ? (size_t)row_base + it * 16 + rl : 0;
+                sh = o4_hi + m * 4 * ELEM; sl = o4_lo + m * 4 * ELEM;
+              }
+              vh[it][hf] = make_uint2(0u, 0u); vl[it][hf] = make_uint2(0u, 0u);
+              if (ok) {
+                vh[it][hf] = __ldg(reinterpret_cast<const uint2*>(sh));
+                vl[it][hf] = __ldg(reinterpret_cast<const uint2*>(sl));
+              }
+            }
+          }
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+#pragma unroll
+          for (int it = 0; it < NIT2; ++it) {
+            const int r = it * 16 + rl;
+            const uint32_t dst = (uint32_t)(r * 128) + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + dst), "r"(vh[it][0].x), "r"(vh[it][0].y),
+                         "r"(vh[it][1].x), "r"(vh[it][1].y) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + dst), "r"(vl[it][0].x), "r"(vl[it][0].y),
+                         "r"(vl[it][1].x), "r"(vl[it][1].y) : "memory");
+          }
+          fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          mbar_arrive(leader ? &ctl->full[s] : &ctl->gfull[s]);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
     } else
     for (int w = cluster_id; w < num_items; w += num_clusters) {
       const int t = w % num_tiles;

@@ -1,0 +1,50 @@
+"""profiles/ncu_traffic.json from an `ncu --set full` report of `python bench.py`:
+    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv ;  python tools/ncu_traffic.py raw.csv "<how it was captured>"
+Per kernel (DPD_LAUNCH name, see MAP): dram__bytes_read.sum + dram__bytes_write.sum of one launch (mean over the captured
+launches), which bench.py quotes as roofline.traffic."""
+import csv
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# kernel function name (regex) + discriminator -> the name bench.py's per-kernel profile uses
+MAP = [(r"fv_g8_ws_kernel", "fv_g8_ws"), (r"fv_g8_kernel", "fv_g8"), (r"fv_generic_kernel", "fv_generic")]
+
+
+def unit_scale(u):
+    return {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+
+
+def main():
+    raw, how = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
+    rows = list(csv.reader(open(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    out = {}
+    acc = {}
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        rd = float(r[col["dram__bytes_read.sum"]]) * unit_scale(units[col["dram__bytes_read.sum"]])
+        wr = float(r[col["dram__bytes_write.sum"]]) * unit_scale(units[col["dram__bytes_write.sum"]])
+        dur = float(r[col["gpu__time_duration.sum"]])
+        key = None
+        for pat, k in MAP:
+            if re.search(pat, name):
+                key = k
+        if key is None and "tc_gemm2_kernel" in name:
+            # the three forward GEMM launches of a step share one template: tell them apart by the bytes they read
+            key = "tc_gemm2:" + name
+        if key is None:
+            continue
+        acc.setdefault(key, []).append((rd, wr, dur))
+    for k, v in acc.items():
+        n = len(v)
+        out[k] = {"bytes": sum(a + b for a, b, _ in v) / n, "read": sum(a for a, _, _ in v) / n, "write": sum(b for _, b, _ in v) / n,
+                  "launches": n, "duration_us_under_ncu": sum(d for _, _, d in v) / n, "source": how}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
