@@ -188,8 +188,10 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.load()
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that fails must not leave the others waiting for NCCL's default ten minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if dist is not None:
@@ -418,10 +420,12 @@ def run_ours(args, rank, world, local_rank):
         ta, tb, tl = (torch.tensor(x, device=dev) for x in (pa, pb, lab))
         tsteps = 30
         tms = event_time(lambda: trainer.step(ta, tb, tl), tsteps, 3)
+        consistent = bool(trainer.ranks_consistent())
+        trainer.close()
         return {"workload": "configs[2]: DPDist training step, %d pairs per GPU, Adam, gradient all-reduce (2 buckets)" % CFG["pairs_per_gpu"],
                 "ms_per_step": tms, "pairs_per_s": CFG["pairs_per_gpu"] * world / (tms * 1e-3), "steps": tsteps,
                 # every rank must hold bit-identical weights after the averaged updates (:936-974)
-                "ranks_consistent": bool(trainer.ranks_consistent())}
+                "ranks_consistent": consistent}
 
     # The reference's own training configuration (global batch 16, train...py:57) sharded over the ranks: strong
     # scaling of a launch-bound step, eager and as one captured CUDA graph (NCCL all-reduce inside the graph).
@@ -437,6 +441,8 @@ def run_ours(args, rank, world, local_rank):
             ms_ = event_time(lambda: trainer.step(*mine), 50, 8)
             out[name] = {"ms_per_step": ms_, "pairs_per_s": 16 / (ms_ * 1e-3), "ranks_consistent": bool(trainer.ranks_consistent()),
                          "captured": trainer._graph is not None}
+            trainer.close()        # the captured NCCL kernels must be gone before the communicator is destroyed
+            del trainer
         return out
 
     # BASELINE configs[4] (stress): 4096 pairs, N = NP = 512 over the ranks (strong scaling), forward only, swept over
@@ -480,6 +486,14 @@ def run_ours(args, rank, world, local_rank):
         src = torch.tensor(P.apply_transformation(tpl.cpu().numpy(), P.generate_poses(16, rng)), device=dev)
         for name, graph in (("eager", False), ("cuda_graph", True)):
             dpd = DPDistLoss(num_point=64, device=dev, seed=1)
+            with torch.no_grad():      # a "trained-like" DPDist: outputs spread over (0, 2) instead of the ~1e-4 of a fresh Xavier init
+                for n_, v_ in dpd.store.vars.items():
+                    if n_.endswith("mapper_conv1/weights"):
+                        v_.mul_(600.0)
+                    elif n_.endswith("weights") and "conv4" not in n_:
+                        v_.mul_(2.0)
+                    elif n_.endswith("mapper_conv4/biases"):
+                        v_.add_(1.0)
             tr = P.IterativePCRNetOurs(dpd, 8, 0.001, False, dev, cuda_graph=graph)
             for _ in range(5):
                 tr.train_step(src, tpl)
@@ -537,7 +551,13 @@ def run_ours(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        # the line is out; never let communicator teardown hold the process (and the GPU box) hostage
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

@@ -79,6 +79,20 @@ SIGNATURES.update({
     "dpd_assemble_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),
+    "dpd_layer_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dpd_layer_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dpd_layer_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_size_t, ctypes.c_void_p]),
+    "dpd_bn_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                      ctypes.c_void_p]),
+    "dpd_bn_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dpd_crc32c": (ctypes.c_uint32, [ctypes.c_char_p, ctypes.c_size_t]),
     "dpd_launch_count": (ctypes.c_longlong, []),
     "dpd_profile_enable": (ctypes.c_int, [ctypes.c_int]),
@@ -101,8 +115,12 @@ def lib_path():
     return _build.LIB_PATH
 
 
+ABI_VERSION = 3          # must equal DPD_ABI_VERSION in include/dpdist_b200.h
+
+
 def load():
-    """Load (building first if the .so is absent and nvcc is present).  Raises if unavailable."""
+    """Load the library, (re)building it first when a compiler is present and the sources changed.  Raises if unavailable:
+    there is no fallback.  Concurrent ranks are safe: the build runs under a file lock and is renamed into place."""
     global _LIB
     if _LIB is not None:
         return _LIB
@@ -110,14 +128,24 @@ def load():
         if _LIB is not None:
             return _LIB
         path = lib_path()
-        if not os.path.exists(path):
+        try:
+            stale = _build.needs_build()
+        except Exception:       # noqa: BLE001  (unreadable sources: trust a library that is there)
+            stale = not os.path.exists(path)
+        if stale:
             try:
                 _build.build_library()
-            except Exception as e:  # no nvcc / compile error: there is no fallback
-                raise DPDistNativeError(
-                    "libdpdist_b200.so is missing and could not be built (%s). "
-                    "dpdist_b200 has no CPU fallback; run `python -m dpdist_b200.build`." % e) from e
+            except Exception as e:  # no nvcc / compile error
+                if not os.path.exists(path):
+                    raise DPDistNativeError(
+                        "libdpdist_b200.so is missing and could not be built (%s). "
+                        "dpdist_b200 has no CPU fallback; run `python -m dpdist_b200.build`." % e) from e
         lib = ctypes.CDLL(path)
+        lib.dpd_version.restype = ctypes.c_int
+        got = lib.dpd_version()
+        if got != ABI_VERSION:
+            raise DPDistNativeError("%s implements ABI version %d, this package binds version %d: rebuild it "
+                                    "(`python -m dpdist_b200.build --force`)" % (path, got, ABI_VERSION))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -76,20 +76,34 @@ def _compile_one(nvcc, src):
 
 
 def build_library(force=False, verbose=False):
-    """Compile every csrc/*.cu for sm_100a and link libdpdist_b200.so.  Returns the .so path."""
+    """Compile every csrc/*.cu for sm_100a and link libdpdist_b200.so.  Returns the .so path.
+    Safe under concurrent callers (one rank per GPU all importing the package): the whole build runs under an exclusive
+    file lock, whoever gets it second finds the library up to date, and the .so appears by an atomic rename so that no
+    process can dlopen a half-written file."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(BUILD_DIR, exist_ok=True)
-    srcs = _sources()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile_one(nvcc, s), srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(STAMP_PATH, "w") as fh:
-        fh.write(_stamp())
+    import fcntl
+    with open(os.path.join(BUILD_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another process built it while we waited
+                return LIB_PATH
+            srcs = _sources()
+            with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+                objs = list(ex.map(lambda s: _compile_one(nvcc, s), srcs))
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP_PATH + ".tmp", "w") as fh:
+                fh.write(_stamp())
+            os.replace(STAMP_PATH + ".tmp", STAMP_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     if verbose:
         print("built", LIB_PATH)
     return LIB_PATH

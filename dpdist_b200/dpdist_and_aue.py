@@ -37,8 +37,9 @@ def get_model(pcA, pcB,
                   [B,V,k^3*20] tensors here; they are LocalPatches handles unless
                   materialize_embeddings=True (5.12 MB per cloud at the defaults).
     `reuse` and `materialize_embeddings` are additions; everything else is the reference signature.
-    `bn` defaults to True as in the reference, whose trainer passes bn=int('0') (train...py:98,225).  With bn truthy only
-    inference (is_training False, moving statistics folded into the layers) is implemented."""
+    `bn` defaults to True as in the reference, whose trainer passes bn=int('0') (train...py:98,225).  With bn truthy the
+    head runs batch norm after every conv: is_training True = batch statistics, moving-average updates with `bn_decay`
+    (layer-by-layer fp32 path); is_training False = moving statistics folded into the fused layers."""
     with tf_util.variable_scope('pc_compare', reuse=reuse):                               # :36
         NUM_DIMS = pcA.shape[-1]
         n_gaussians = Embedding_Size

@@ -505,6 +505,111 @@ def _fold_batch_norm(weights, bns):
     return out
 
 
+class _BnTrainHead(torch.autograd.Function):
+    """The head with training-mode batch norm (`--BN 1`, is_training True): conv + bias, batch statistics, affine map and
+    activation per layer (utils/tf_util.py:213-227, 558-577), layer by layer in fp32 through dpd_layer_forward /
+    dpd_bn_forward, and the gradient graph over it through dpd_bn_backward / dpd_layer_backward.
+    Inputs: fv [2B,V,C], query [2B,NP,3], the 8 conv variables (reference layouts) and (gamma, beta) of the 4 layers.
+    Outputs: out [2B,NP,3] and, not differentiable, (batch mean, biased batch variance) of every layer for the moving
+    averages."""
+
+    @staticmethod
+    def forward(ctx, fv, query, tables, k, *params):
+        lib = _lib.load()
+        weights, affine = params[:8], params[8:]
+        fv = _check_cuda(fv.detach(), "fv")
+        query = _check_cuda(query.detach(), "query")
+        n_clouds, V, Cc = fv.shape
+        NP = query.shape[1]
+        rows = n_clouds * NP
+        G, l, lo, hi = tables
+        dev = fv.device
+        H = weights[0].shape[-1]
+        E = k ** 3 * Cc
+        Kp1 = -(-(E + 3) // 32) * 32
+        idx = torch.empty(rows, device=dev, dtype=torch.int32)
+        mask = torch.empty(rows, device=dev, dtype=torch.float32)
+        off = torch.empty((rows, 3), device=dev, dtype=torch.float32)
+        st = _stream()
+        with torch.cuda.device(dev):
+            _lib.check(lib.dpd_voxel_assign(_ptr(query), 1, rows, G, _lib.fptr(l), _lib.fptr(lo), _lib.fptr(hi), _ptr(idx), _ptr(mask),
+                                            _ptr(off), st), "dpd_voxel_assign")
+            w1 = weights[0].detach().reshape(E + 3, H)
+            w1p = torch.cat([w1[3:], w1[:3], w1.new_zeros((Kp1 - E - 3, H))], 0).contiguous()     # patch | offset | pad
+            ws_bytes = max(lib.dpd_layer_workspace_bytes(rows, Kp1, H), lib.dpd_layer_workspace_bytes(rows, H, H),
+                           lib.dpd_layer_workspace_bytes(rows, H, 3))
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            zs, ys, stats = [], [], []
+            x = None
+            for layer in range(4):
+                wl = w1p if layer == 0 else weights[2 * layer].detach().reshape(H, -1).contiguous()
+                bl = weights[2 * layer + 1].detach().contiguous()
+                K, N = wl.shape
+                z = torch.empty((rows, N), device=dev, dtype=torch.float32)
+                if layer == 0:
+                    rc = lib.dpd_layer_forward(None, rows, K, _ptr(wl), _ptr(bl), N, _ptr(z), _ptr(fv), _ptr(idx), _ptr(off), NP, G, Cc, k, st)
+                else:
+                    rc = lib.dpd_layer_forward(_ptr(x), rows, K, _ptr(wl), _ptr(bl), N, _ptr(z), None, None, None, 0, 0, 0, 0, st)
+                _lib.check(rc, "dpd_layer_forward")
+                gamma, beta = affine[2 * layer].detach().contiguous(), affine[2 * layer + 1].detach().contiguous()
+                y = torch.empty_like(z)
+                mean = torch.empty(N, device=dev, dtype=torch.float32)
+                var = torch.empty(N, device=dev, dtype=torch.float32)
+                rc = lib.dpd_bn_forward(_ptr(z), rows, N, _ptr(gamma), _ptr(beta), tf_util.BN_EPSILON, 1 if layer < 3 else 0, _ptr(y),
+                                        _ptr(mean), _ptr(var), _ptr(ws), ws.numel(), st)
+                _lib.check(rc, "dpd_bn_forward")
+                zs.append(z); ys.append(y); stats += [mean, var]
+                x = y
+        y4 = ys[3]
+        out = (torch.clamp(y4, 0.0, 6.0) / 3.0 * mask[:, None]).view(n_clouds, NP, 3)          # :690-691, :697-698
+        ctx.cfg = (rows, NP, G, Cc, k, H, E, Kp1)
+        ctx.keep = (fv, idx, off, mask, w1p, zs, ys, stats, ws, [w.detach() for w in weights], [a.detach() for a in affine])
+        ctx.mark_non_differentiable(*stats)
+        return (out,) + tuple(stats)
+
+    @staticmethod
+    def backward(ctx, grad_out, *_unused):
+        lib = _lib.load()
+        rows, NP, G, Cc, k, H, E, Kp1 = ctx.cfg
+        fv, idx, off, mask, w1p, zs, ys, stats, ws, weights, affine = ctx.keep
+        dev = fv.device
+        st = _stream()
+        y4 = ys[3]
+        dy = (grad_out.reshape(rows, 3).float() * mask[:, None] * ((y4 > 0) & (y4 < 6)).float() / 3.0).contiguous()    # relu6' / 3
+        gw, gb, gg, gbeta = [None] * 4, [None] * 4, [None] * 4, [None] * 4
+        with torch.cuda.device(dev):
+            for layer in (3, 2, 1, 0):
+                z = zs[layer]
+                N = z.shape[1]
+                gamma, beta = affine[2 * layer].contiguous(), affine[2 * layer + 1].contiguous()
+                dz = torch.empty_like(z)
+                gg[layer] = torch.empty(N, device=dev, dtype=torch.float32)
+                gbeta[layer] = torch.empty(N, device=dev, dtype=torch.float32)
+                rc = lib.dpd_bn_backward(_ptr(z), _ptr(dy), rows, N, _ptr(gamma), _ptr(beta), _ptr(stats[2 * layer]), _ptr(stats[2 * layer + 1]),
+                                         tf_util.BN_EPSILON, 1 if layer < 3 else 0, _ptr(dz), _ptr(gg[layer]), _ptr(gbeta[layer]),
+                                         _ptr(ws), ws.numel(), st)
+                _lib.check(rc, "dpd_bn_backward")
+                gb[layer] = torch.empty(N, device=dev, dtype=torch.float32)
+                if layer == 0:
+                    gw[0] = torch.empty((E + 3, H), device=dev, dtype=torch.float32)
+                    rc = lib.dpd_layer_backward(None, rows, Kp1, _ptr(w1p), H, _ptr(dz), _ptr(gw[0]), _ptr(gb[0]), None, _ptr(fv), _ptr(idx),
+                                                _ptr(off), NP, G, Cc, k, _ptr(ws), ws.numel(), st)
+                else:
+                    wl = weights[2 * layer].reshape(H, -1).contiguous()
+                    gw[layer] = torch.empty_like(wl)
+                    dx = torch.empty((rows, H), device=dev, dtype=torch.float32)
+                    rc = lib.dpd_layer_backward(_ptr(ys[layer - 1]), rows, H, _ptr(wl), N, _ptr(dz), _ptr(gw[layer]), _ptr(gb[layer]), _ptr(dx),
+                                                None, None, None, 0, 0, 0, 0, _ptr(ws), ws.numel(), st)
+                    dy = dx
+                _lib.check(rc, "dpd_layer_backward")
+        grads = []
+        for layer in range(4):
+            grads += [gw[layer].view(weights[2 * layer].shape), gb[layer]]
+        for layer in range(4):
+            grads += [gg[layer], gbeta[layer]]
+        return (None, None, None, None) + tuple(grads)
+
+
 def model_forward(points, query, n_gaussians, sigma, full_fv, k, mlp, reuse=None, impl=None):
     """One dpd_model_forward call: 3DmFV of `points` [2B,N,3] (rows [A | B]) and the head evaluated at `query`
     [2B,NP,3] (rows [pcB | pcA]) -> (fv [2B,V,C], out [2B,NP,3], C [V,3]).  Inference only (no autograd node);
@@ -545,7 +650,8 @@ def DPDist(point_cloud, point_cloudB, embedding,
            bn=True, wd=0.0,
            sig=True, Embedding_Size=512,
            NUM_DIMS=2, mlp=[32, 16, 16], k=3, conv_version=1, output_act='relu'):
-    """utils/dpdist_util.py:412-700 for k > 0, conv_version 1, NUM_DIMS 3, bn off.
+    """utils/dpdist_util.py:412-700 for k > 0, conv_version 1, NUM_DIMS 3; `bn` truthy adds batch norm after every conv
+    (training mode: batch statistics and moving-average updates; inference: moving statistics).
     Returns [pred_AB, pred_BA], each [B,NP,1,3]: queries point_cloudB against A's field and
     queries point_cloud against B's field (:494-500), masked to the unit cube (:697-698)."""
     _check_head_options(k, conv_version, NUM_DIMS, bn, output_act, mlp)
@@ -558,13 +664,27 @@ def DPDist(point_cloud, point_cloudB, embedding,
     B, NP, _ = pcA.shape
     E = fvA.shape[2] * k ** 3
     H = mlp[0]
+    training = not (isinstance(is_training, (bool, int)) and not is_training)
+    if bn and training:
+        # batch statistics (utils/tf_util.py:221-224, 558-577): layer-by-layer fp32 path, _BnTrainHead
+        weights, bns = _head_variables(E, NUM_DIMS, mlp, reuse, bn=True)
+        fv_all = torch.cat([fvA, fvB], 0)
+        query = torch.cat([pcB, pcA], 0)
+        affine = [t for (beta, gamma, _, _) in bns for t in (gamma, beta)]
+        res = _BnTrainHead.apply(fv_all, query, _assign_tables(C), k, *weights, *affine)
+        out, stats = res[0], res[1:]
+        # moving averages, updated in place as with updates_collections=None [TF-semantics: the fused batch norm feeds
+        # them the unbiased batch variance]; decay = bn_decay, 0.9 if None (utils/tf_util.py:569)
+        d = 0.9 if bn_decay is None else float(bn_decay)
+        n = fv_all.shape[0] * NP
+        with torch.no_grad():
+            for i, (_, _, mm, mv) in enumerate(bns):
+                mm.mul_(d).add_(stats[2 * i], alpha=1.0 - d)
+                mv.mul_(d).add_(stats[2 * i + 1], alpha=(1.0 - d) * n / max(n - 1, 1))
+        out = out.view(2, B, NP, 1, 3)
+        return [out[0], out[1]]
     if bn:
-        # batch norm after every conv + bias (utils/tf_util.py:221-224).  Inference (moving statistics) folds into the
-        # layers; training-mode batch statistics are not implemented (the reference trains with --BN 0, the log-dir
-        # name of its shipped run says BN0).
-        if not (isinstance(is_training, (bool, int)) and not is_training):
-            raise NotImplementedError("bn=True with is_training=True (batch statistics) is not implemented; "
-                                      "inference with the moving statistics (is_training=False) is")
+        # inference: the moving statistics fold into the layers
         weights, bns = _head_variables(E, NUM_DIMS, mlp, reuse, bn=True)
         weights = _fold_batch_norm(weights, bns)
     else:

@@ -26,6 +26,11 @@ def get_learning_rate(batch, base_lr=0.0001, decay_step=300 * 512, decay_rate=0.
     return max(lr, 0.0000001)
 
 
+def get_bn_decay(batch, decay_step=300 * 512, init_decay=0.5, decay_rate=0.5, clip=0.99):
+    """:172-175, :992-1000: min(BN_DECAY_CLIP, 1 - BN_INIT_DECAY * BN_DECAY_DECAY_RATE^floor(batch / DECAY_STEP))."""
+    return min(clip, 1.0 - init_decay * decay_rate ** (int(batch) // int(decay_step)))
+
+
 def assemble_batch(batch_data, batch_label, NUM_POINT):
     """:749-766.  batch_data [bsize, 3*npoints, 3] = surface | close | far (modelnet_dataset.py:136-139),
     batch_label [bsize, 2*npoints] = GT distances of close | far  ->  (pcA, pcB, labels_AB)."""
@@ -108,6 +113,7 @@ class FlatState:
                 self.grad_view[n] = self.grad[offs[n]:offs[n] + p.numel()].view(p.shape)
                 self.params[n] = p
         self.offs = offs
+        self.accum = None           # gradient accumulator of micro-batched steps, allocated on first use
         self.buckets = [(0, self.split), (self.split, self.total)] if last and first else [(0, self.total)]
 
     def offset(self, name):
@@ -141,11 +147,13 @@ class DPDistTrainer:
 
     def __init__(self, device, base_lr=0.0001, decay_step=300 * 512, decay_rate=0.5, seed=1, store=None,
                  Embedding_Size=512, k=5, sigma3dmfv=0.125, mlp=(1024, 1024, 1024), overlap_allreduce=True,
-                 cuda_graph=False, group=None):
+                 cuda_graph=False, group=None, bn=0):
         self.device = torch.device(device)
         self.store = store if store is not None else tf_util.VariableStore(device=self.device, seed=seed)
         self.base_lr, self.decay_step, self.decay_rate = base_lr, decay_step, decay_rate
-        self.kw = dict(bn=0, Embedding_Size=Embedding_Size, k=k, sigma3dmfv=sigma3dmfv, localSNmlp=list(mlp))
+        # bn truthy = the reference's --BN 1: batch norm after every conv, batch statistics per tower (not synchronised
+        # across towers, utils/tf_util.py:573-577), gamma / beta trained with the other variables, bn_decay of :992-1000
+        self.kw = dict(bn=int(bn), Embedding_Size=Embedding_Size, k=k, sigma3dmfv=sigma3dmfv, localSNmlp=list(mlp))
         self.batch = 0                      # the 'batch' global step variable (:201)
         self.overlap = overlap_allreduce
         self.group = group
@@ -180,7 +188,7 @@ class DPDistTrainer:
         mlp = self.kw["localSNmlp"]
         G, _ = dpdist_util._fv_grid(self.kw["Embedding_Size"], 3)
         with tf_util.use_store(self.store), tf_util.variable_scope('pc_compare'):
-            dpdist_util._head_variables(dpdist_util.FV_CHANNELS[True] * self.kw["k"] ** 3, 3, mlp, None)
+            dpdist_util._head_variables(dpdist_util.FV_CHANNELS[True] * self.kw["k"] ** 3, 3, mlp, None, bn=bool(self.kw["bn"]))
 
     def _ensure_flat(self):
         named = self._named()
@@ -225,15 +233,52 @@ class DPDistTrainer:
         elif layer == 1:
             self._reduce_bucket(1)
 
+    MAX_ROWS = 1 << 18      # rows (2 * pairs * NP) one DPD_HEAD_TRAIN call keeps activations for (head.cu MAX_CHUNK_ROWS)
+
     def _forward_backward_update(self, pcA, pcB, labels_AB, add_noise):
         flat = self._ensure_flat()
+        pairs, NP = pcA.shape[0], pcB.shape[1]
+        per = max(1, self.MAX_ROWS // (2 * NP))
+        if pairs > per:
+            # The training forward keeps every activation of its rows, so it is bounded to one row chunk.  Larger tower
+            # batches (config E: N = NP = 512) run as micro-batches whose gradients are accumulated with the weights
+            # n_i / n: the loss is a mean over the batch, so the sum is the gradient of the whole batch.
+            if flat.accum is None:
+                flat.accum = torch.zeros_like(flat.grad)
+            flat.accum.zero_()
+            total = None
+            for lo in range(0, pairs, per):
+                hi = min(pairs, lo + per)
+                noise = add_noise[lo:hi] if torch.is_tensor(add_noise) else add_noise
+                loss = self._forward_backward(flat, pcA[lo:hi], pcB[lo:hi], labels_AB[lo:hi], noise, reduce=False)
+                w = (hi - lo) / pairs
+                flat.accum.add_(flat.grad, alpha=w)
+                total = loss * w if total is None else total + loss * w
+            flat.grad.copy_(flat.accum)
+            loss = total
+        else:
+            loss = self._forward_backward(flat, pcA, pcB, labels_AB, add_noise, reduce=True)
+        if self._world() > 1:
+            for i in range(len(flat.buckets)):
+                if i not in self._reduced:
+                    self._reduce_bucket(i)
+            for w in self._works:
+                w.wait()                                            # stream-ordered: the compute stream waits, not the host
+        self._works = []
+        self._adam(flat)
+        return loss.detach()
+
+    def _forward_backward(self, flat, pcA, pcB, labels_AB, add_noise, reduce):
+        """Forward, loss_samples and the gradients of every trainable variable into flat.grad.  `reduce`: let the head's
+        backward start the all-reduce of a bucket as soon as its layers are done."""
         tf_util.clear_collections()
         head_ok = all(n in flat.grad_view for n in self.HEAD)
-        self.store.grad_sink = _GradSink(flat, self.HEAD, self._on_layer_ready) if head_ok else None
+        self.store.grad_sink = _GradSink(flat, self.HEAD, self._on_layer_ready if reduce else (lambda layer: None)) if head_ok else None
         self._works, self._reduced = [], set()
         try:
+            kw = dict(self.kw, bn_decay=get_bn_decay(max(self.batch - 1, 0), self.decay_step)) if self.kw["bn"] else self.kw
             with tf_util.use_store(self.store):
-                pred, end_points, _ = MODEL.get_model(pcA, pcB, True, add_noise=add_noise, **self.kw)
+                pred, end_points, _ = MODEL.get_model(pcA, pcB, True, add_noise=add_noise, **kw)
                 MODEL.get_loss(pred, end_points, labels_AB)
             loss = tf_util.get_collection("loss_samples")[-1]      # total_loss_samples (:262-263)
             names = list(flat.params.keys())
@@ -251,15 +296,7 @@ class DPDistTrainer:
                     if self._reduced:
                         raise RuntimeError("gradient of %s was not written into the trainer's buffer" % n)
                     view.copy_(g)
-        if self._world() > 1:
-            for i in range(len(flat.buckets)):
-                if i not in self._reduced:
-                    self._reduce_bucket(i)
-            for w in self._works:
-                w.wait()                                            # stream-ordered: the compute stream waits, not the host
-        self._works = []
-        self._adam(flat)
-        return loss.detach()
+        return loss
 
     def _adam(self, flat):
         """One TF-semantics Adam launch over the whole flat buffer; the bias-corrected rate is read from device memory."""
@@ -286,7 +323,10 @@ class DPDistTrainer:
             gs = {"shape": tuple(pcA.shape), "a": pcA.clone(), "b": pcB.clone(), "l": labels_AB.clone()}
             graph = torch.cuda.CUDAGraph()
             self._weights_changed()              # the capture starts with a weight re-pack, so every replay does
-            with torch.cuda.graph(graph, stream=self._side):
+            # distributed: NCCL's watchdog thread polls events while this thread captures; only this thread's calls may
+            # invalidate the capture
+            mode = "thread_local" if self._world() > 1 else "global"
+            with torch.cuda.graph(graph, stream=self._side, capture_error_mode=mode):
                 gs["loss"] = self._forward_backward_update(gs["a"], gs["b"], gs["l"], 0)
             gs["graph"] = graph
             self._graph = gs
@@ -299,7 +339,7 @@ class DPDistTrainer:
         return gs["loss"].clone()        # the graph's own output buffer is overwritten by the next replay
 
     def step(self, pcA, pcB, labels_AB, add_noise=0):
-        if self.cuda_graph and not torch.is_tensor(add_noise) and add_noise == 0:
+        if self.cuda_graph and not self.kw["bn"] and not torch.is_tensor(add_noise) and add_noise == 0:
             if self._eager_steps >= 3:
                 return self._graph_step(pcA, pcB, labels_AB)
             self._eager_steps += 1
@@ -316,6 +356,15 @@ class DPDistTrainer:
         loss = self._forward_backward_update(pcA, pcB, labels_AB, add_noise)
         self._weights_changed()
         return loss
+
+    def close(self):
+        """Drop the captured graph.  Call before dist.destroy_process_group(): a communicator cannot be torn down while a
+        live CUDA graph still holds its captured collective kernels (the destroy call then never returns)."""
+        torch.cuda.synchronize(self.device)
+        self._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(self.device)
 
     def weights_checksum(self):
         """Order-independent 64-bit checksum of the parameter bits (sum of the words as integers): equal on every rank

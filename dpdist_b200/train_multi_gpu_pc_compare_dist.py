@@ -35,23 +35,33 @@ def train_on_dataset(FLAGS, tr, dev, rank, world):
     TRAIN_DATASET, TEST_DATASET = mk('train'), mk('test')
 
     def batches(ds, augment):
+        # "Make sure batch data is of same size" (:735-739, :815-817): the reference feeds fixed BATCH_SIZE buffers and
+        # overwrites only the first `bsize` rows, so a short last batch is completed by the rows the previous batch left
+        # there (zeros in the very first batch).  Same here, which also keeps every batch divisible by the towers.
+        cur = None
         while ds.has_next_batch():
             pcA, pcB, lab = ds.next_batch_device(FLAGS.num_point, augment=augment)
-            if pcA.shape[0] % world != 0:            # the reference pads the last batch with zeros (:736-739); drop it instead
-                continue
-            yield [train.shard(x, rank, world).contiguous() for x in (pcA, pcB, lab)]
+            bsize = pcA.shape[0]
+            if cur is None:
+                cur = [torch.zeros((FLAGS.batch_size,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype) for t in (pcA, pcB, lab)]
+            for buf, t in zip(cur, (pcA, pcB, lab)):
+                buf[:bsize] = t
+            yield [train.shard(x, rank, world).contiguous() for x in cur]
         ds.reset()
 
     def eval_one_epoch():
         from . import dpdist_and_aue as MODEL, tf_util
-        tot, cnt = 0.0, 0
+        tot, cnt = torch.zeros((), device=dev), 0
         with torch.no_grad():
             for a, b, l in batches(TEST_DATASET, False):
                 with tf_util.use_store(tr.store):
                     pred, _, _ = MODEL.get_model(a, b, False, **tr.kw)
-                tot += float((pred['pred_listAB'][:, :, 0, 0] - l).abs().mean())           # :840-852 loss_samples
+                tot += (pred['pred_listAB'][:, :, 0, 0] - l).abs().mean()                  # :840-852 loss_samples
                 cnt += 1
-        return tot / max(cnt, 1)
+        t = torch.stack([tot, torch.tensor(float(cnt), device=dev)])
+        if world > 1:       # the towers' losses are averaged (:297), so the figure does not depend on the number of GPUs
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0] / t[1].clamp_min(1.0))
 
     for epoch in range(FLAGS.max_epoch):
         losses = []
@@ -87,6 +97,7 @@ def main(argv=None):
     p.add_argument('--K', default='5')
     p.add_argument('--sigma3dmfv', type=float, default=2.0)
     p.add_argument('--add_noise', type=float, default=0.0)
+    p.add_argument('--BN', default='0', help='1: batch norm after every conv of the head (reference flag, :61,105)')
     p.add_argument('--steps', type=int, default=50, help='training steps to run (synthetic data has no epochs)')
     p.add_argument('--warmup', type=int, default=5)
     p.add_argument('--distinct_batches', type=int, default=4)
@@ -110,7 +121,7 @@ def main(argv=None):
     sigma = FLAGS.sigma3dmfv * 0.0625                                       # :103
     tr = train.DPDistTrainer(dev, base_lr=FLAGS.learning_rate_dpdist, decay_step=FLAGS.decay_step,
                              decay_rate=FLAGS.decay_rate, Embedding_Size=FLAGS.embedding_size, k=int(FLAGS.K),
-                             sigma3dmfv=sigma, seed=1, cuda_graph=bool(FLAGS.cuda_graph))
+                             sigma3dmfv=sigma, seed=1, cuda_graph=bool(FLAGS.cuda_graph), bn=int(FLAGS.BN))
     if FLAGS.data_root:
         return train_on_dataset(FLAGS, tr, dev, rank, world)
     batches = []

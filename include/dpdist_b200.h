@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DPD_ABI_VERSION 2
+#define DPD_ABI_VERSION 3
 #define DPD_MAX_GRID 16
 #define DPD_FV_CHANNELS_FULL 20
 #define DPD_FV_CHANNELS_SMALL 7
@@ -194,6 +194,38 @@ int dpd_adam_step_dev(float* d_param, const float* d_grad, float* d_m, float* d_
  * d_scratch >= 8*(M*K + N*K) + 256 bytes.                                                      */
 int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
                       float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream);
+
+/* ---- layer-by-layer fp32 path for training-mode batch norm (--BN 1) --------------------------------------------------
+ * Replaces, for `bn` truthy and is_training True, what utils/tf_util.py:213-227 builds per conv layer: conv2d + bias_add
+ * (dpd_layer_forward), tf.contrib.layers.batch_norm with batch statistics (utils/tf_util.py:558-577; dpd_bn_forward) and
+ * the activation, plus the gradient graph over them (dpd_bn_backward, dpd_layer_backward).  Batch statistics need a whole
+ * layer's pre-activations before it can be normalised, so this configuration cannot use the fused head; it is off at the
+ * reference defaults (train_multi_gpu_pc_compare_dist.py:61,105).  All arrays fp32, row-major, device memory.
+ *
+ * dpd_layer_forward:  z[rows,N] = x[rows,K] . w[K,N] + b[N].
+ *   d_fv != NULL selects the gathered layer 1: x is virtual, row r = [patch_k(fv[cloud(r)], idx[r]) | offset[r] | 0 pad],
+ *   cloud(r) = r / n_query, and w must be packed the same way (patch rows, 3 offset rows, zero rows; K = rows of w, a
+ *   multiple of 16, >= k^3*C + 3); d_x is ignored.  N <= 4 (the output layer) uses a narrow kernel, otherwise N % 4 == 0
+ *   and K % 16 == 0.
+ * dpd_layer_backward: gw[K',N] = x^T . dz, gb[N] = column sums of dz, dx[rows,K] = dz . w^T (d_dx may be NULL; not
+ *   available for the gathered layer).  For the gathered layer gw is returned in the REFERENCE row order (offset first,
+ *   utils/dpdist_util.py:455) with K' = k^3*C + 3 rows.  Needs N % 128 == 0 unless N <= 4.
+ * dpd_bn_forward:  mean[c], var[c] (biased) over the rows, y = act(gamma * (z - mean) * rsqrt(var + eps) + beta),
+ *   act 0 = none, 1 = relu.  Two-pass statistics, fixed-order reductions (deterministic).
+ * dpd_bn_backward: dz, dgamma, dbeta from dy (the gradient w.r.t. y; the activation's gate is re-derived from z).
+ * Workspace for all four: dpd_layer_workspace_bytes(rows, K, N) bytes (use the layer's K and N; K = N for the bn calls). */
+size_t dpd_layer_workspace_bytes(int rows, int K, int N);
+int dpd_layer_forward(const float* d_x, int rows, int K, const float* d_w, const float* d_b, int N, float* d_z,
+                      const float* d_fv, const int32_t* d_idx, const float* d_offset, int n_query, int G, int C, int k,
+                      void* stream);
+int dpd_layer_backward(const float* d_x, int rows, int K, const float* d_w, int N, const float* d_dz, float* d_gw,
+                       float* d_gb, float* d_dx, const float* d_fv, const int32_t* d_idx, const float* d_offset,
+                       int n_query, int G, int C, int k, void* d_workspace, size_t workspace_bytes, void* stream);
+int dpd_bn_forward(const float* d_z, int rows, int N, const float* d_gamma, const float* d_beta, float eps, int act,
+                   float* d_y, float* d_mean, float* d_var, void* d_workspace, size_t workspace_bytes, void* stream);
+int dpd_bn_backward(const float* d_z, const float* d_dy, int rows, int N, const float* d_gamma, const float* d_beta,
+                    const float* d_mean, const float* d_var, float eps, int act, float* d_dz, float* d_dgamma,
+                    float* d_dbeta, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Ground-truth distances of the dataset generator: replaces scipy cdist(point_set, neg_set).min(0)
  * (dataset_sample_with_gt.py:87-91, 116-117), brute force in fp32 on d^2 = dx^2 + dy^2 + dz^2 (no |a|^2+|b|^2-2ab).

@@ -312,8 +312,23 @@ def bn_inference_variables(seed=2, mlp=(1024, 1024, 1024), dtype=torch.float32):
     return out
 
 
-def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, output_act="relu", bn=False):
-    """utils/dpdist_util.py:412-544,688-700, conv_version 1, k>0, bn off.
+BN_TRAINING = True   # bn="train" is implemented (tests/test_tf_golden.py looks at this)
+
+
+def get_bn_decay(batch, decay_step=300 * 512):
+    """train_multi_gpu_pc_compare_dist.py:172-175, 992-1000: min(0.99, 1 - 0.5 * 0.5^floor(batch / DECAY_STEP))."""
+    return min(0.99, 1.0 - 0.5 * 0.5 ** (int(batch) // int(decay_step)))
+
+
+def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, output_act="relu", bn=False, bn_decay=None,
+           bn_updates=None):
+    """utils/dpdist_util.py:412-544,688-700, conv_version 1, k>0.
+
+    bn False: no batch norm (the reference default, --BN 0).  bn True: inference-mode batch norm (moving statistics).
+    bn "train": training-mode batch norm -- tf.contrib.layers.batch_norm(is_training=True, decay=bn_decay,
+    updates_collections=None), utils/tf_util.py:558-577 [TF-semantics: the fused implementation normalises with the biased
+    batch variance and feeds the moving average with the unbiased one; epsilon 0.001]; the new moving statistics are
+    returned through the dict `bn_updates` ({variable name: tensor}) instead of being assigned in place.
 
     embedding / embeddingB are the [B,V,k^3*20] patch tensors from local_z.
     Returns [pred_AB, pred_BA], each [B,NP,1,3]."""
@@ -325,7 +340,19 @@ def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, outpu
     for i, scope in enumerate(MLP_SCOPES):                                       # :516-544
         x = conv2d_1xw(x, variables[VAR_PREFIX + scope + "/weights"],
                        variables[VAR_PREFIX + scope + "/biases"], relu=(i < 3) and not bn)
-        if bn:   # inference-mode batch norm between bias_add and the activation (utils/tf_util.py:219-227)
+        if bn == "train":   # batch statistics over every row of the tower (moments over axes [0,1,2] of NHWC)
+            p = VAR_PREFIX + scope + "/bn/"
+            n = x.shape[0] * x.shape[1]
+            mean = x.mean(dim=(0, 1))
+            var = ((x - mean) ** 2).mean(dim=(0, 1))
+            x = (x - mean) * torch.rsqrt(var + BN_EPSILON) * variables[p + "gamma"] + variables[p + "beta"]
+            if bn_updates is not None:
+                d = 0.9 if bn_decay is None else bn_decay                        # utils/tf_util.py:569
+                bn_updates[p + "moving_mean"] = (d * variables[p + "moving_mean"] + (1 - d) * mean).detach()
+                bn_updates[p + "moving_variance"] = (d * variables[p + "moving_variance"] + (1 - d) * var * (n / max(n - 1, 1))).detach()
+            if i < 3:
+                x = torch.relu(x)
+        elif bn:   # inference-mode batch norm between bias_add and the activation (utils/tf_util.py:219-227)
             p = VAR_PREFIX + scope + "/bn/"
             x = (x - variables[p + "moving_mean"]) * torch.rsqrt(variables[p + "moving_variance"] + BN_EPSILON) \
                 * variables[p + "gamma"] + variables[p + "beta"]
@@ -350,7 +377,8 @@ def get_loss(pred_set, end_points, labels, loss_type="l1_dist"):
     return loss, loss_pred
 
 
-def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3dmfv=0.125, add_noise=0, bn=False):
+def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3dmfv=0.125, add_noise=0, bn=False,
+              bn_decay=None, bn_updates=None):
     """models/dpdist_and_aue.py:31-86 (3dmfv encoder, k>0, conv_version 1)."""
     pcA_noise = pcA + add_noise                                                  # :45
     embedding_A = get_3dmfv(pcA_noise, n_gaussians=Embedding_Size, flatten=False,
@@ -361,7 +389,7 @@ def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3
     embedding_A, C = local_z(embedding_A, k=k)                                   # :64
     embedding_B, _ = local_z(embedding_B, k=k)                                   # :65
     C = C.to(pcA.dtype)
-    net = DPDist(pcA, pcB, embedding_A, embedding_B, C, variables, bn=bn)        # :69-75
+    net = DPDist(pcA, pcB, embedding_A, embedding_B, C, variables, bn=bn, bn_decay=bn_decay, bn_updates=bn_updates)   # :69-75
     pred_set = {"pred_listAB": net[0], "pred_listBA": net[1]}                    # :80-81
     embedding_set = {"embedding_A": embedding_A, "embedding_B": embedding_B}
     return pred_set, {"fvA": fvA, "fvB": fvB, "C": C}, embedding_set

@@ -27,7 +27,7 @@ def test_header_symbols_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), "libdpdist_b200.so does not export %s" % name
     assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and include/dpdist_b200.h disagree"
-    assert lib.dpd_version() == 2     # DPD_ABI_VERSION
+    assert lib.dpd_version() == _lib.ABI_VERSION == 3     # DPD_ABI_VERSION
 
 
 def test_header_cites_reference_lines():

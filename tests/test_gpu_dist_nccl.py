@@ -37,11 +37,14 @@ def _worker(rank, world, port, out_dir, pairs, graph):
     os.environ["MASTER_PORT"] = str(port)
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=120))
     tr, losses = _steps(dev, rank, world, pairs, graph)
     ok = tr.ranks_consistent()
     torch.save({"w": {n: v.detach().cpu() for n, v in tr.store.vars.items()}, "losses": losses, "consistent": ok,
                 "graph": tr._graph is not None}, os.path.join(out_dir, "r%d.pt" % rank))
+    tr.close()                       # captured NCCL kernels must be released before the communicator goes away
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -52,7 +55,14 @@ def test_two_rank_nccl_step_equals_single_gpu_full_batch_step(tmp_path, pairs, g
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path), pairs, graph), nprocs=2, join=True)
+    ctx = mp.spawn(_worker, args=(2, port, str(tmp_path), pairs, graph), nprocs=2, join=False)
+    import time
+    deadline = time.time() + 240
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("the two NCCL ranks did not finish within 240 s")
     r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
     assert r0["consistent"] and r1["consistent"] and r0["graph"] == graph
     tr, losses = _steps(torch.device("cuda", 0), 0, 1, pairs, graph)
@@ -67,6 +77,6 @@ def test_two_rank_nccl_step_equals_single_gpu_full_batch_step(tmp_path, pairs, g
         # after a few Adam steps every weight has moved by ~steps*lr; a different summation order of the same mean
         # gradient can flip the sign of near-zero gradient entries, so compare against the size of the move
         moved = len(losses) * 1e-4
-        bad = ((w0 - full).abs() > 0.05 * moved + 2e-4 * scale * 0).double().mean()
+        bad = ((w0 - full).abs() > 0.05 * moved).double().mean()
         assert float(bad) < 2e-3, (n, float(bad))
         assert float((w0 - full).abs().max()) <= 2.5 * moved, n

@@ -202,3 +202,57 @@ def test_anchor_gradients_match_the_golden_fixture():
     assert np.abs(w4 - z["grad_w4"]).max() <= 2e-4 * np.abs(z["grad_w4"]).max()
     b1 = store.vars[O.VAR_PREFIX + "mapper_conv1/biases"].grad.cpu().numpy()
     assert np.abs(b1 - z["grad_b1"]).max() <= 2e-4 * np.abs(z["grad_b1"]).max()
+
+
+# ------------------------------------------------------------------ loss-level effect of the ill-conditioned entries
+def test_fv_gradient_directional_derivatives_match_fp64():
+    """The entry-wise check above lets 5 % of the unconditioned entries miss the tight tolerance (the 0.5/sqrt|x|
+    amplification of the signed square root).  What a consumer's optimizer sees is the gradient as a linear functional:
+    for random directions d the directional derivative <g, d> of the CUDA gradient must agree with the fp64 oracle's to
+    5e-4 of |g| |d| (measured on B200: 2.6e-4; the fp32 CPU oracle is at 1e-5 .. 5e-5 on the same inputs), i.e. the
+    loose entries carry no weight."""
+    rng = np.random.default_rng(864)
+    G, N, sigma, V = 8, 64, 0.125, 512
+    pts = rng.uniform(-0.85, 0.85, size=(3, N, 3)).astype(np.float32)
+    gup = rng.normal(size=(3, V, 20)).astype(np.float32)
+    want = _oracle_fv_grad(pts, gup, V, sigma, True, False)
+    x = torch.tensor(pts, device=DEV, requires_grad=True)
+    fv = dpdist_util.get_3dmfv_tf(x, n_gaussians=V, sigma=sigma, flatten=False)
+    (fv * torch.tensor(gup, device=DEV)).sum().backward()
+    err = x.grad.double().cpu().numpy() - want
+    gn = np.linalg.norm(want)
+    worst = 0.0
+    for _ in range(32):
+        d = rng.normal(size=want.shape)
+        worst = max(worst, abs(float((err * d).sum())) / (gn * np.linalg.norm(d)))
+    along = abs(float((err * want).sum())) / (gn * gn)      # along the gradient itself (where a first-order optimizer moves)
+    print("directional derivative error: worst of 32 random directions %.3e, along the gradient %.3e, |err|/|g| %.3e" % (
+        worst, along, np.linalg.norm(err) / gn))
+    assert worst <= 5e-4, worst
+    # Along g itself the ill-conditioned entries do carry weight: on these inputs 5 of the 576 entries hold 60 % of |g|^2
+    # (max |g| 84 against a median of 2), and they are exactly the ones whose statistic nearly cancels.  The fp32 CPU oracle
+    # is 2.5e-4 off its fp64 twin in this direction and 7e-4 in relative L2; measured on B200: 1.3e-3.
+    assert along <= 3e-3, along
+
+
+def test_model_input_gradient_directional_derivatives_match_fp64():
+    """Same functional check through the whole frozen model (3DmFV -> patches -> head -> consumer loss), the gradient
+    PCRNet-ours trains on (iterative_PCRNet_ours.py:229-257)."""
+    pcA, pcB, _ = synthetic.chair_batch(5, 2, 64)
+    var = O.unit_scale_variables(4)
+    a64 = torch.tensor(pcA, dtype=torch.float64, requires_grad=True)
+    p, _, _ = O.get_model(a64, torch.tensor(pcB, dtype=torch.float64), {k: v.double() for k, v in var.items()})
+    ((p["pred_listAB"][..., 0].mean() + p["pred_listBA"][..., 0].mean()) / 2).backward()
+    want = a64.grad.numpy()
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    a = torch.tensor(pcA, device=DEV, requires_grad=True)
+    with tf_util.use_store(store):
+        pred, _, _ = MODEL.get_model(a, torch.tensor(pcB, device=DEV), False, bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+    ((pred["pred_listAB"][..., 0].mean() + pred["pred_listBA"][..., 0].mean()) / 2).backward()
+    err = a.grad.double().cpu().numpy() - want
+    gn = np.linalg.norm(want)
+    assert gn > 0
+    rng = np.random.default_rng(3)
+    worst = max(abs(float((err * d).sum())) / (gn * np.linalg.norm(d)) for d in (rng.normal(size=want.shape) for _ in range(32)))
+    assert worst <= 5e-4, worst

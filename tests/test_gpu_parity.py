@@ -350,12 +350,32 @@ def test_inference_batch_norm_folds_into_the_layers(impl):
         with tf_util.use_store(store):
             p, _, _ = MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), False, bn=1,
                                       Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
-            with pytest.raises(NotImplementedError):
-                MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), True, bn=1,
-                                Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
     finally:
         dpdist_util.HEAD_IMPL = _lib.HEAD_AUTO
     assert_out_close(p["pred_listAB"], want["pred_listAB"], "bn inference AB")
     assert_out_close(p["pred_listBA"], want["pred_listBA"], "bn inference BA")
     names = [n for n in store.names() if "/bn/" in n]
     assert len(names) == 16 and not store.vars[O.VAR_PREFIX + "mapper_conv1/bn/moving_mean"].requires_grad
+
+
+# ------------------------------------------------------------------ points far outside the cube
+def test_fv_far_points_get_the_limit_value_not_nan():
+    """0/0 policy.  The reference evaluates exp() unshifted (utils/dpdist_util.py:69-74): for a point farther than
+    ~13 sigma from every Gaussian all 512 densities underflow, Q = 0/0 = NaN and the whole cloud's FV is NaN (the fp32
+    oracle reproduces that).  The G = 8 kernel shifts every axis by its smallest exponent before exp(), which is the
+    same number wherever the reference is finite and the mathematical limit where it is not: checked against the fp64
+    twin of the oracle, in which nothing underflows at these distances."""
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-0.8, 0.8, size=(4, 64, 3)).astype(np.float32)
+    pts[0, 0] = [3.0, 3.0, 3.0]           # joint underflow in the reference: NaN there
+    pts[1, :3] = [[2.9, 0.1, -0.2], [-3.5, -3.5, 0.0], [0.0, 0.0, 4.5]]
+    pts[2, 5] = [1.9, 1.9, 1.9]           # every axis alone is fine, the product underflows in fp32
+    with O.tf_cpu_numerics():
+        ref32 = O.get_3dmfv(torch.tensor(pts), 512, 0.125, flatten=False)
+    assert not torch.isfinite(ref32[0]).all()                      # the reference's behaviour, for the record
+    got = dpdist_util.get_3dmfv_tf(torch.tensor(pts, device=DEV), n_gaussians=512, sigma=0.125, flatten=False)
+    assert torch.isfinite(got).all()
+    want = O.get_3dmfv(torch.tensor(pts, dtype=torch.float64), 512, 0.125, flatten=False)
+    assert torch.isfinite(want).all()
+    assert_fv_close(got, want, "fv with far points vs the fp64 twin")
+    assert_fv_close(got[3], ref32[3], "an ordinary cloud in the same batch")

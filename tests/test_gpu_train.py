@@ -125,3 +125,122 @@ def test_cuda_graph_step_equals_eager_step():
     assert torch.allclose(res[0][0], res[1][0], rtol=1e-6, atol=1e-7), (res[0][0], res[1][0])
     for n in res[0][1]:
         assert torch.equal(res[0][1][n], res[1][1][n]), n          # same kernels, same order: bit-identical weights
+
+
+def test_bench_size_backward_tensor_core_equals_simt():
+    """The tensor-core backward (fp16x3 products, split-K over the active extent, 9 / 11 slices, fixed-order partial sums)
+    at the bench size -- 1024 pairs = 131072 rows, where it takes different paths than at the 3-4 pair sizes above --
+    against the fp32 SIMT backward of the same step: every gradient within 3e-5 of its maximum (measured: 1.4e-6 .. 1.4e-5)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tools", "grad_compare.py")
+    with tempfile.TemporaryDirectory() as d:
+        for flag, name in (("1", "tc.pt"), ("0", "simt.pt")):      # DPD_TC_BWD is read once per process
+            env = dict(os.environ, DPD_TC_BWD=flag)
+            subprocess.run([sys.executable, script, os.path.join(d, name)], check=True, env=env, timeout=600)
+        a, b = torch.load(os.path.join(d, "tc.pt")), torch.load(os.path.join(d, "simt.pt"))
+    assert sorted(a) == sorted(b) and len(a) == 8
+    for n in sorted(a):
+        scale = float(b[n].abs().max())
+        assert scale > 0, n
+        dev = float((a[n].double() - b[n].double()).abs().max())
+        assert dev <= 3e-5 * scale, "%s: %.3e of max" % (n, dev / scale)
+
+
+# ------------------------------------------------------------------ training-mode batch norm (--BN 1, SURVEY 8 a13)
+def _bn_variables(seed):
+    var = O.unit_scale_variables(seed)
+    bnv = O.bn_inference_variables(seed + 1)
+    for k in list(bnv):
+        if k.endswith("moving_mean"):
+            bnv[k] = torch.zeros_like(bnv[k])                   # fresh moving statistics, as tf.contrib initialises them
+        if k.endswith("moving_variance"):
+            bnv[k] = torch.ones_like(bnv[k])
+    var.update(bnv)
+    return var
+
+
+@pytest.mark.parametrize("B", [3, 2])
+def test_training_mode_batch_norm_matches_the_oracle(B):
+    """Forward (batch statistics), moving-average updates with bn_decay, and the gradients of loss_samples w.r.t. all 16
+    trainable variables (conv weights / biases and bn gamma / beta) against autograd through the oracle's restatement of
+    tf.contrib.layers.batch_norm(is_training=True) (utils/tf_util.py:558-577)."""
+    pcA, pcB, labels = synthetic.uniform_batch(50 + B, B, 64, outside_frac=0.05)
+    labels = labels * 3.0
+    var = _bn_variables(13)
+    decay = 0.5
+    v = {k: t.clone().requires_grad_(k.endswith(("weights", "biases", "gamma", "beta"))) for k, t in var.items()}
+    upd = {}
+    with O.tf_cpu_numerics():
+        p, _, _ = O.get_model(torch.tensor(pcA), torch.tensor(pcB), v, bn="train", bn_decay=decay, bn_updates=upd)
+        loss, _ = O.get_loss(p, {}, torch.tensor(labels))
+    loss.backward()
+    store = tf_util.VariableStore(device=DEV)
+    store.load_state_dict(var, strict=False)
+    for n, t in store.vars.items():
+        if "moving_" in n:
+            t.requires_grad_(False)
+    tf_util.clear_collections()
+    with tf_util.use_store(store):
+        pred, ep, _ = MODEL.get_model(torch.tensor(pcA, device=DEV), torch.tensor(pcB, device=DEV), True, bn=1, bn_decay=decay,
+                                      Embedding_Size=512, k=5, sigma3dmfv=0.125, reuse=True)
+        MODEL.get_loss(pred, ep, torch.tensor(labels, device=DEV))
+    lg = tf_util.get_collection("loss_samples")[-1]
+    lg.backward()
+    torch.cuda.synchronize()
+    for key in ("pred_listAB", "pred_listBA"):
+        g, w = pred[key].detach().cpu(), p[key].detach()
+        assert float((g - w).abs().max()) <= 2e-4 * max(1.0, float(w.abs().max())), key       # normalised activations are O(1)
+    assert abs(float(lg) - float(loss)) <= 1e-5 * max(1.0, abs(float(loss)))
+    for n, want in upd.items():                                  # moving statistics after one training-mode evaluation
+        got = store.vars[n].detach().cpu()
+        assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-6, n
+    checked = 0
+    for n, t in v.items():
+        if t.grad is None:
+            continue
+        got = store.vars[n].grad
+        assert got is not None, n
+        scale = float(t.grad.abs().max())
+        err = float((got.cpu() - t.grad).abs().max())
+        # conv biases in front of a batch norm have an exactly-zero gradient (the mean subtraction removes them)
+        assert err <= 5e-4 * scale + 1e-7, "%s: %.3e vs scale %.3e" % (n, err, scale)
+        checked += 1
+    assert checked == 16
+
+
+def test_batch_norm_trainer_steps_and_inference_uses_the_moving_statistics():
+    pcA, pcB, labels = synthetic.uniform_batch(61, 8, 64)
+    a, b, l = (torch.tensor(x, device=DEV) for x in (pcA, pcB, labels * 3.0))
+    tr = train.DPDistTrainer(DEV, seed=3, bn=1)
+    losses = [float(tr.step(a, b, l)) for _ in range(6)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    names = [n for n in tr.store.vars if "/bn/" in n]
+    assert len(names) == 16 and len(tr.flat.params) == 16            # gamma / beta are trained, moving statistics are not
+    mm = tr.store.vars["pc_compare/dpdist_local/mapper_conv2/bn/moving_mean"]
+    assert float(mm.abs().max()) > 0 and not mm.requires_grad
+    with tf_util.use_store(tr.store), torch.no_grad():
+        p_eval, _, _ = MODEL.get_model(a, b, False, **tr.kw)
+        p_eval2, _, _ = MODEL.get_model(a, b, False, **tr.kw)
+    assert torch.isfinite(p_eval["pred_listAB"]).all() and torch.equal(p_eval["pred_listAB"], p_eval2["pred_listAB"])
+
+
+def test_micro_batched_step_equals_the_single_chunk_step():
+    """A tower batch larger than one DPD_HEAD_TRAIN row chunk is split into micro-batches whose gradients are accumulated
+    with weights n_i / n (config E training: N = NP = 512).  Forced here by lowering the row limit: 12 pairs as 5 + 5 + 2
+    must give the weights of the one-chunk step up to fp32 summation order."""
+    pcA, pcB, labels = synthetic.uniform_batch(71, 12, 64)
+    a, b, l = (torch.tensor(x, device=DEV) for x in (pcA, pcB, labels * 3.0))
+    res = []
+    for limit in (train.DPDistTrainer.MAX_ROWS, 5 * 2 * 64):
+        tr = train.DPDistTrainer(DEV, seed=9)
+        tr.MAX_ROWS = limit
+        losses = [float(tr.step(a, b, l)) for _ in range(2)]
+        res.append((losses, {n: v.detach().clone() for n, v in tr.store.vars.items()}))
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-5)
+    for n in res[0][1]:
+        d = (res[0][1][n] - res[1][1][n]).abs()
+        assert float((d > 1e-5).double().mean()) < 1e-3 and float(d.max()) <= 4.1e-4, n      # Adam moves every weight by ~1e-4 per step
