@@ -181,21 +181,22 @@ extern "C" size_t dpd_layer_workspace_bytes(int rows, int K, int N) {
   return 4 * ((wide > narrow ? wide : narrow) + stats + act) + 1024;
 }
 
-extern "C" int dpd_layer_forward(const float* d_x, int rows, int K, const float* d_w, const float* d_b, int N, float* d_z,
+extern "C" int dpd_layer_forward(const float* d_x, int rows, int K, const float* d_w, const float* d_b, int N, int act, float* d_z,
                                  const float* d_fv, const int32_t* d_idx, const float* d_offset, int n_query, int G, int C,
                                  int k, void* stream) {
   using namespace dpd;
   DPD_REQUIRE(d_w && d_b && d_z && rows > 0 && K > 0 && N > 0, DPD_E_INVALID, "dpd_layer_forward: bad arguments");
+  DPD_REQUIRE(act == 0 || act == 1, DPD_E_INVALID, "dpd_layer_forward: act must be 0 (none) or 1 (relu)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool gather = d_fv != nullptr;
   if (!gather && N <= NARROW_MAX) {
-    DPD_REQUIRE(d_x != nullptr, DPD_E_INVALID, "dpd_layer_forward: null input");
+    DPD_REQUIRE(d_x != nullptr && act == 0, DPD_E_INVALID, "dpd_layer_forward: the narrow layer has no input or asks for an activation");
     DPD_LAUNCH("layer_narrow_fwd", st, narrow_forward_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(d_x, rows, K, d_w, d_b, N, d_z));
     DPD_CUDA_CHECK_LAUNCH("narrow_forward_kernel");
     return 0;
   }
   SimtGemmParams p;
-  p.A = d_x; p.lda = K; p.B = d_w; p.bias = d_b; p.Cout = d_z; p.M = rows; p.N = N; p.Kp = K; p.relu = 0;
+  p.A = d_x; p.lda = K; p.B = d_w; p.bias = d_b; p.Cout = d_z; p.M = rows; p.N = N; p.Kp = K; p.relu = act;
   if (gather) {
     DPD_REQUIRE(d_idx && d_offset && n_query > 0 && G >= 2 && G <= DPD_MAX_GRID && C > 0 && k > 0, DPD_E_INVALID,
                 "dpd_layer_forward: bad gather description");
@@ -252,12 +253,83 @@ extern "C" int dpd_layer_backward(const float* d_x, int rows, int K, const float
   // (offset | patch) order here
   if ((rc = launch_reduce_partials(part, part_bias, K, gather ? tp.g.E + 3 : K, N, gather ? tp.g.E : 0, gather ? 1 : 0, d_gw, d_gb, st))) return rc;
   if (d_dx) {
-    DPD_REQUIRE(!gather, DPD_E_UNSUPPORTED, "dpd_layer_backward: no input gradient for the gathered layer");
     if ((rc = launch_transpose(d_w, K, N, wt, st))) return rc;
     SimtGemmParams gp;
     gp.A = d_dz; gp.lda = N; gp.B = wt; gp.bias = nullptr; gp.Cout = d_dx; gp.M = rows; gp.N = K; gp.Kp = N; gp.relu = 0;
-    if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+    if (!gather) return launch_simt_gemm(gp, false, st);
+    // gathered layer: d_dx is the gradient w.r.t. fv [rows / n_query, G^3, C].  Per group of clouds, dx1 = dz . w^T holds the
+    // gradient of the virtual rows [patch | offset | pad]; patch_scatter_kernel gathers, for every voxel, the patch parts
+    // of the queries whose neighbourhood contains it (fixed order: deterministic).  The offset part is dropped.
+    DPD_REQUIRE(rows % n_query == 0, DPD_E_INVALID, "dpd_layer_backward: rows must be whole clouds");
+    const int n_clouds = rows / n_query;
+    const size_t used = (size_t)((char*)(active + rows / 128 + 2) - (char*)d_workspace);
+    const size_t used_al = round_up<size_t>(used, 256);
+    DPD_REQUIRE(workspace_bytes > used_al, DPD_E_WORKSPACE, "dpd_layer_backward: workspace too small for the input gradient");
+    float* gq = (float*)((char*)d_workspace + used_al);                 // [rows, 3] offset gradients (not returned)
+    const size_t gq_bytes = round_up<size_t>((size_t)rows * 3 * 4, 256);
+    DPD_REQUIRE(workspace_bytes > used_al + gq_bytes, DPD_E_WORKSPACE, "dpd_layer_backward: workspace too small for the input gradient");
+    float* dx1 = (float*)((char*)gq + gq_bytes);
+    const size_t avail = workspace_bytes - used_al - gq_bytes;
+    size_t group = avail / ((size_t)n_query * K * 4);
+    DPD_REQUIRE(group >= 1, DPD_E_WORKSPACE, "dpd_layer_backward: workspace too small for one cloud of input gradients (%zu bytes)",
+                (size_t)n_query * K * 4);
+    if (group > (size_t)n_clouds) group = n_clouds;
+    // groups must start on a 128-row boundary of `active` only in the sense that active is all ones here
+    for (int c0 = 0; c0 < n_clouds; c0 += (int)group) {
+      const int nc = (int)((size_t)(n_clouds - c0) < group ? (size_t)(n_clouds - c0) : group);
+      gp.A = d_dz + (size_t)c0 * n_query * N; gp.Cout = dx1; gp.M = nc * n_query;
+      if ((rc = launch_simt_gemm(gp, false, st))) return rc;
+      if ((rc = launch_patch_scatter(dx1, K, d_idx, active, c0, nc, n_query, G, C, k, d_dx, gq, st))) return rc;
+    }
   }
+  return 0;
+}
+
+namespace dpd {
+namespace {
+__global__ void relu_backward_kernel(float* __restrict__ dy, const float* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(y[i] > 0.f)) dy[i] = 0.f;
+}
+// out[r, :] = [offset[r] (3) | patch_k(fv[cloud(r)], idx[r]) (E)]: the row get_emb_and_concat builds (utils/dpdist_util.py:455)
+__global__ void gather_rows_kernel(GatherDesc g, int rows, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  const RowInfo ri = make_row_info(g, r, rows);
+  float* o = out + (size_t)r * (g.E + 3);
+  for (int e = threadIdx.x; e < g.E + 3; e += blockDim.x)
+    o[e] = e < 3 ? ri.off[e] : gather_elem(g, ri, e - 3);
+}
+}  // namespace
+}  // namespace dpd
+
+extern "C" int dpd_relu_backward(float* d_dy, const float* d_y, size_t n, void* stream) {
+  using namespace dpd;
+  DPD_REQUIRE(d_dy && d_y, DPD_E_INVALID, "dpd_relu_backward: null pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DPD_LAUNCH("relu_backward", st, relu_backward_kernel<<<(unsigned)ceil_div<size_t>(n, 256), 256, 0, st>>>(d_dy, d_y, n));
+  DPD_CUDA_CHECK_LAUNCH("relu_backward_kernel");
+  return 0;
+}
+
+extern "C" int dpd_add_inplace(float* d_a, const float* d_b, size_t n, void* stream) {
+  using namespace dpd;
+  DPD_REQUIRE(d_a && d_b && n % 4 == 0 && aligned16(d_a) && aligned16(d_b), DPD_E_INVALID, "dpd_add_inplace: needs 16-byte aligned arrays, n %% 4 == 0");
+  if (n == 0) return 0;
+  return launch_add_inplace(d_a, d_b, n, (cudaStream_t)stream);
+}
+
+extern "C" int dpd_gather_rows(const float* d_fv, const int32_t* d_idx, const float* d_offset, int rows, int n_query, int G, int C,
+                               int k, float* d_out, void* stream) {
+  using namespace dpd;
+  DPD_REQUIRE(d_fv && d_idx && d_offset && d_out && rows > 0 && n_query > 0 && G >= 2 && G <= DPD_MAX_GRID && C > 0 && k > 0,
+              DPD_E_INVALID, "dpd_gather_rows: bad arguments");
+  GatherDesc g;
+  g.fv = d_fv; g.idx = d_idx; g.offset = d_offset; g.row0 = 0; g.n_query = n_query; g.G = G; g.C = C; g.k = k; g.E = k * k * k * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  DPD_LAUNCH("gather_rows", st, gather_rows_kernel<<<rows, 256, 0, st>>>(g, rows, d_out));
+  DPD_CUDA_CHECK_LAUNCH("gather_rows_kernel");
   return 0;
 }
 

@@ -308,9 +308,11 @@ __global__ void merge_f16_kernel(const __half* __restrict__ hi, const __half* __
 }
 
 // output layer finish for the fused layer-3/4 kernel: sums the per-(N-tile, half) partial dot products in
-// fixed order, adds b4, relu6(x)/3 and the in-cube mask (utils/dpdist_util.py:690-691, 697-698)
+// fixed order, adds b4, relu6(x)/3 and the in-cube mask (utils/dpdist_util.py:690-691, 697-698).  With `perm` the GEMM
+// rows were visited in class-sorted order: row r of part4 belongs to query perm[r].
 __global__ void head_out_finish_kernel(const float4* __restrict__ part4, int nslots, const float* __restrict__ b4,
-                                       const float* __restrict__ mask, float* __restrict__ out, int M) {
+                                       const float* __restrict__ mask, float* __restrict__ out, int M,
+                                       const int32_t* __restrict__ perm) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -318,10 +320,101 @@ __global__ void head_out_finish_kernel(const float4* __restrict__ part4, int nsl
     const float4 v = part4[(size_t)row * nslots + i];
     s0 += v.x; s1 += v.y; s2 += v.z;
   }
-  const float m = mask[row];
-  out[(size_t)row * 3 + 0] = fminf(fmaxf(s0 + b4[0], 0.f), 6.f) / 3.0f * m;
-  out[(size_t)row * 3 + 1] = fminf(fmaxf(s1 + b4[1], 0.f), 6.f) / 3.0f * m;
-  out[(size_t)row * 3 + 2] = fminf(fmaxf(s2 + b4[2], 0.f), 6.f) / 3.0f * m;
+  const int orow = perm ? perm[row] : row;
+  const float m = mask[orow];
+  out[(size_t)orow * 3 + 0] = fminf(fmaxf(s0 + b4[0], 0.f), 6.f) / 3.0f * m;
+  out[(size_t)orow * 3 + 1] = fminf(fmaxf(s1 + b4[1], 0.f), 6.f) / 3.0f * m;
+  out[(size_t)orow * 3 + 2] = fminf(fmaxf(s2 + b4[2], 0.f), 6.f) / 3.0f * m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// structurally-zero K-blocks of layer 1 (inference)
+// ---------------------------------------------------------------------------------------------
+// extract_volume_patches pads with zeros (utils/dpdist_util.py:922-924, 932-957): for a query whose voxel has
+// i0 < pb the a0 slabs 0 .. pb-i0-1 of its patch are zero, for i0 > G-1-(k-1-pb) the last i0+(k-1-pb)-(G-1) are.  The
+// operand's K order is a0-major, so those are a prefix / suffix of the patch part of the row.  Class of a row =
+// pb - (zero prefix slabs) + (zero suffix slabs), in [0, 2 pb'] : sorted ascending, the zero prefix shrinks and the zero
+// suffix grows along the rows, and a 256-row tile can skip the K-blocks that are zero for its first / last row's class.
+__device__ __forceinline__ void slab_zeros(int i0, int G, int k, int* pre, int* suf) {
+  const int pb = (k - 1) >> 1;
+  *pre = max(0, pb - i0);
+  *suf = max(0, i0 + (k - 1 - pb) - (G - 1));
+}
+constexpr int SORT_THREADS = 1024, SORT_MAX_CLASSES = 2 * DPD_MAX_GRID + 1;
+
+__device__ __forceinline__ int row_class(const int32_t* idx, int r, int rows, int G, int k, int mid) {
+  if (r >= rows) return -1;
+  int pre, suf;
+  slab_zeros(idx[r] / (G * G), G, k, &pre, &suf);
+  return mid - pre + suf;
+}
+
+// Stable counting sort of the rows by class in three small launches: per-block class counts, a scan over
+// (class major, block minor), and a scatter whose in-block ranks come from warp ballots (thread order = row order).
+__global__ void __launch_bounds__(SORT_THREADS) class_count_kernel(const int32_t* __restrict__ idx, int rows, int G, int k, int ncls,
+                                                                  int* __restrict__ hist) {
+  const int r = blockIdx.x * SORT_THREADS + threadIdx.x;
+  const int c = row_class(idx, r, rows, G, k, ncls / 2);
+  for (int j = 0; j < ncls; ++j) {
+    const int n = __syncthreads_count(c == j);
+    if (threadIdx.x == 0) hist[j * gridDim.x + blockIdx.x] = n;
+  }
+}
+__global__ void class_scan_kernel(int* __restrict__ hist, int n) {      // exclusive scan in place, n = ncls * blocks (small)
+  __shared__ int part[SORT_THREADS];
+  const int t = threadIdx.x, per = (n + SORT_THREADS - 1) / SORT_THREADS;
+  const int lo = min(n, t * per), hi = min(n, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += hist[i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) { int run = 0; for (int i = 0; i < SORT_THREADS; ++i) { const int v = part[i]; part[i] = run; run += v; } }
+  __syncthreads();
+  int run = part[t];
+  for (int i = lo; i < hi; ++i) { const int v = hist[i]; hist[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(SORT_THREADS) class_scatter_kernel(const int32_t* __restrict__ idx, int rows, int G, int k, int ncls,
+                                                                    const int* __restrict__ offs, int32_t* __restrict__ perm) {
+  __shared__ int warp_cnt[SORT_MAX_CLASSES][32];
+  const int r = blockIdx.x * SORT_THREADS + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = row_class(idx, r, rows, G, k, ncls / 2);
+  int my_rank = 0;
+  for (int j = 0; j < ncls; ++j) {
+    const unsigned m = __ballot_sync(0xffffffffu, c == j);
+    if (c == j) my_rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[j][warp] = __popc(m);
+  }
+  __syncthreads();
+  if (c >= 0) {
+    int base = offs[c * gridDim.x + blockIdx.x];
+    for (int w = 0; w < warp; ++w) base += warp_cnt[c][w];
+    perm[base + my_rank] = r;
+  }
+}
+
+// tile_range[t] = {lo, hi, tail_lo, 0}: K-blocks [lo, hi) and [tail_lo, num_kb) can be non-zero for the rows of tile t.
+// One warp per tile: min / max over all of its rows (sorted rows make the ranges tight, any order keeps them correct).
+__global__ void tile_range_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ perm, int rows, int G, int k, int C,
+                                  int num_kb, int4* __restrict__ tile_range) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (rows + 2 * BM - 1) / (2 * BM);
+  if (t >= ntiles) return;
+  const int slab = k * k * C, E = k * slab;
+  const int tail_lo = min(E / 64, num_kb);                       // the block that holds the end of the patch and the offsets
+  int lo = tail_lo, hi = 0;
+  for (int r = t * 2 * BM + lane; r < min(rows, (t + 1) * 2 * BM); r += 32) {
+    int pre, suf;
+    slab_zeros(idx[perm[r]] / (G * G), G, k, &pre, &suf);
+    lo = min(lo, (pre * slab) / 64);
+    hi = max(hi, (E - suf * slab + 63) / 64);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  hi = max(lo, min(hi, tail_lo));
+  if (lane == 0) tile_range[t] = make_int4(lo, hi, tail_lo, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -400,6 +493,12 @@ static bool gather_ldg() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DPD_TC_GATHER_LDG"); v = e ? (atoi(e) != 0) : 0; }
   return v != 0;
+}
+
+// DPD_TC_ZSKIP=0 visits every K-block of layer 1 (no row classes; A/B measurements)
+static bool zskip_env() {      // read per call: tools/ab_env.py alternates it inside one process
+  const char* e = getenv("DPD_TC_ZSKIP");
+  return e ? (atoi(e) != 0) : true;
 }
 
 // DPD_TC_FUSE_L4=0 keeps the separate output-layer kernel (A/B measurements)
@@ -686,6 +785,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
     int Mo;       // rows of the weight gradient in kernel order
     if (layer == 1) {
       tc::GatherArgs ga;
+      ga.perm = nullptr; ga.tile_range = nullptr;
       ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g->idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g->row0;
       ga.n_query = g->n_query; ga.G = g->G; ga.C = g->C; ga.k = g->k; ga.E = g->E;
       // the gather warps of the GEMM kernel assemble the MN-major A tiles on the fly: nothing is materialised
@@ -820,6 +920,7 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
   const int H = c.H, Kp1 = kp1_of(c, f16);
   const float* sc = (const float*)(ws + w.scales);
   tc::GatherArgs ga;
+  ga.perm = nullptr; ga.tile_range = nullptr;
   ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g.idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g.row0;
   ga.n_query = g.n_query; ga.G = g.G; ga.C = g.C; ga.k = g.k; ga.E = g.E;
   float* out3 = h3_out ? h3_out : ha;
@@ -835,13 +936,33 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
     DPD_LAUNCH("tc_split_off", st, tc::split_off4_f16_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
         g.offset, mask, rows, sc + tc::S_A1, (__half*)(ws + w.o4h), (__half*)(ws + w.o4l)));
     DPD_CUDA_CHECK_LAUNCH("split_off4_f16_kernel");
+    // Inference with the fused output layer: rows sorted by the boundary class of their voxel so that whole tiles can skip
+    // the structurally-zero K-blocks of layer 1; the permutation is undone by head_out_finish_kernel.  `hb` is not used by
+    // this path and holds perm [rows] and tile_range.
+    const bool fused = fused_out != nullptr && tc::use_2cta() && tc::fuse_l4();
+    const int32_t* perm = nullptr;
+    if (fused && !tc_train(c) && tc::zskip_env() && rows >= 2048 && g.k >= 3 && (g.k * g.k * g.C) % 4 == 0) {
+      int32_t* pm = (int32_t*)hb;
+      int4* tr = (int4*)(hb + round_up<size_t>((size_t)rows, 256));
+      const int pbk = (g.k - 1) >> 1, ncls = 2 * (g.k - 1 - pbk > pbk ? g.k - 1 - pbk : pbk) + 1;
+      const int nsb = ceil_div(rows, tc::SORT_THREADS);
+      int* hist = (int*)(tr + ceil_div(rows, 2 * tc::BM) + 1);
+      DPD_LAUNCH("tc_class_sort", st, tc::class_count_kernel<<<nsb, tc::SORT_THREADS, 0, st>>>(g.idx, rows, g.G, g.k, ncls, hist));
+      DPD_LAUNCH("tc_class_sort", st, tc::class_scan_kernel<<<1, tc::SORT_THREADS, 0, st>>>(hist, ncls * nsb));
+      DPD_LAUNCH("tc_class_sort", st, tc::class_scatter_kernel<<<nsb, tc::SORT_THREADS, 0, st>>>(g.idx, rows, g.G, g.k, ncls, hist, pm));
+      const int ntiles = ceil_div(rows, 2 * tc::BM);
+      DPD_LAUNCH("tc_tile_range", st, tc::tile_range_kernel<<<ceil_div(ntiles * 32, 128), 128, 0, st>>>(g.idx, pm, rows, g.G, g.k, g.C, Kp1 / 64, tr));
+      DPD_CUDA_CHECK_LAUNCH("class_sort / tile_range");
+      ga.perm = pm; ga.tile_range = tr;
+      perm = pm;
+    }
     // layer 1: gathered A -> (xh, xl) scaled by sA2; layer 2 -> (yh, yl) scaled by sA3; layer 3 -> fp32
     const bool bits = tc_train(c) && tc::use_2cta();    // ReLU' bit masks for the tensor-core backward
     if ((rc = tc::launch(true, true, nullptr, nullptr, rows, Kp1, blob + b.w1h, blob + b.w1l, H, b1, ws + w.xh, ws + w.xl, 1,
                          sc + tc::S_ACC1, sc + tc::S_A2, &ga, st, bits ? (uint4*)(ws + w.rb1) : nullptr))) return rc;
     if ((rc = tc::launch(false, true, ws + w.xh, ws + w.xl, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.yh, ws + w.yl, 1,
                          sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st, bits ? (uint4*)(ws + w.rb2) : nullptr))) return rc;
-    if (fused_out != nullptr && tc::use_2cta() && tc::fuse_l4()) {
+    if (fused) {
       // layer 3 with the output layer fused into its epilogue.  Inference: H3 never reaches HBM.  Training (h3_out set):
       // the fp32 activations are stored as well, for the backward pass.  `ha` (not read by this path; the SIMT backward
       // refills it later) holds the [rows, 2*H/256] float4 partials.
@@ -850,7 +971,7 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
       if ((rc = tc::launch2(false, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, h3_out, nullptr, 0,
                             sc + tc::S_ACC3, nullptr, nullptr, st, w4, part4))) return rc;
       DPD_LAUNCH("head_out_finish", st, tc::head_out_finish_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
-          (const float4*)part4, nslots, b4, mask, fused_out, rows));
+          (const float4*)part4, nslots, b4, mask, fused_out, rows, perm));
       DPD_CUDA_CHECK_LAUNCH("head_out_finish_kernel");
       *h3 = nullptr;
       return 0;

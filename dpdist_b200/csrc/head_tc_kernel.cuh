@@ -27,6 +27,13 @@ struct GatherArgs {
   const void* off4_lo;
   long long row0;          // global row of chunk-local row 0
   int n_query, G, C, k, E;
+  // Optional (2-CTA kernel, K-major operand, inference): rows visited in the order perm[] (sorted by the boundary class of
+  // their voxel along i0, class_sort_kernel) and, per 256-row tile, the K-blocks that can be non-zero for any of its rows:
+  // tile_range[t] = {lo, hi, tail_lo, 0} -> K-blocks [lo, hi) and [tail_lo, num_kb).  SAME padding makes the leading /
+  // trailing a0 slabs of the patch of a voxel near the i0 boundary structurally zero; the MMAs and the gather of those
+  // K-blocks are skipped by every warp role.
+  const int32_t* perm;
+  const int4* tile_range;
 };
 
 struct KernelArgs {

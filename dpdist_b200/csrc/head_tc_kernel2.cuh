@@ -115,6 +115,22 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     return !__ldg(args.active + b0) && !(b0 + 1 < num_row_blocks && __ldg(args.active + b0 + 1));
   };
 
+  // K-blocks an item visits: a main run [lo, lo + n_main) and a tail run [tail_lo, ...), cnt in total.  Forward: all of
+  // them, or (layer 1 with row classes) the tile's non-zero range; backward: the item's K slice.
+  struct Seq { int lo, n_main, tail_lo, cnt; };
+  auto make_seq = [&](int mt, int sl) -> Seq {
+    Seq q;
+    if (GATHER && !args.mn_major && args.g.tile_range != nullptr) {
+      const int4 r = __ldg(args.g.tile_range + mt);
+      q.lo = r.x; q.n_main = r.y - r.x; q.tail_lo = r.z; q.cnt = q.n_main + (args.num_kb - r.z);
+    } else {
+      const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+      q.lo = kb_lo; q.n_main = max(kb_hi - kb_lo, 0); q.tail_lo = 0; q.cnt = q.n_main;
+    }
+    return q;
+  };
+  auto kb_of = [&](const Seq& q, int i) -> int { return i < q.n_main ? q.lo + i : q.tail_lo + (i - q.n_main); };
+
   auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 Ah, 1 Al, 2 Bh (half), 3 Bl (half)
     uint8_t* b = smem + s * STAGE2_BYTES;
     return which == 0 ? b : which == 1 ? b + A_TILE : which == 2 ? b + 2 * A_TILE : b + 2 * A_TILE + B_HALF;
@@ -173,8 +189,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         if (item_skipped(mt)) continue;
         const int row0 = mt * 2 * BM + (int)rank * BM;
         const int brow0 = nt * BN + (int)rank * (BN / 2);
-        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
-        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const Seq q = make_seq(mt, sl);
+        for (int i = 0; i < q.cnt; ++i) {
+          const int kb = kb_of(q, i);
           mbar_wait(&ctl->empty[s], ph ^ 1);
           const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
@@ -208,14 +225,15 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       for (int w = cluster_id; w < num_items; w += num_clusters) {
         const int t = w % num_tiles, sl = w / num_tiles;
         if (item_skipped(t / num_n_tiles)) continue;
-        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
-        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += SEG) {
+        const Seq q = make_seq(t / num_n_tiles, sl);
+        for (int i0 = 0; i0 < q.cnt; i0 += SEG) {
           mbar_wait_cluster(&ctl->seg_empty[sb], sb_ph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
           uint32_t accumulate = 0;
-          const int kb1 = min(kb0 + SEG, kb_hi);
-          for (int kb = kb0; kb < kb1; ++kb) {
+          const int i1 = min(i0 + SEG, q.cnt);
+          for (int i = i0; i < i1; ++i) {
+            const int kb = kb_of(q, i);
             mbar_wait_cluster(&ctl->full[s], ph);
             tc_fence_after();
             const bool mn = args.mn_major != 0;
@@ -249,8 +267,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       for (int w = cluster_id; w < num_items; w += num_clusters) {
         const int t = w % num_tiles, sl = w / num_tiles;
         if (item_skipped(t / num_n_tiles)) continue;
-        const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
-        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const Seq q = make_seq(t / num_n_tiles, sl);
+        for (int i = 0; i < q.cnt; ++i) {
           mbar_wait(&ctl->gfull[s], ph);
           fence_proxy_async();
           mbar_arrive_remote(map_to_rank(smem_u32(&ctl->full[s]), 0));
@@ -273,13 +291,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
       if (item_skipped(mt)) continue;
       const int row_base = mt * 2 * BM + (int)rank * BM;
-      const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+      const Seq sq = make_seq(mt, sl);
       bool first = true;
-      if (kb_lo >= kb_hi) {          // an empty slice (k_limit cut it off) contributes zeros
+      if (sq.cnt == 0) {          // an empty slice (k_limit cut it off) contributes zeros
 #pragma unroll
         for (int j = 0; j < EPI_COLS; ++j) sum[j] = 0.f;
       }
-      for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += SEG) {
+      for (int i0 = 0; i0 < sq.cnt; i0 += SEG) {
         mbar_wait(&ctl->seg_full[sb], sb_ph);
         tc_fence_after();
 #pragma unroll
@@ -551,8 +569,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const int m = row_base + it * 16 + rl;
           rel[it] = -1; rmsk[it] = 0;
           if (m < args.M) {
-            const long long cloud = (g.row0 + m) / g.n_query;
-            const int v = __ldg(g.idx + m);
+            const int mo = g.perm ? __ldg(g.perm + m) : m;
+            const long long cloud = (g.row0 + mo) / g.n_query;
+            const int v = __ldg(g.idx + mo);
             rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
             const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
             uint32_t mk = 0;
@@ -564,7 +583,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             rmsk[it] = mk;
           }
         }
-        for (int kb = 0; kb < args.num_kb; ++kb) {
+        const Seq q = make_seq(mt, 0);
+        for (int qi = 0; qi < q.cnt; ++qi) {
+          const int kb = kb_of(q, qi);
           uint32_t code[2]; int32_t delta[2];
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -586,7 +607,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 sh = fv_hi + el * ELEM; sl = fv_lo + el * ELEM;
               } else {
                 ok = (c == LUT_OFFS) && rel[it] >= 0;
-                const size_t m = ok ? (size_t)row_base + it * 16 + rl : 0;
+                size_t m = ok ? (size_t)row_base + it * 16 + rl : 0;
+                if (ok && g.perm) m = (size_t)__ldg(g.perm + m);
                 sh = o4_hi + m * 4 * ELEM; sl = o4_lo + m * 4 * ELEM;
               }
               vh[it][hf] = make_uint2(0u, 0u); vl[it][hf] = make_uint2(0u, 0u);
@@ -625,8 +647,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int m = row_base + it * ROWS_PER_IT + sub;
         rel[it] = -1; rmsk[it] = 0;
         if (m < args.M) {
-          const long long cloud = (g.row0 + m) / g.n_query;
-          const int v = __ldg(g.idx + m);
+          const int mo = g.perm ? __ldg(g.perm + m) : m;
+          const long long cloud = (g.row0 + mo) / g.n_query;
+          const int v = __ldg(g.idx + mo);
           rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
           const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
           uint32_t mk = 0;
@@ -638,7 +661,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           rmsk[it] = mk;
         }
       }
-      for (int kb = 0; kb < args.num_kb; ++kb) {
+      const Seq q = make_seq(mt, 0);
+      for (int qi = 0; qi < q.cnt; ++qi) {
+        const int kb = kb_of(q, qi);
         mbar_wait(&ctl->empty[s], ph ^ 1);
         const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
         uint32_t code; int32_t delta;
@@ -664,7 +689,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const int r = it * ROWS_PER_IT + sub;
             const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
             const bool ok = (code == LUT_OFFS) && rel[it] >= 0;
-            const size_t m = ok ? (size_t)row_base + r : 0;
+            size_t m = ok ? (size_t)row_base + r : 0;
+            if (ok && g.perm) m = (size_t)__ldg(g.perm + m);
             const uint32_t nbytes = ok ? 4u * ELEM : 0u;
             cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
             cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);

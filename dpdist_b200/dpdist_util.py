@@ -454,8 +454,10 @@ def _as_fv(embedding, k):
 def _check_head_options(k, conv_version, NUM_DIMS, bn, output_act, mlp):
     if k <= 0:
         raise NotImplementedError("k == 0 (global embedding) is not the DPDist hot path")
-    if conv_version != 1:
-        raise NotImplementedError("conv_version %d: only the shared-MLP head (1) is implemented" % conv_version)
+    if conv_version not in (1, 3):
+        raise NotImplementedError("conv_version %d: the shared-MLP head (1) and the 3-D CNN head (3) are implemented" % conv_version)
+    if conv_version == 3 and bn:
+        raise NotImplementedError("conv_version 3 with batch norm is not implemented")
     if NUM_DIMS != 3:
         raise NotImplementedError("NUM_DIMS must be 3")
     if output_act != 'relu':
@@ -547,9 +549,9 @@ class _BnTrainHead(torch.autograd.Function):
                 K, N = wl.shape
                 z = torch.empty((rows, N), device=dev, dtype=torch.float32)
                 if layer == 0:
-                    rc = lib.dpd_layer_forward(None, rows, K, _ptr(wl), _ptr(bl), N, _ptr(z), _ptr(fv), _ptr(idx), _ptr(off), NP, G, Cc, k, st)
+                    rc = lib.dpd_layer_forward(None, rows, K, _ptr(wl), _ptr(bl), N, 0, _ptr(z), _ptr(fv), _ptr(idx), _ptr(off), NP, G, Cc, k, st)
                 else:
-                    rc = lib.dpd_layer_forward(_ptr(x), rows, K, _ptr(wl), _ptr(bl), N, _ptr(z), None, None, None, 0, 0, 0, 0, st)
+                    rc = lib.dpd_layer_forward(_ptr(x), rows, K, _ptr(wl), _ptr(bl), N, 0, _ptr(z), None, None, None, 0, 0, 0, 0, st)
                 _lib.check(rc, "dpd_layer_forward")
                 gamma, beta = affine[2 * layer].detach().contiguous(), affine[2 * layer + 1].detach().contiguous()
                 y = torch.empty_like(z)
@@ -610,6 +612,180 @@ class _BnTrainHead(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+def _cv3_variables(Cc, k, NUM_DIMS, mlp, reuse):
+    """The 16 variables of the conv_version 3 head, scope 'dpdist_local_cnn_fc' (utils/dpdist_util.py:647-687):
+    mapper_conv0 (1x1x1, C -> 64), mapper_conv1_1 / 1_2 / 2_1 / 2_2 (3x3x3, 64 -> 64, the two resnet3d blocks :394-410),
+    mapper_conv3 (1x1x1, 64 -> 16), mapper_conv5 (16 k^3 + 3 -> mlp[2]), mapper_conv6 (-> 3)."""
+    out = []
+    with tf_util.variable_scope('dpdist_local_cnn_fc', reuse=reuse):
+        out += tf_util.conv3d_variables(Cc, 64, [1, 1, 1], 'mapper_conv0', reuse=reuse)
+        for blk in ('mapper_conv1', 'mapper_conv2'):
+            for part in ('_1', '_2'):
+                out += tf_util.conv3d_variables(64, 64, [3, 3, 3], blk + part, reuse=reuse)
+        out += tf_util.conv3d_variables(64, 16, [1, 1, 1], 'mapper_conv3', reuse=reuse)
+        out += tf_util.conv2d_variables(16 * k ** 3 + NUM_DIMS, mlp[2], [1, 1], 'mapper_conv5', reuse=reuse)
+        out += tf_util.conv2d_variables(mlp[2], NUM_DIMS, [1, 1], 'mapper_conv6', reuse=reuse)
+    return out
+
+
+def _pad_cols(t, n):
+    return t if t.shape[1] == n else torch.nn.functional.pad(t, (0, n - t.shape[1]))
+
+
+def _pad_rows(t, n):
+    return t if t.shape[0] == n else torch.nn.functional.pad(t, (0, 0, 0, n - t.shape[0]))
+
+
+class _Cv3Head(torch.autograd.Function):
+    """conv_version 3 head (utils/dpdist_util.py:640-687), the reference's other implicit net (--implicit_net_type 3):
+    per query the row [offset | patch] is cut as the REFERENCE cuts it -- net[:, :, :E] / net[:, :, E:] with the three
+    offsets first (:455), so the "patch volume" is [offset | patch[0:E-3]] reshaped to [k,k,k,C] and the "offset" fed to the
+    FC layer is the last three patch values (:641-642); a drop-in reproduces that.  Then 1x1x1 conv (C -> 64), two residual
+    blocks of two 3x3x3 SAME convs (:394-410), 1x1x1 conv (64 -> 16), flatten, concat, FC (mlp[2]) and the output layer.
+    Every convolution is one fp32 library call: a 3x3x3 SAME conv over a [k,k,k,64] volume is dpd_layer_forward's gathered
+    layer with fv = the volumes, grid k, patch edge 3 (extract_volume_patches semantics, zero padding); 1x1x1 convs and FC
+    are dense layers.  115 MFLOP per query (12 x the default head), SIMT fp32: correct, not fast.
+    Gradients w.r.t. the 16 variables (training); the clouds are data."""
+
+    @staticmethod
+    def forward(ctx, fv, query, tables, k, *weights):
+        lib = _lib.load()
+        fv = _check_cuda(fv.detach(), "fv")
+        query = _check_cuda(query.detach(), "query")
+        n_clouds, V, Cc = fv.shape
+        NP = query.shape[1]
+        rows = n_clouds * NP
+        G, l, lo, hi = tables
+        dev = fv.device
+        k3, E = k ** 3, k ** 3 * Cc
+        M = rows * k3
+        W = [w.detach() for w in weights]
+        H = W[12].shape[-1]
+        st = _stream()
+        idx = torch.empty(rows, device=dev, dtype=torch.int32)
+        mask = torch.empty(rows, device=dev, dtype=torch.float32)
+        off = torch.empty((rows, 3), device=dev, dtype=torch.float32)
+        keep = {}
+
+        def dense(x, w2d, b, act):
+            Kp = -(-w2d.shape[0] // 16) * 16
+            x, w2d = _pad_cols(x, Kp).contiguous(), _pad_rows(w2d, Kp).contiguous()
+            z = torch.empty((x.shape[0], w2d.shape[1]), device=dev, dtype=torch.float32)
+            _lib.check(lib.dpd_layer_forward(_ptr(x), x.shape[0], Kp, _ptr(w2d), _ptr(b.contiguous()), w2d.shape[1], act, _ptr(z),
+                                             None, None, None, 0, 0, 0, 0, st), "dpd_layer_forward")
+            return x, w2d, z
+
+        Kc = -(-(27 * 64 + 3) // 16) * 16
+        idx_c = torch.arange(k3, device=dev, dtype=torch.int32).repeat(rows)
+        off_c = torch.zeros((M, 3), device=dev, dtype=torch.float32)
+
+        def conv(x, w5d, b):
+            wp = _pad_rows(w5d.reshape(27 * 64, 64), Kc).contiguous()
+            z = torch.empty((M, 64), device=dev, dtype=torch.float32)
+            _lib.check(lib.dpd_layer_forward(None, M, Kc, _ptr(wp), _ptr(b.contiguous()), 64, 1, _ptr(z), _ptr(x), _ptr(idx_c),
+                                             _ptr(off_c), k3, k, 64, 3, st), "dpd_layer_forward (conv3d)")
+            return wp, z
+
+        def add(a, b):
+            out = a.clone()
+            _lib.check(lib.dpd_add_inplace(_ptr(out), _ptr(b), out.numel(), st), "dpd_add_inplace")
+            return out
+
+        with torch.cuda.device(dev):
+            _lib.check(lib.dpd_voxel_assign(_ptr(query), 1, rows, G, _lib.fptr(l), _lib.fptr(lo), _lib.fptr(hi), _ptr(idx), _ptr(mask),
+                                            _ptr(off), st), "dpd_voxel_assign")
+            R = torch.empty((rows, E + 3), device=dev, dtype=torch.float32)
+            _lib.check(lib.dpd_gather_rows(_ptr(fv), _ptr(idx), _ptr(off), rows, NP, G, Cc, k, _ptr(R), st), "dpd_gather_rows")
+            x0 = R[:, :E].reshape(M, Cc)                       # :641,644-646  (offset | patch[:E-3]) as [k,k,k,C]
+            netD = R[:, E:E + 3]                               # :642          the last three patch values
+            x0p, w0p, y0 = dense(x0, W[0].reshape(Cc, 64), W[1], 1)
+            w11, a = conv(y0, W[2], W[3])
+            w12, b_ = conv(a, W[4], W[5])
+            r1 = add(b_, y0)
+            w21, c = conv(r1, W[6], W[7])
+            w22, d = conv(c, W[8], W[9])
+            r2 = add(d, r1)
+            _, w3p, y3 = dense(r2, W[10].reshape(64, 16), W[11], 1)
+            f = torch.cat([y3.view(rows, 16 * k3), netD], 1)                        # :671-673
+            fp, w5p, y5 = dense(f, W[12].reshape(16 * k3 + 3, H), W[13], 1)
+            w6 = W[14].reshape(H, 3).contiguous()
+            z6 = torch.empty((rows, 3), device=dev, dtype=torch.float32)
+            _lib.check(lib.dpd_layer_forward(_ptr(y5), rows, H, _ptr(w6), _ptr(W[15].contiguous()), 3, 0, _ptr(z6), None, None, None,
+                                             0, 0, 0, 0, st), "dpd_layer_forward")
+        out = (torch.clamp(z6, 0.0, 6.0) / 3.0 * mask[:, None]).view(n_clouds, NP, 3)          # :690-691, :697-698
+        if any(ctx.needs_input_grad[4:]):
+            ctx.dims = (rows, M, k, k3, Cc, H, Kc)
+            ctx.keep = dict(mask=mask, x0p=x0p, w0p=w0p, y0=y0, a=a, b_=b_, r1=r1, c=c, d=d, r2=r2, y3=y3, fp=fp, w5p=w5p, y5=y5, w6=w6,
+                            z6=z6, w11=w11, w12=w12, w21=w21, w22=w22, w3p=w3p, idx_c=idx_c, off_c=off_c,
+                            shapes=[tuple(w.shape) for w in weights])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        rows, M, k, k3, Cc, H, Kc = ctx.dims
+        K = ctx.keep
+        dev = K["y0"].device
+        st = _stream()
+        extra = 768 << 20          # room for the gathered layers' input gradients (dx1 of a group of volumes)
+        ws_bytes = max(lib.dpd_layer_workspace_bytes(M, Kc, 128), lib.dpd_layer_workspace_bytes(rows, K["fp"].shape[1], H),
+                       lib.dpd_layer_workspace_bytes(M, 64, 128)) + M * 12 + extra
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+
+        def relu_bwd(dy, y):
+            _lib.check(lib.dpd_relu_backward(_ptr(dy), _ptr(y), dy.numel(), st), "dpd_relu_backward")
+            return dy
+
+        def dense_bwd(x, w2d, dz, want_dx):
+            """x [R,K], w2d [K,N], dz [R,N] -> gw [K,N], gb [N], dx [R,K] (N padded to a multiple of 128 for the product)."""
+            R, Kd = x.shape
+            N = w2d.shape[1]
+            Np = N if N <= 4 else -(-N // 128) * 128
+            wq, dzq = _pad_cols(w2d, Np).contiguous(), _pad_cols(dz, Np).contiguous()
+            gw = torch.empty((Kd, Np), device=dev, dtype=torch.float32)
+            gb = torch.empty(Np, device=dev, dtype=torch.float32)
+            dx = torch.empty((R, Kd), device=dev, dtype=torch.float32) if want_dx else None
+            _lib.check(lib.dpd_layer_backward(_ptr(x), R, Kd, _ptr(wq), Np, _ptr(dzq), _ptr(gw), _ptr(gb), _ptr(dx) if want_dx else None,
+                                              None, None, None, 0, 0, 0, 0, _ptr(ws), ws.numel(), st), "dpd_layer_backward")
+            return gw[:, :N], gb[:N], dx
+
+        def conv_bwd(x, wp, dz, want_dx):
+            """3x3x3 conv: x [M,64] volumes, wp [Kc,64] packed, dz [M,64] -> gw [3,3,3,64,64], gb, dx [M,64]."""
+            wq, dzq = _pad_cols(wp, 128).contiguous(), _pad_cols(dz, 128).contiguous()
+            gw = torch.empty((27 * 64 + 3, 128), device=dev, dtype=torch.float32)       # reference row order: 3 offset rows first
+            gb = torch.empty(128, device=dev, dtype=torch.float32)
+            dx = torch.empty((M, 64), device=dev, dtype=torch.float32) if want_dx else None
+            _lib.check(lib.dpd_layer_backward(None, M, Kc, _ptr(wq), 128, _ptr(dzq), _ptr(gw), _ptr(gb), _ptr(dx) if want_dx else None,
+                                              _ptr(x), _ptr(K["idx_c"]), _ptr(K["off_c"]), k3, k, 64, 3, _ptr(ws), ws.numel(), st),
+                       "dpd_layer_backward (conv3d)")
+            return gw[3:, :64].reshape(3, 3, 3, 64, 64), gb[:64], dx
+
+        def add_(a, b):
+            _lib.check(lib.dpd_add_inplace(_ptr(a), _ptr(b), a.numel(), st), "dpd_add_inplace")
+            return a
+
+        with torch.cuda.device(dev):
+            z6 = K["z6"]
+            dz6 = (grad_out.reshape(rows, 3).float() * K["mask"][:, None] * ((z6 > 0) & (z6 < 6)).float() / 3.0).contiguous()
+            g14, g15, dy5 = dense_bwd(K["y5"], K["w6"], dz6, True)
+            g12, g13, df = dense_bwd(K["fp"], K["w5p"], relu_bwd(dy5, K["y5"]), True)
+            dy3 = df[:, :16 * k3].reshape(M, 16).contiguous()
+            g10, g11, dr2 = dense_bwd(K["r2"], K["w3p"][:64], relu_bwd(dy3, K["y3"]), True)
+            dr1 = dr2.clone()                                                    # r2 = d + r1
+            g8, g9, dc = conv_bwd(K["c"], K["w22"], relu_bwd(dr2, K["d"]), True)
+            g6, g7, t = conv_bwd(K["r1"], K["w21"], relu_bwd(dc, K["c"]), True)
+            add_(dr1, t)
+            dy0 = dr1.clone()                                                    # r1 = b_ + y0
+            g4, g5, da = conv_bwd(K["a"], K["w12"], relu_bwd(dr1, K["b_"]), True)
+            g2, g3, t = conv_bwd(K["y0"], K["w11"], relu_bwd(da, K["a"]), True)
+            add_(dy0, t)
+            g0, g1, _ = dense_bwd(K["x0p"], K["w0p"], relu_bwd(dy0, K["y0"]), False)
+        sh = K["shapes"]
+        grads = [g0[:Cc].reshape(sh[0]), g1, g2.reshape(sh[2]), g3, g4.reshape(sh[4]), g5, g6.reshape(sh[6]), g7, g8.reshape(sh[8]), g9,
+                 g10.reshape(sh[10]), g11, g12[:16 * k3 + 3].reshape(sh[12]), g13, g14.reshape(sh[14]), g15]
+        return (None, None, None, None) + tuple(g.contiguous() for g in grads)
+
+
 def model_forward(points, query, n_gaussians, sigma, full_fv, k, mlp, reuse=None, impl=None):
     """One dpd_model_forward call: 3DmFV of `points` [2B,N,3] (rows [A | B]) and the head evaluated at `query`
     [2B,NP,3] (rows [pcB | pcA]) -> (fv [2B,V,C], out [2B,NP,3], C [V,3]).  Inference only (no autograd node);
@@ -665,6 +841,13 @@ def DPDist(point_cloud, point_cloudB, embedding,
     E = fvA.shape[2] * k ** 3
     H = mlp[0]
     training = not (isinstance(is_training, (bool, int)) and not is_training)
+    if conv_version == 3:
+        weights = _cv3_variables(fvA.shape[2], k, NUM_DIMS, mlp, reuse)
+        if not training:
+            weights = [w.detach() for w in weights]
+        out = _Cv3Head.apply(torch.cat([fvA, fvB], 0), torch.cat([pcB, pcA], 0), _assign_tables(C), k, *weights)
+        out = out.view(2, B, NP, 1, 3)
+        return [out[0], out[1]]
     if bn and training:
         # batch statistics (utils/tf_util.py:221-224, 558-577): layer-by-layer fp32 path, _BnTrainHead
         weights, bns = _head_variables(E, NUM_DIMS, mlp, reuse, bn=True)

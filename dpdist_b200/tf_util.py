@@ -151,6 +151,16 @@ def conv2d_variables(num_in_channels, num_output_channels, kernel_size, scope, r
     return kernel, biases
 
 
+def conv3d_variables(num_in_channels, num_output_channels, kernel_size, scope, reuse=None):
+    """The variables `tf_util.conv3d` creates (utils/tf_util.py:344-359): DHWIO `weights`, zero `biases`."""
+    with variable_scope(scope, reuse=reuse):
+        kd, kh, kw = kernel_size
+        kernel = _variable_with_weight_decay("weights", [kd, kh, kw, num_in_channels, num_output_channels],
+                                             stddev=1e-3, wd=0.0, use_xavier=True)
+        biases = _variable_on_cpu("biases", [num_output_channels], constant_initializer(0.0))
+    return kernel, biases
+
+
 BN_EPSILON = 0.001     # TF-semantics: tf.contrib.layers.batch_norm default epsilon (utils/tf_util.py:573-577 passes none)
 
 

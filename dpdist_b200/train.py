@@ -147,13 +147,15 @@ class DPDistTrainer:
 
     def __init__(self, device, base_lr=0.0001, decay_step=300 * 512, decay_rate=0.5, seed=1, store=None,
                  Embedding_Size=512, k=5, sigma3dmfv=0.125, mlp=(1024, 1024, 1024), overlap_allreduce=True,
-                 cuda_graph=False, group=None, bn=0):
+                 cuda_graph=False, group=None, bn=0, conv_version=1):
         self.device = torch.device(device)
         self.store = store if store is not None else tf_util.VariableStore(device=self.device, seed=seed)
         self.base_lr, self.decay_step, self.decay_rate = base_lr, decay_step, decay_rate
         # bn truthy = the reference's --BN 1: batch norm after every conv, batch statistics per tower (not synchronised
         # across towers, utils/tf_util.py:573-577), gamma / beta trained with the other variables, bn_decay of :992-1000
         self.kw = dict(bn=int(bn), Embedding_Size=Embedding_Size, k=k, sigma3dmfv=sigma3dmfv, localSNmlp=list(mlp))
+        if int(conv_version) != 1:          # --implicit_net_type 3: the 3-D CNN head (utils/dpdist_util.py:640-687)
+            self.kw["conv_version"] = int(conv_version)
         self.batch = 0                      # the 'batch' global step variable (:201)
         self.overlap = overlap_allreduce
         self.group = group
@@ -188,11 +190,14 @@ class DPDistTrainer:
         mlp = self.kw["localSNmlp"]
         G, _ = dpdist_util._fv_grid(self.kw["Embedding_Size"], 3)
         with tf_util.use_store(self.store), tf_util.variable_scope('pc_compare'):
+            if self.kw.get("conv_version", 1) == 3:
+                dpdist_util._cv3_variables(dpdist_util.FV_CHANNELS[True], self.kw["k"], 3, mlp, None)
+                return
             dpdist_util._head_variables(dpdist_util.FV_CHANNELS[True] * self.kw["k"] ** 3, 3, mlp, None, bn=bool(self.kw["bn"]))
 
     def _ensure_flat(self):
         named = self._named()
-        if not all(n in named for n in self.HEAD):
+        if not named or (self.kw.get("conv_version", 1) == 1 and not all(n in named for n in self.HEAD)):
             self._create_variables()
             named = self._named()
         f = self.flat
@@ -339,7 +344,7 @@ class DPDistTrainer:
         return gs["loss"].clone()        # the graph's own output buffer is overwritten by the next replay
 
     def step(self, pcA, pcB, labels_AB, add_noise=0):
-        if self.cuda_graph and not self.kw["bn"] and not torch.is_tensor(add_noise) and add_noise == 0:
+        if self.cuda_graph and not self.kw["bn"] and "conv_version" not in self.kw and not torch.is_tensor(add_noise) and add_noise == 0:
             if self._eager_steps >= 3:
                 return self._graph_step(pcA, pcB, labels_AB)
             self._eager_steps += 1

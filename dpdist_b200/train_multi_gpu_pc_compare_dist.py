@@ -97,6 +97,7 @@ def main(argv=None):
     p.add_argument('--K', default='5')
     p.add_argument('--sigma3dmfv', type=float, default=2.0)
     p.add_argument('--add_noise', type=float, default=0.0)
+    p.add_argument('--implicit_net_type', default='1', help='1: shared-MLP head, 3: 3-D CNN head (reference flag, :65,112)')
     p.add_argument('--BN', default='0', help='1: batch norm after every conv of the head (reference flag, :61,105)')
     p.add_argument('--steps', type=int, default=50, help='training steps to run (synthetic data has no epochs)')
     p.add_argument('--warmup', type=int, default=5)
@@ -121,7 +122,8 @@ def main(argv=None):
     sigma = FLAGS.sigma3dmfv * 0.0625                                       # :103
     tr = train.DPDistTrainer(dev, base_lr=FLAGS.learning_rate_dpdist, decay_step=FLAGS.decay_step,
                              decay_rate=FLAGS.decay_rate, Embedding_Size=FLAGS.embedding_size, k=int(FLAGS.K),
-                             sigma3dmfv=sigma, seed=1, cuda_graph=bool(FLAGS.cuda_graph), bn=int(FLAGS.BN))
+                             sigma3dmfv=sigma, seed=1, cuda_graph=bool(FLAGS.cuda_graph), bn=int(FLAGS.BN),
+                             conv_version=int(FLAGS.implicit_net_type))
     if FLAGS.data_root:
         return train_on_dataset(FLAGS, tr, dev, rank, world)
     batches = []

@@ -202,25 +202,36 @@ int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, c
  * layer's pre-activations before it can be normalised, so this configuration cannot use the fused head; it is off at the
  * reference defaults (train_multi_gpu_pc_compare_dist.py:61,105).  All arrays fp32, row-major, device memory.
  *
- * dpd_layer_forward:  z[rows,N] = x[rows,K] . w[K,N] + b[N].
+ * dpd_layer_forward:  z[rows,N] = act(x[rows,K] . w[K,N] + b[N]), act 0 = none, 1 = relu.
  *   d_fv != NULL selects the gathered layer 1: x is virtual, row r = [patch_k(fv[cloud(r)], idx[r]) | offset[r] | 0 pad],
  *   cloud(r) = r / n_query, and w must be packed the same way (patch rows, 3 offset rows, zero rows; K = rows of w, a
  *   multiple of 16, >= k^3*C + 3); d_x is ignored.  N <= 4 (the output layer) uses a narrow kernel, otherwise N % 4 == 0
  *   and K % 16 == 0.
- * dpd_layer_backward: gw[K',N] = x^T . dz, gb[N] = column sums of dz, dx[rows,K] = dz . w^T (d_dx may be NULL; not
- *   available for the gathered layer).  For the gathered layer gw is returned in the REFERENCE row order (offset first,
+ * dpd_layer_backward: gw[K',N] = x^T . dz, gb[N] = column sums of dz, dx[rows,K] = dz . w^T (d_dx may be NULL).  For the
+ *   gathered layer d_dx is the gradient w.r.t. fv, [rows / n_query, G^3, C] (the transpose of the patch gather, without
+ *   atomics); the workspace must then hold, beyond dpd_layer_workspace_bytes, rows*12 bytes and at least one cloud's
+ *   n_query * K * 4 bytes (more = fewer passes).  For the gathered layer gw is returned in the REFERENCE row order (offset first,
  *   utils/dpdist_util.py:455) with K' = k^3*C + 3 rows.  Needs N % 128 == 0 unless N <= 4.
  * dpd_bn_forward:  mean[c], var[c] (biased) over the rows, y = act(gamma * (z - mean) * rsqrt(var + eps) + beta),
  *   act 0 = none, 1 = relu.  Two-pass statistics, fixed-order reductions (deterministic).
  * dpd_bn_backward: dz, dgamma, dbeta from dy (the gradient w.r.t. y; the activation's gate is re-derived from z).
  * Workspace for all four: dpd_layer_workspace_bytes(rows, K, N) bytes (use the layer's K and N; K = N for the bn calls). */
 size_t dpd_layer_workspace_bytes(int rows, int K, int N);
-int dpd_layer_forward(const float* d_x, int rows, int K, const float* d_w, const float* d_b, int N, float* d_z,
+int dpd_layer_forward(const float* d_x, int rows, int K, const float* d_w, const float* d_b, int N, int act, float* d_z,
                       const float* d_fv, const int32_t* d_idx, const float* d_offset, int n_query, int G, int C, int k,
                       void* stream);
 int dpd_layer_backward(const float* d_x, int rows, int K, const float* d_w, int N, const float* d_dz, float* d_gw,
                        float* d_gb, float* d_dx, const float* d_fv, const int32_t* d_idx, const float* d_offset,
                        int n_query, int G, int C, int k, void* d_workspace, size_t workspace_bytes, void* stream);
+/* Pieces the conv_version 3 head (utils/dpdist_util.py:640-687: 1x1x1 and 3x3x3 conv3d over the k^3 patch, residual blocks,
+ * FC) is assembled from, together with dpd_layer_forward / dpd_layer_backward: a 3x3x3 SAME conv3d over the [k,k,k,Cin]
+ * volume of every query IS the gathered layer with fv = the volumes, G = k, patch edge 3, n_query = k^3, idx = 0..k^3-1.
+ *   dpd_gather_rows:   out[r,:] = [offset (3) | patch (k^3*C)], the row get_emb_and_concat builds (:434-457)
+ *   dpd_relu_backward: dy[i] = 0 where y[i] <= 0 (in place)        dpd_add_inplace: a += b (residual connections) */
+int dpd_gather_rows(const float* d_fv, const int32_t* d_idx, const float* d_offset, int rows, int n_query, int G, int C, int k,
+                    float* d_out, void* stream);
+int dpd_relu_backward(float* d_dy, const float* d_y, size_t n, void* stream);
+int dpd_add_inplace(float* d_a, const float* d_b, size_t n, void* stream);
 int dpd_bn_forward(const float* d_z, int rows, int N, const float* d_gamma, const float* d_beta, float eps, int act,
                    float* d_y, float* d_mean, float* d_var, void* d_workspace, size_t workspace_bytes, void* stream);
 int dpd_bn_backward(const float* d_z, const float* d_dy, int rows, int N, const float* d_gamma, const float* d_beta,

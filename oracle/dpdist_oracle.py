@@ -367,6 +367,65 @@ def DPDist(point_cloud, point_cloudB, embedding, embeddingB, C, variables, outpu
     return [x[:B] * binary_vect, x[B:] * binary_vectB]                           # :695-698
 
 
+CV3_PREFIX = "pc_compare/dpdist_local_cnn_fc/"
+CV3_LAYERS = [("mapper_conv0", (1, 1, 1, None, 64)), ("mapper_conv1_1", (3, 3, 3, 64, 64)), ("mapper_conv1_2", (3, 3, 3, 64, 64)),
+              ("mapper_conv2_1", (3, 3, 3, 64, 64)), ("mapper_conv2_2", (3, 3, 3, 64, 64)), ("mapper_conv3", (1, 1, 1, 64, 16))]
+
+
+def init_cv3_variables(k=5, channels=20, mlp=(1024, 1024, 1024), seed=1, dtype=torch.float32, gain=1.0, bias_std=0.0, out_bias=0.0):
+    """Variables of the conv_version 3 head under their TF names (utils/dpdist_util.py:647-687; conv3d kernels are DHWIO,
+    utils/tf_util.py:347-353).  gain / bias_std / out_bias as in init_variables."""
+    gen = torch.Generator().manual_seed(seed)
+    out = {}
+    shapes = [(n, tuple(channels if d is None else d for d in shp)) for n, shp in CV3_LAYERS]
+    shapes += [("mapper_conv5", (1, 1, 16 * k ** 3 + 3, mlp[2])), ("mapper_conv6", (1, 1, mlp[2], 3))]
+    gains = gain if isinstance(gain, (tuple, list)) else (gain,) * len(shapes)
+    for (name, shp), gn in zip(shapes, gains):
+        out[CV3_PREFIX + name + "/weights"] = xavier_uniform_hwio(shp, gen, dtype) * gn
+        b = torch.randn(shp[-1], generator=gen, dtype=torch.float64) * bias_std
+        if name == "mapper_conv6":
+            b = b + out_bias
+        out[CV3_PREFIX + name + "/biases"] = b.to(dtype)
+    return out
+
+
+def _conv3d_same(x, w, b, relu=True):
+    """tf.nn.conv3d(NDHWC, DHWIO kernel, stride 1, 'SAME') + bias_add (+ relu), utils/tf_util.py:355-371."""
+    y = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(4, 3, 0, 1, 2), padding=[(d - 1) // 2 for d in w.shape[:3]])
+    y = y.permute(0, 2, 3, 4, 1) + b
+    return torch.relu(y) if relu else y
+
+
+def DPDist_cv3(point_cloud, point_cloudB, embedding, embeddingB, C, variables, k):
+    """utils/dpdist_util.py:412-511, 640-700 with conv_version 3 (NUM_DIMS 3, bn off), as written: the row
+    [offset (3) | patch (E)] is sliced at E, so net_E = [offset | patch[:E-3]] and net_D = patch[E-3:] (:641-642, :455)."""
+    bv, net, argmax = get_pc_grid_binary_mask_from_centers(C, point_cloudB)
+    net, binary_vect = get_emb_and_concat(net, embedding, argmax, bv)
+    bvB, netB, argmaxB = get_pc_grid_binary_mask_from_centers(C, point_cloud)
+    netB, binary_vectB = get_emb_and_concat(netB, embeddingB, argmaxB, bvB)
+    x = torch.cat([net, netB], 0)                                                # :511  [2B,NP,E+3]
+    B2, NP, _ = x.shape
+    E = embedding.shape[2]
+    net_E, net_D = x[:, :, :E], x[:, :, E:]                                      # :641-642
+    v = net_E.reshape(B2 * NP, k, k, k, -1)                                      # :644-646
+    P = CV3_PREFIX
+    get = lambda n: (variables[P + n + "/weights"], variables[P + n + "/biases"])
+    v = _conv3d_same(v, *get("mapper_conv0"))                                    # :648-652
+    for blk in ("mapper_conv1", "mapper_conv2"):                                 # resnet3d :394-410, :653-662
+        t = _conv3d_same(v, *get(blk + "_1"))
+        t = _conv3d_same(t, *get(blk + "_2"))
+        v = t + v
+    v = _conv3d_same(v, *get("mapper_conv3"))                                    # :663-667
+    f = torch.cat([v.reshape(B2, NP, -1), net_D], -1)                            # :668-673
+    w5, b5 = get("mapper_conv5")
+    w6, b6 = get("mapper_conv6")
+    f = torch.relu(f @ w5.reshape(w5.shape[2], w5.shape[3]) + b5)                # :680-684
+    f = f @ w6.reshape(w6.shape[2], w6.shape[3]) + b6                            # :686-690
+    out = (torch.clamp(f, 0.0, 6.0) / 3)[:, :, None, :]                          # :690-691
+    B = point_cloud.shape[0]
+    return [out[:B] * binary_vect, out[B:] * binary_vectB]                       # :695-698
+
+
 def get_loss(pred_set, end_points, labels, loss_type="l1_dist"):
     """utils/dpdist_util.py:962-980."""
     pred_listAB, pred_listBA = pred_set["pred_listAB"], pred_set["pred_listBA"]
@@ -378,7 +437,7 @@ def get_loss(pred_set, end_points, labels, loss_type="l1_dist"):
 
 
 def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3dmfv=0.125, add_noise=0, bn=False,
-              bn_decay=None, bn_updates=None):
+              bn_decay=None, bn_updates=None, conv_version=1):
     """models/dpdist_and_aue.py:31-86 (3dmfv encoder, k>0, conv_version 1)."""
     pcA_noise = pcA + add_noise                                                  # :45
     embedding_A = get_3dmfv(pcA_noise, n_gaussians=Embedding_Size, flatten=False,
@@ -389,7 +448,10 @@ def get_model(pcA, pcB, variables, Embedding_Size=512, k=5, full_fv=True, sigma3
     embedding_A, C = local_z(embedding_A, k=k)                                   # :64
     embedding_B, _ = local_z(embedding_B, k=k)                                   # :65
     C = C.to(pcA.dtype)
-    net = DPDist(pcA, pcB, embedding_A, embedding_B, C, variables, bn=bn, bn_decay=bn_decay, bn_updates=bn_updates)   # :69-75
+    if conv_version == 3:
+        net = DPDist_cv3(pcA, pcB, embedding_A, embedding_B, C, variables, k)
+    else:
+        net = DPDist(pcA, pcB, embedding_A, embedding_B, C, variables, bn=bn, bn_decay=bn_decay, bn_updates=bn_updates)   # :69-75
     pred_set = {"pred_listAB": net[0], "pred_listBA": net[1]}                    # :80-81
     embedding_set = {"embedding_A": embedding_A, "embedding_B": embedding_B}
     return pred_set, {"fvA": fvA, "fvB": fvB, "C": C}, embedding_set
