@@ -56,10 +56,17 @@ __global__ void __launch_bounds__(FV_THREADS) fv_generic_kernel(const FvParams p
         float* q = tab + ((a * 3 + 0) * FV_PCHUNK + pi) * G;
         float* m = tab + ((a * 3 + 1) * FV_PCHUNK + pi) * G;
         float* s = tab + ((a * 3 + 2) * FV_PCHUNK + pi) * G;
+        // exponentials shifted by the axis' smallest exponent (softmax shift: same q wherever the reference is finite, the
+        // limit value instead of 0/0 = NaN for a point far outside the cube; see fv_ws.cu)
+        float hmin = INFINITY;
+        for (int i = 0; i < G; ++i) {
+          const float z = (x - p.c[i]) / p.sigma;
+          hmin = fminf(hmin, z * z);
+        }
         float sum = 0.f;
         for (int i = 0; i < G; ++i) {
           const float z = (x - p.c[i]) / p.sigma;
-          const float e = expf(-0.5f * z * z);
+          const float e = expf(-0.5f * (z * z - hmin));
           q[i] = e;
           sum += e;
         }

@@ -58,10 +58,15 @@ __device__ __forceinline__ void build_tables(const BwdParams& p, const float* pt
     const float x = pts[(size_t)(n0 + pi) * 3 + a];
     float* q = tq + (a * BP + pi) * G;
     float* z = tz + (a * BP + pi) * G;
+    float hmin = INFINITY;             // softmax shift, as in the forward kernels (no 0/0 for far points)
+    for (int i = 0; i < G; ++i) {
+      const float zz = (x - p.c[i]) / p.sigma;
+      hmin = fminf(hmin, zz * zz);
+    }
     float sum = 0.f;
     for (int i = 0; i < G; ++i) {
       const float zz = (x - p.c[i]) / p.sigma;
-      const float e = expf(-0.5f * zz * zz);
+      const float e = expf(-0.5f * (zz * zz - hmin));
       z[i] = zz; q[i] = e; sum += e;
     }
     const float inv = 1.0f / sum;

@@ -147,12 +147,16 @@ __global__ void __launch_bounds__(T8) fv_g8_kernel(const FvParams p) {
         const int pp = task / 3, a = task - pp * 3;
         const float x = sm.pts[buf][task];
         float q[8], m[8], s[8];
-        float S = 0.f;
+        float S = 0.f, hmin = INFINITY;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float z = (x - p.c[i]) * inv_sigma;
           m[i] = z;
-          q[i] = __expf(-0.5f * z * z);
+          hmin = fminf(hmin, z * z);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {      // softmax shift: no 0/0 for far points (see fv_ws.cu)
+          q[i] = __expf(-0.5f * (m[i] * m[i] - hmin));
           S += q[i];
         }
         const float inv = __fdividef(1.0f, S);

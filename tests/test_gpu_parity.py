@@ -379,3 +379,19 @@ def test_fv_far_points_get_the_limit_value_not_nan():
     assert torch.isfinite(want).all()
     assert_fv_close(got, want, "fv with far points vs the fp64 twin")
     assert_fv_close(got[3], ref32[3], "an ordinary cloud in the same batch")
+
+
+def test_far_points_generic_kernel_and_backward_follow_the_same_policy():
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(-0.8, 0.8, size=(2, 40, 3)).astype(np.float32)
+    pts[0, 0] = [3.0, -3.0, 2.5]
+    got = dpdist_util.get_3dmfv_tf(torch.tensor(pts, device=DEV), n_gaussians=125, sigma=0.2, flatten=False)
+    want = O.get_3dmfv(torch.tensor(pts, dtype=torch.float64), 125, 0.2, flatten=False)
+    assert torch.isfinite(got).all()
+    assert_fv_close(got, want, "generic kernel with a far point vs the fp64 twin")
+    for V, sigma in ((512, 0.125), (125, 0.2)):                    # gradient into the clouds stays finite as well
+        x = torch.tensor(pts, device=DEV, requires_grad=True)
+        fv = dpdist_util.get_3dmfv_tf(x, n_gaussians=V, sigma=sigma, flatten=False)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        (fv * torch.randn(fv.shape, generator=g).to(DEV)).sum().backward()
+        assert torch.isfinite(x.grad).all()
