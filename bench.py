@@ -38,6 +38,14 @@ FLOPS_PER_EVAL = 2 * ((3 + CFG["C"] * CFG["k"] ** 3) * CFG["H"] + 2 * CFG["H"] *
 FV_BYTES_PER_CLOUD = 4 * (3 * CFG["N"] + CFG["C"] * CFG["G"] ** 3)                                        # 41,728
 
 
+def shared_config(world):
+    """`config` of both arms (ours and --impl reference): the same workload, described the same way."""
+    return {"workload": "configs[1]: batch=%d synthetic pairs per GPU, N=NP=64, G=8 (512 Gaussians), k=5, MLP 1024x3, forward-only" % CFG["pairs_per_gpu"],
+            "evals_per_step": CFG["pairs_per_gpu"] * 2 * CFG["NP"] * world,
+            "l2": "per-step working set (activations ~1 GB on the GPU, the 10.5 GB patch tensor on the CPU) exceeds the 126 MB L2; inputs rotate over 4 batches",
+            "weights": "Xavier-uniform random init (TF fan rules), zero biases, seed 1"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -167,9 +175,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch=%d synthetic pairs per step, N=NP=64, G=8 (512 Gaussians), k=5, MLP 1024x3, forward-only" % pairs,
-                   "evals_per_step": pairs * 2 * CFG["NP"],
-                   "note": "CPU restatement of the reference TF1 graph (oracle/dpdist_oracle.py, torch CPU, literal tiles and patch tensor); TF1 not installable here"},
+        "config": shared_config(1) if pairs == CFG["pairs_per_gpu"] else dict(shared_config(1), evals_per_step=pairs * 2 * CFG["NP"],
+                                                                             workload="configs[1] sample: %d pairs per step" % pairs),
+        "notes": "CPU restatement of the reference TF1 graph (oracle/dpdist_oracle.py, torch CPU, literal tiles and patch tensor, "
+                 "8 pairs per chunk); TF1 itself is not installable here (DESIGN.md 6)",
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d steps x %d pairs (%d evals)" % (args.steps, pairs, evals)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -533,10 +542,8 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: batch=1024 synthetic pairs per GPU, N=NP=64, G=8 (512 Gaussians), k=5, MLP 1024x3, forward-only",
-                       "evals_per_step": evals_per_step_rank * world,
-                       "l2": "per-step working set (activations ~1 GB) exceeds the 126 MB L2; inputs rotate over 4 batches",
-                       "head_impl": "auto = fp16x3 tcgen05, cta_group::2 pairs", "weights": "Xavier-uniform random init (TF fan rules), zero biases"},
+            "config": shared_config(world),
+            "notes": "head: fp16x3 tcgen05, cta_group::2 pairs (fp32-grade results, 3 tensor passes per algorithmic flop); 3DmFV: fv_g8_ws_kernel",
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "mode": "batches streamed: H2D of batch i+1 and D2H of batch i-1 overlap the compute of batch i on separate "
                             "streams; the host receives every batch's distances",

@@ -495,10 +495,13 @@ static bool gather_ldg() {
   return v != 0;
 }
 
-// DPD_TC_ZSKIP=0 visits every K-block of layer 1 (no row classes; A/B measurements)
-static bool zskip_env() {      // read per call: tools/ab_env.py alternates it inside one process
+// DPD_TC_ZSKIP=1 sorts the rows of an inference chunk by voxel boundary class and skips the structurally-zero K-blocks of
+// layer 1 per tile.  Off by default: 8.2 % fewer MMAs and gathers on the bench distribution, but the class-sorted rows no
+// longer share clouds within a tile, the gather's L1 / L2 locality drops (DRAM reads 97 -> 209 MB per launch) and the step
+// time does not move (profiles/ncu_r2_summary.md section 3).  Read per call: tools/ab_env.py alternates it in one process.
+static bool zskip_env() {
   const char* e = getenv("DPD_TC_ZSKIP");
-  return e ? (atoi(e) != 0) : true;
+  return e ? (atoi(e) != 0) : false;
 }
 
 // DPD_TC_FUSE_L4=0 keeps the separate output-layer kernel (A/B measurements)

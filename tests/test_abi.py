@@ -108,3 +108,29 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_layer_and_batch_norm_entry_points_validate_their_arguments():
+    """dpd_layer_* / dpd_bn_* / dpd_gather_rows (ABI 3: --BN 1 and conv_version 3) reject bad calls before any launch."""
+    lib = _lib.load()
+    p = ctypes.c_void_p(256)
+    need = lib.dpd_layer_workspace_bytes(1024, 1024, 1024)
+    assert need > 8 * 1024 * 1024 * 4                                     # split-K partials of a 1024 x 1024 weight gradient
+    assert lib.dpd_layer_workspace_bytes(0, 16, 16) == 0
+    assert lib.dpd_layer_forward(p, 128, 64, None, p, 64, 0, p, None, None, None, 0, 0, 0, 0, None) == -1        # null weights
+    assert lib.dpd_layer_forward(p, 128, 64, p, p, 64, 7, p, None, None, None, 0, 0, 0, 0, None) == -1           # bad act
+    assert lib.dpd_layer_forward(p, 128, 64, p, p, 3, 1, p, None, None, None, 0, 0, 0, 0, None) == -1            # narrow + relu
+    # gathered layer: packed weights must cover k^3*C + 3 rows; a bad grid is refused
+    assert lib.dpd_layer_forward(None, 128, 64, p, p, 64, 0, p, p, p, p, 64, 8, 20, 5, None) == -1
+    assert b"k^3*C + 3" in lib.dpd_last_error()
+    assert lib.dpd_layer_forward(None, 128, 2528, p, p, 64, 0, p, p, p, p, 64, 99, 20, 5, None) == -1
+    # backward: workspace size is checked; wide layers need N % 128 == 0
+    assert lib.dpd_layer_backward(p, 1024, 1024, p, 1024, p, p, p, None, None, None, None, 0, 0, 0, 0, p, 1024, None) == -3
+    assert lib.dpd_layer_backward(p, 1024, 1024, p, 64, p, p, p, None, None, None, None, 0, 0, 0, 0, p, need, None) == -2
+    assert b"N % 128" in lib.dpd_last_error()
+    assert lib.dpd_bn_forward(p, 128, 64, p, p, 1e-3, 5, p, p, p, p, 1 << 20, None) == -1                         # bad act
+    assert lib.dpd_bn_forward(p, 128, 64, p, p, 1e-3, 1, p, p, p, p, 16, None) == -3                              # workspace
+    assert lib.dpd_bn_backward(p, None, 128, 64, p, p, p, p, 1e-3, 1, p, p, p, p, 1 << 20, None) == -1
+    assert lib.dpd_gather_rows(p, p, p, 0, 64, 8, 20, 5, p, None) == -1
+    assert lib.dpd_relu_backward(None, p, 16, None) == -1
+    assert lib.dpd_add_inplace(p, p, 6, None) == -1                                                               # n % 4

@@ -244,3 +244,27 @@ def test_micro_batched_step_equals_the_single_chunk_step():
     for n in res[0][1]:
         d = (res[0][1][n] - res[1][1][n]).abs()
         assert float((d > 1e-5).double().mean()) < 1e-3 and float(d.max()) <= 4.1e-4, n      # Adam moves every weight by ~1e-4 per step
+
+
+def test_inference_after_graph_replays_sees_the_updated_weights():
+    """Graph replays (and the flat Adam launch) update the variables without touching their tensor version counters; the
+    packed-weight caches key on store.weights_generation instead.  Inference on the trainer's store after replays must equal
+    inference on a fresh store holding the same weights."""
+    pcA, pcB, labels = synthetic.chair_batch(5, 16, 64)
+    a, b, l = (torch.tensor(x, device=DEV) for x in (pcA, pcB, labels))
+    tr = train.DPDistTrainer(DEV, seed=11, cuda_graph=True)
+    kw = dict(bn=0, Embedding_Size=512, k=5, sigma3dmfv=0.125)
+    with tf_util.use_store(tr.store), torch.no_grad():
+        first = MODEL.get_model(a, b, False, **kw)[0]["pred_listAB"].clone()      # fills the inference cache early
+    for _ in range(7):                                                            # 3 eager steps, capture, replays
+        tr.step(a, b, l)
+    assert tr._graph is not None
+    with tf_util.use_store(tr.store), torch.no_grad():
+        got = MODEL.get_model(a, b, False, **kw)[0]["pred_listAB"].clone()
+    fresh = tf_util.VariableStore(device=DEV)
+    fresh.load_state_dict(tr.store.state_dict(), strict=False)
+    with tf_util.use_store(fresh), torch.no_grad():
+        want = MODEL.get_model(a, b, False, **kw)[0]["pred_listAB"]
+    assert torch.equal(got, want)
+    assert not torch.equal(got, first)                                            # the weights did move
+    tr.close()

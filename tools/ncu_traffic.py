@@ -33,9 +33,12 @@ def main():
         for pat, k in MAP:
             if re.search(pat, name):
                 key = k
-        if key is None and "tc_gemm2_kernel" in name:
-            # the three forward GEMM launches of a step share one template: tell them apart by the bytes they read
-            key = "tc_gemm2:" + name
+        if key is None and "tc_gemm2_kernel<1>" in name:
+            key = "tc_gemm2_gather_l1_f16"
+        if key is None and "tc_gemm2_kernel<0>" in name:
+            # layers 2 and 3 share one instantiation: layer 2 writes the (hi, lo) activations (~0.5 GB at the bench size),
+            # layer 3 with the fused output layer writes one float4 per row and column slice
+            key = "tc_gemm2_dense_f16" if wr > 0.2 * rd else "tc_gemm2_dense_l3_l4_f16"
         if key is None:
             continue
         acc.setdefault(key, []).append((rd, wr, dur))
@@ -43,6 +46,9 @@ def main():
         n = len(v)
         out[k] = {"bytes": sum(a + b for a, b, _ in v) / n, "read": sum(a for a, _, _ in v) / n, "write": sum(b for _, b, _ in v) / n,
                   "launches": n, "duration_us_under_ncu": sum(d for _, _, d in v) / n, "source": how}
+    dst = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    with open(dst, "w") as fh:
+        json.dump(out, fh, indent=1)
     print(json.dumps(out, indent=1))
 
 
