@@ -1,7 +1,8 @@
 """Interleaved A/B of one library switch inside ONE process (drift of clocks / power state cancels): the forward step of
 configs[1] is timed in alternating blocks with the environment variable set to each value.
-    python tools/ab_env.py DPD_TC_ZSKIP 0 1 [blocks] [steps per block]
-Only switches the library reads per call can be compared this way (DPD_TC_ZSKIP, DPD_FV_IMPL)."""
+    python tools/ab_env.py DPD_TC_ZSKIP 0 1 [blocks] [steps per block] [idle seconds before every block]
+With an idle time (e.g. 1.0) every block is a cold burst at the boost clock - what a 20-step bench run measures; without
+it the blocks run back to back at the power-capped clock.  Only switches the library reads per call can be compared this way (DPD_TC_ZSKIP, DPD_FV_IMPL)."""
 import os
 import sys
 
@@ -13,6 +14,7 @@ from dpdist_b200 import dpdist_and_aue as MODEL, synthetic, tf_util  # noqa: E40
 var, va, vb = sys.argv[1], sys.argv[2], sys.argv[3]
 blocks = int(sys.argv[4]) if len(sys.argv) > 4 else 12
 steps = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+idle = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
 dev = torch.device("cuda", 0)
 store = tf_util.VariableStore(device=dev, seed=1)
 sets = []
@@ -36,6 +38,12 @@ torch.cuda.synchronize()
 for blk in range(blocks):
     for v in ((va, vb) if blk % 2 == 0 else (vb, va)):
         os.environ[var] = v
+        if idle > 0:
+            import time
+            time.sleep(idle)
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
