@@ -10,6 +10,8 @@
 //                    the weights), so nothing can overflow; 11+11 mantissa bits like TF32, but the fp16 pipe
 //                    runs at twice the TF32 rate and the operands are half the bytes.
 //   DPD_HEAD_TC_TF32 3xTF32: hi = tf32(x), lo = tf32(x - hi); no scaling needed (fp32 exponent range).
+#include <vector>
+#include <cstdio>
 #include "head_bwd.cuh"
 #include "head_tc.cuh"
 #include "head_tc_kernel.cuh"
@@ -286,9 +288,24 @@ __global__ void split_f16_kernel(const float* __restrict__ x, size_t n, const fl
 // offsets of rows outside the unit cube are zeroed: their output is masked to 0 anyway (:697-698) and an
 // arbitrary far-away query must not be able to overflow fp16
 __global__ void split_off4_f16_kernel(const float* __restrict__ off, const float* __restrict__ mask, int rows,
-                                      const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo) {
+                                      const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                      const int32_t* __restrict__ idx, long long row0, int n_query, int G, int Cc, int k,
+                                      int2* __restrict__ rowinfo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
+  if (rowinfo != nullptr) {     // the gather producers' per-row words, same contents as rowinfo_kernel
+    const int V = G * G * G, pb = (k - 1) >> 1;
+    const long long cloud = (row0 + i) / n_query;
+    const int v = idx[i];
+    const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
+    uint32_t mk = 0;
+    for (int a = 0; a < k; ++a) {
+      mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
+      mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
+      mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
+    }
+    rowinfo[i] = make_int2((int)(cloud * V * Cc) + v * Cc, (int)mk);
+  }
   const float s = mask[i] != 0.f ? *scale : 0.f;
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
@@ -466,15 +483,15 @@ static int launch_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CU
   return 0;
 }
 
-template <bool GATHER>
+template <int GM>
 static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
                      const KernelArgs& ka, int grid, size_t smem, cudaStream_t st) {
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
   }
-  DPD_LAUNCH(GATHER ? (ka.mn_major ? "tc_gemm2_bwd_dw1_gather_f16" : "tc_gemm2_gather_l1_f16") : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
-             tc_gemm2_kernel<GATHER><<<grid, GATHER ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
+  DPD_LAUNCH(GM ? (ka.mn_major ? "tc_gemm2_bwd_dw1_gather_f16" : "tc_gemm2_gather_l1_f16") : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
+             tc_gemm2_kernel<GM><<<grid, GM ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
   DPD_CUDA_CHECK_LAUNCH("tc_gemm2_kernel");
   return 0;
 }
@@ -483,15 +500,6 @@ static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const C
 static bool use_2cta() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DPD_TC_2CTA"); v = e ? (atoi(e) != 0) : 1; }
-  return v != 0;
-}
-
-// DPD_TC_GATHER_LDG=1 assembles the layer-1 operand through registers (LDG.64 x 2 -> STS.128) instead of cp.async.  Measured
-// on B200 (profiles/ncu_r2_summary.md): 2.17 ms per launch against 1.69 ms -- the full-width shared-memory stores do not
-// pay for the load latency a register path exposes (one K-block in flight per thread instead of three).  Off by default.
-static bool gather_ldg() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DPD_TC_GATHER_LDG"); v = e ? (atoi(e) != 0) : 0; }
   return v != 0;
 }
 
@@ -563,7 +571,8 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
   ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4; ka.relu_bits_out = relu_bits_out;
   const bool gather_mn = gather && bx && bx->mn_major;
-  ka.gather_ldg = (gather && !gather_mn && gather_ldg()) ? 1 : 0;
+  { const char* e = getenv("DPD_TC_EPI_BACKOFF"); ka.epi_backoff_ns = e ? (unsigned)atoi(e) : 0u; }
+  { const char* e = getenv("DPD_TC_DBG"); ka.dbg = e ? atoi(e) : 0; }
   if (g) {
     ka.g = *g;
     if (gather && !gather_mn) {   // valid operand length E + 3; everything from there to K is zero padding
@@ -585,8 +594,34 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   const size_t lut_entries = gather ? (gather_mn ? (size_t)bx->lut_chunks : (size_t)(K / 4)) : 0;
   const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + 2 * lut_entries * sizeof(uint32_t);
-  return gather ? launch2_t<true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st)
-                : launch2_t<false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem, st);
+  const int gm = gather ? 1 : 0;
+  const size_t smem_use = smem;
+  auto go = [&]() -> int {
+    return gm == 1 ? launch2_t<1>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem_use, st)
+                   : launch2_t<0>(ta_hi, ta_lo, tb_hi, tb_lo, ka, 2 * clusters, smem_use, st);
+  };
+  // DPD_TC_TRACE=<prefix>: timeline of cluster 0 (clock64 stamps per warp role) of launches 20..22 of every kernel flavour,
+  // written to <prefix>.<flavour>.<n>.bin after a stream synchronise (tools/tc_trace.py reads them).  Measurement aid only.
+  if (const char* tp = getenv("DPD_TC_TRACE")) {
+    static int counter[2] = {0, 0};
+    static unsigned long long* buf = nullptr;
+    const int n = counter[gather ? 1 : 0]++;
+    if (n >= 20 && n < 23 && !bx) {
+      const size_t bytes = 4 * 65536 * sizeof(unsigned long long);
+      if (!buf) DPD_CUDA_CALL(cudaMalloc(&buf, bytes));
+      DPD_CUDA_CALL(cudaMemsetAsync(buf, 0, bytes, st));
+      ka.trace = buf;
+      const int rc2 = go();
+      DPD_CUDA_CALL(cudaStreamSynchronize(st));
+      std::vector<unsigned long long> h(4 * 65536);
+      DPD_CUDA_CALL(cudaMemcpy(h.data(), buf, bytes, cudaMemcpyDeviceToHost));
+      char path[512];
+      snprintf(path, sizeof(path), "%s.%s.K%d.%d.bin", tp, (gather ? "gather" : (part4 ? "dense_l3" : "dense")), K, n);
+      if (FILE* f = fopen(path, "wb")) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+      return rc2;
+    }
+  }
+  return go();
 }
 
 // D[M,N] = relu(acc_scale * A[M,K] * B[N,K]^T + bias), operands pre-split (hi, lo); K % kb == 0, N % 256 == 0
@@ -674,11 +709,12 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.xh = o; o += up256(rows * (size_t)c.H * e); w.xl = o; o += up256(rows * (size_t)c.H * e);
   w.yh = w.yl = o;
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
-  w.gh = w.gl = w.rinfo = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
-  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, per-row gather info, partials
+  w.rinfo = o;
+  if (f16) o += up256(rows * 8);      // per-row gather info (forward: split_off4_f16_kernel, backward: rowinfo_kernel)
+  w.gh = w.gl = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
+  if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, partials
     const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);
     w.gh = o; o += act; w.gl = o; o += act;
-    w.rinfo = o; o += up256(rows * 8);
     const size_t p1 = (size_t)TC_DW1_SLICES * Kp1 * c.H * 4, p2 = (size_t)TC_DW_SLICES * c.H * c.H * 4;
     w.part = o; o += up256(p1 > p2 ? p1 : p2);
     w.cpart = o; o += up256((rows / 64 + 1) * (size_t)c.H * 4);      // per-64-row-block column sums of dZ
@@ -788,7 +824,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
     int Mo;       // rows of the weight gradient in kernel order
     if (layer == 1) {
       tc::GatherArgs ga;
-      ga.perm = nullptr; ga.tile_range = nullptr;
+      ga.perm = nullptr; ga.tile_range = nullptr; ga.rowinfo = nullptr;
       ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g->idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g->row0;
       ga.n_query = g->n_query; ga.G = g->G; ga.C = g->C; ga.k = g->k; ga.E = g->E;
       // the gather warps of the GEMM kernel assemble the MN-major A tiles on the fly: nothing is materialised
@@ -923,7 +959,7 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
   const int H = c.H, Kp1 = kp1_of(c, f16);
   const float* sc = (const float*)(ws + w.scales);
   tc::GatherArgs ga;
-  ga.perm = nullptr; ga.tile_range = nullptr;
+  ga.perm = nullptr; ga.tile_range = nullptr; ga.rowinfo = nullptr;
   ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g.idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g.row0;
   ga.n_query = g.n_query; ga.G = g.G; ga.C = g.C; ga.k = g.k; ga.E = g.E;
   float* out3 = h3_out ? h3_out : ha;
@@ -937,8 +973,10 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
     if ((rc = tc::launch(false, false, ws + w.xh, ws + w.xl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, out3, nullptr, 0, nullptr, nullptr, nullptr, st))) return rc;
   } else {
     DPD_LAUNCH("tc_split_off", st, tc::split_off4_f16_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
-        g.offset, mask, rows, sc + tc::S_A1, (__half*)(ws + w.o4h), (__half*)(ws + w.o4l)));
+        g.offset, mask, rows, sc + tc::S_A1, (__half*)(ws + w.o4h), (__half*)(ws + w.o4l),
+        g.idx, g.row0, g.n_query, g.G, g.C, g.k, (int2*)(ws + w.rinfo)));
     DPD_CUDA_CHECK_LAUNCH("split_off4_f16_kernel");
+    ga.rowinfo = (const int2*)(ws + w.rinfo);
     // Inference with the fused output layer: rows sorted by the boundary class of their voxel so that whole tiles can skip
     // the structurally-zero K-blocks of layer 1; the permutation is undone by head_out_finish_kernel.  `hb` is not used by
     // this path and holds perm [rows] and tile_range.

@@ -34,6 +34,11 @@ struct GatherArgs {
   // K-blocks are skipped by every warp role.
   const int32_t* perm;
   const int4* tile_range;
+  // per query row {element offset of its voxel record in the FV tensor, tap validity bits}: written by the kernel that
+  // splits the offsets (split_off4_f16_kernel), so the gather warps load two words per row at a tile boundary instead of
+  // decoding the voxel index (64-bit division by n_query, three divisions by G, 3k range tests per row: the timeline showed
+  // the MMAs idle for ~26 k cycles per tile behind that decode, profiles/ncu_r3_summary.md)
+  const int2* rowinfo;
 };
 
 struct KernelArgs {
@@ -71,9 +76,9 @@ struct KernelArgs {
                            // so that the next layer's operand scale needs no extra pass over the gradient
   int last_ks;             // 2-CTA kernel: K-steps (16 elements) of the LAST K-block that hold data; 0 = all four.  The padded
                            // tail of the layer-1 operand (2503 -> 2560) is zero on both sides: its MMAs are not issued.
-  int gather_ldg;          // 2-CTA gather kernel, K-major operand: assemble the A tile through registers (LDG.64 x 2 ->
-                           // STS.128, full 128-byte shared-memory wavefronts) instead of 8-byte cp.async, whose data lands
-                           // sector by sector (about 3.8 x the ideal number of write wavefronts, profiles/ncu_r1_summary.md)
+  unsigned long long* trace;   // timing experiments only (DPD_TC_TRACE): per-role clock64 stamps of cluster 0's leader CTA, see tools/tc_trace.py
+  int dbg;                 // timing experiments only (DPD_TC_DBG): 1 = staged gather without the copies, 2 = without the proxy fence
+  unsigned epi_backoff_ns; // 2-CTA kernel: nanosleep between the epilogue warps' polls of seg_full (0 = tight spin)
   GatherArgs g;
 };
 

@@ -55,6 +55,22 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   } while (!done);
 }
+// wait of a role that is off the critical path (the epilogue's wait for a finished segment: one per four K-blocks): back
+// off between polls so that the spinning warps do not take issue slots from the gather / TMA warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (ns) __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -82,15 +98,18 @@ __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols)
 
 // warps: 0 TMA producer | 1 MMA issuer (leader) | 2 TMEM allocator | 3 gather relay (peer, layer 1) |
 //        4-11 epilogue | 12-15 gather (layer 1)
-template <bool GATHER>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GATHER ? 512 : 384, 1)
+// GM: 0 = dense (A by TMA) | 1 = A gathered from the 3DmFV records by cp.async (layer 1 and its weight gradient)
+template <int GM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM ? 512 : 384, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 const KernelArgs args) {
   constexpr int KB_ELEMS = 64, ELEM = 2, CHUNKS = 16, SEG = 4;
+  constexpr bool GATHER = GM != 0;
+  constexpr int STG = STAGES2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  SharedCtl2* ctl = (SharedCtl2*)(smem + STAGES2 * STAGE2_BYTES);
+  SharedCtl2* ctl = (SharedCtl2*)(smem + STG * STAGE2_BYTES);
   uint32_t* lut = (uint32_t*)(ctl + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,10 +128,24 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int kbps = num_slices > 1 ? (args.k_limit ? ((nkb_eff + num_slices - 1) / num_slices + SEG - 1) / SEG * SEG : args.kb_per_slice)
                                   : args.num_kb;
   const int num_row_blocks = (args.M + BM - 1) / BM;
+  // j-th work item of this cluster -> (tile t = m-tile * num_n_tiles + n-tile, slice)
+  auto get_item = [&](int j, int& t, int& sl) -> bool {
+    const int w = cluster_id + j * num_clusters;
+    if (w >= num_items) return false;
+    t = w % num_tiles; sl = w / num_tiles;
+    return true;
+  };
   auto item_skipped = [&](int mt) -> bool {
     if (args.active == nullptr) return false;
     const int b0 = 2 * mt;
     return !__ldg(args.active + b0) && !(b0 + 1 < num_row_blocks && __ldg(args.active + b0 + 1));
+  };
+
+  // optional timeline (DPD_TC_TRACE): role r of cluster 0's leader appends (tag << 56 | clock) to its own 64K-entry region
+  const bool tracing = args.trace != nullptr && cluster_id == 0 && leader;
+  int trace_n = 0;
+  auto stamp = [&](int role, unsigned long long tag) {
+    if (tracing && trace_n < 65536) args.trace[(size_t)role * 65536 + trace_n++] = (tag << 56) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFFFull);
   };
 
   // K-blocks an item visits: a main run [lo, lo + n_main) and a tail run [tail_lo, ...), cnt in total.  Forward: all of
@@ -141,7 +174,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (!GATHER) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES2; ++s) {
+    for (int s = 0; s < STG; ++s) {
       mbar_init(&ctl->full[s], GATHER ? (2 + NUM_GATHER_THREADS) : 1);
       mbar_init(&ctl->empty[s], 1);
       mbar_init(&ctl->gfull[s], NUM_GATHER_THREADS);
@@ -183,8 +216,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
       int s = 0; uint32_t ph = 0;
-      for (int w = cluster_id; w < num_items; w += num_clusters) {
-        const int t = w % num_tiles, sl = w / num_tiles;
+      for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         const int mt = t / num_n_tiles, nt = t % num_n_tiles;
         if (item_skipped(mt)) continue;
         const int row0 = mt * 2 * BM + (int)rank * BM;
@@ -192,7 +224,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const Seq q = make_seq(mt, sl);
         for (int i = 0; i < q.cnt; ++i) {
           const int kb = kb_of(q, i);
+          stamp(0, 14);
           mbar_wait(&ctl->empty[s], ph ^ 1);
+          stamp(0, 15);
           const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
           if (args.mn_major) {
@@ -215,26 +249,29 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               tma_load_2d_cg2(stage_ptr(s, 1), &tm_a_lo, lbar, kb * KB_ELEMS, row0);
             }
           }
-          if (++s == STAGES2) { s = 0; ph ^= 1; }
+          if (++s == STG) { s = 0; ph ^= 1; }
         }
       }
     } else if (warp == 1 && lane == 0 && leader) {
       // ===================== MMA issuer (leader only) =====================
       int s = 0; uint32_t ph = 0;
       int sb = 0; uint32_t sb_ph = 0;
-      for (int w = cluster_id; w < num_items; w += num_clusters) {
-        const int t = w % num_tiles, sl = w / num_tiles;
+      for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         if (item_skipped(t / num_n_tiles)) continue;
         const Seq q = make_seq(t / num_n_tiles, sl);
         for (int i0 = 0; i0 < q.cnt; i0 += SEG) {
+          stamp(1, 4);
           mbar_wait_cluster(&ctl->seg_empty[sb], sb_ph ^ 1);
+          stamp(1, 5);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
           uint32_t accumulate = 0;
           const int i1 = min(i0 + SEG, q.cnt);
           for (int i = i0; i < i1; ++i) {
             const int kb = kb_of(q, i);
+            stamp(1, 1);
             mbar_wait_cluster(&ctl->full[s], ph);
+            stamp(1, 2);
             tc_fence_after();
             const bool mn = args.mn_major != 0;
             const uint64_t ah = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 0)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 0)));
@@ -255,7 +292,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               accumulate = 1;
             }
             umma_commit_cg2_mcast(&ctl->empty[s]);
-            if (++s == STAGES2) { s = 0; ph ^= 1; }
+            stamp(1, 3);
+            if (++s == STG) { s = 0; ph ^= 1; }
           }
           umma_commit_cg2_mcast(&ctl->seg_full[sb]);
           if (++sb == 2) { sb = 0; sb_ph ^= 1; }
@@ -264,15 +302,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     } else if (GATHER && warp == 3 && lane == 0 && !leader) {
       // ===================== gather relay (peer only): local gfull[s] -> leader's full[s] =====================
       int s = 0; uint32_t ph = 0;
-      for (int w = cluster_id; w < num_items; w += num_clusters) {
-        const int t = w % num_tiles, sl = w / num_tiles;
+      for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         if (item_skipped(t / num_n_tiles)) continue;
         const Seq q = make_seq(t / num_n_tiles, sl);
         for (int i = 0; i < q.cnt; ++i) {
           mbar_wait(&ctl->gfull[s], ph);
           fence_proxy_async();
           mbar_arrive_remote(map_to_rank(smem_u32(&ctl->full[s]), 0));
-          if (++s == STAGES2) { s = 0; ph ^= 1; }
+          if (++s == STG) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -286,8 +323,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const float out_scale = args.out_scale ? __ldg(args.out_scale) : 1.0f;
     int sb = 0; uint32_t sb_ph = 0;
     float sum[EPI_COLS];
-    for (int w = cluster_id; w < num_items; w += num_clusters) {
-      const int t = w % num_tiles, sl = w / num_tiles;
+    for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
       if (item_skipped(mt)) continue;
       const int row_base = mt * 2 * BM + (int)rank * BM;
@@ -298,7 +334,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         for (int j = 0; j < EPI_COLS; ++j) sum[j] = 0.f;
       }
       for (int i0 = 0; i0 < sq.cnt; i0 += SEG) {
-        mbar_wait(&ctl->seg_full[sb], sb_ph);
+        if (e == 0 && lane == 0) stamp(2, 6);
+        mbar_wait_backoff(&ctl->seg_full[sb], sb_ph, args.epi_backoff_ns);
+        if (e == 0 && lane == 0) stamp(2, 7);
         tc_fence_after();
 #pragma unroll
         for (int rh = 0; rh < 2; ++rh) {
@@ -327,7 +365,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           else mbar_arrive_remote(map_to_rank(smem_u32(&ctl->seg_empty[sb]), 0));
         }
         if (++sb == 2) { sb = 0; sb_ph ^= 1; }
+        if (e == 0 && lane == 0) stamp(2, 8);
       }
+      if (e == 0 && lane == 0) stamp(2, 9);
       const int col0 = nt * BN + half * EPI_COLS + 2 * (lane & 3);
       if (!GATHER && args.part4 != nullptr) {
         // fused output layer: this warp's share of H3[row, :] . W4 for its 64 rows x 128 columns.  A thread holds
@@ -490,9 +530,6 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     // ===================== patch-gather producers (both CTAs, own 128 rows) =====================
     reg_dec<96>();
     const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
-    constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / CHUNKS;
-    constexpr int NIT = BM / ROWS_PER_IT;
-    const int sub = p / CHUNKS, chunk = p % CHUNKS;
     const GatherArgs& g = args.g;
     const int G = g.G, Cc = g.C, pb = (g.k - 1) >> 1;
     const int V = G * G * G;
@@ -508,8 +545,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const int chunk32 = p & 31, sub = p >> 5;                 // 32 chunk columns (2 groups x 16) x 4 row lanes
       const uint32_t c16 = (uint32_t)((chunk32 & 15) >> 1);
       const uint32_t dst0 = (uint32_t)((chunk32 >> 4) * 8192 + (chunk32 & 1) * 8);
-      for (int w = cluster_id; w < num_items; w += num_clusters) {
-        const int t = w % num_tiles, sl = w / num_tiles;
+      for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         const int mt = t / num_n_tiles;
         const int q = (mt * 2 * BM + (int)rank * BM) / 4 + chunk32;
         uint32_t code = LUT_ZERO; int32_t delta = 0;
@@ -548,156 +584,86 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
           }
           cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
-          if (++s == STAGES2) { s = 0; ph ^= 1; }
+          if (++s == STG) { s = 0; ph ^= 1; }
         }
       }
-    } else if (args.gather_ldg) {
-      // Register path: thread (rl = p / 8, u = p % 8) fills the 16-byte unit u of rows it*16 + rl, it = 0..7, of every
-      // K-block: two 8-byte loads (the two 4-element chunks of the unit; a chunk never straddles a tap) and one STS.128.
-      // A quarter warp writes the eight units of one 128-byte row: full-width, conflict-free shared-memory wavefronts.
-      constexpr int NIT2 = 8;
-      const int rl = p >> 3, u = p & 7;
-      for (int w = cluster_id; w < num_items; w += num_clusters) {
-        const int t = w % num_tiles;
+    } else {
+      // K-major operand (forward).  Thread (sub = p / 16, chunk = p % 16) copies the 8-byte chunk `chunk` of rows
+      // it * 8 + sub; half a warp covers one row's 128 bytes contiguously.
+      constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / CHUNKS;
+      constexpr int NIT = BM / ROWS_PER_IT;
+      const int sub = p / CHUNKS, chunk = p % CHUNKS;
+      const uint32_t dst0 = (uint32_t)(sub * 128 + (chunk & 1) * 8);
+      const uint32_t c16 = (uint32_t)(chunk >> 1);
+      for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         const int mt = t / num_n_tiles;
         if (item_skipped(mt)) continue;
         const int row_base = mt * 2 * BM + (int)rank * BM;
-        int32_t rel[NIT2];
-        uint32_t rmsk[NIT2];
+        int32_t rel[NIT];
+        uint32_t rmsk[NIT];
 #pragma unroll
-        for (int it = 0; it < NIT2; ++it) {
-          const int m = row_base + it * 16 + rl;
+        for (int it = 0; it < NIT; ++it) {
+          const int m = row_base + it * ROWS_PER_IT + sub;
           rel[it] = -1; rmsk[it] = 0;
           if (m < args.M) {
             const int mo = g.perm ? __ldg(g.perm + m) : m;
-            const long long cloud = (g.row0 + mo) / g.n_query;
-            const int v = __ldg(g.idx + mo);
-            rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
-            const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
-            uint32_t mk = 0;
-            for (int a = 0; a < g.k; ++a) {
-              mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
-              mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
-              mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
+            if (g.rowinfo != nullptr) {
+              const int2 ri = __ldg(g.rowinfo + mo);
+              rel[it] = ri.x; rmsk[it] = (uint32_t)ri.y;
+            } else {
+              const long long cloud = (g.row0 + mo) / g.n_query;
+              const int v = __ldg(g.idx + mo);
+              rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
+              const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
+              uint32_t mk = 0;
+              for (int a = 0; a < g.k; ++a) {
+                mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
+                mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
+                mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
+              }
+              rmsk[it] = mk;
             }
-            rmsk[it] = mk;
           }
         }
         const Seq q = make_seq(mt, 0);
         for (int qi = 0; qi < q.cnt; ++qi) {
           const int kb = kb_of(q, qi);
-          uint32_t code[2]; int32_t delta[2];
+          uint32_t code; int32_t delta;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+          if (p == 0) stamp(3, 11);
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          if (p == 0) stamp(3, 12);
+          const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+          if (code < LUT_OFFS) {
+            const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code[hf]) : "r"(lut_s + (uint32_t)(kb * CHUNKS + 2 * u + hf) * 4u));
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta[hf]) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + 2 * u + hf) * 4u));
-          }
-          uint2 vh[NIT2][2], vl[NIT2][2];
+            for (int it = 0; it < NIT; ++it) {
+              const int r = it * ROWS_PER_IT + sub;
+              const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+              const uint32_t ok = (rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u;
+              const size_t el = ok ? (size_t)(rel[it] + delta) : 0;
+              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+              cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
+              cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
+            }
+          } else {
 #pragma unroll
-          for (int it = 0; it < NIT2; ++it) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint32_t c = code[hf];
-              const uint8_t *sh, *sl;
-              bool ok;
-              if (c < LUT_OFFS) {
-                const uint32_t s0 = c & 255u, s1 = 8u + ((c >> 8) & 255u), s2 = 16u + ((c >> 16) & 255u);
-                ok = ((rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u) != 0;
-                const size_t el = ok ? (size_t)(rel[it] + delta[hf]) : 0;
-                sh = fv_hi + el * ELEM; sl = fv_lo + el * ELEM;
-              } else {
-                ok = (c == LUT_OFFS) && rel[it] >= 0;
-                size_t m = ok ? (size_t)row_base + it * 16 + rl : 0;
-                if (ok && g.perm) m = (size_t)__ldg(g.perm + m);
-                sh = o4_hi + m * 4 * ELEM; sl = o4_lo + m * 4 * ELEM;
-              }
-              vh[it][hf] = make_uint2(0u, 0u); vl[it][hf] = make_uint2(0u, 0u);
-              if (ok) {
-                vh[it][hf] = __ldg(reinterpret_cast<const uint2*>(sh));
-                vl[it][hf] = __ldg(reinterpret_cast<const uint2*>(sl));
-              }
+            for (int it = 0; it < NIT; ++it) {
+              const int r = it * ROWS_PER_IT + sub;
+              const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+              const bool ok = (code == LUT_OFFS) && rel[it] >= 0;
+              size_t m = ok ? (size_t)row_base + r : 0;
+              if (ok && g.perm) m = (size_t)__ldg(g.perm + m);
+              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+              cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
+              cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
             }
           }
-          mbar_wait(&ctl->empty[s], ph ^ 1);
-          const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-#pragma unroll
-          for (int it = 0; it < NIT2; ++it) {
-            const int r = it * 16 + rl;
-            const uint32_t dst = (uint32_t)(r * 128) + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + dst), "r"(vh[it][0].x), "r"(vh[it][0].y),
-                         "r"(vh[it][1].x), "r"(vh[it][1].y) : "memory");
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + dst), "r"(vl[it][0].x), "r"(vl[it][0].y),
-                         "r"(vl[it][1].x), "r"(vl[it][1].y) : "memory");
-          }
-          fence_proxy_async();            // generic-proxy stores -> visible to the tensor core's async-proxy reads
-          mbar_arrive(leader ? &ctl->full[s] : &ctl->gfull[s]);
-          if (++s == STAGES2) { s = 0; ph ^= 1; }
+          cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
+          if (p == 0) stamp(3, 13);
+          if (++s == STG) { s = 0; ph ^= 1; }
         }
-      }
-    } else
-    for (int w = cluster_id; w < num_items; w += num_clusters) {
-      const int t = w % num_tiles;
-      const int mt = t / num_n_tiles;
-      if (item_skipped(mt)) continue;
-      const int row_base = mt * 2 * BM + (int)rank * BM;
-      int32_t rel[NIT];
-      uint32_t rmsk[NIT];
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int m = row_base + it * ROWS_PER_IT + sub;
-        rel[it] = -1; rmsk[it] = 0;
-        if (m < args.M) {
-          const int mo = g.perm ? __ldg(g.perm + m) : m;
-          const long long cloud = (g.row0 + mo) / g.n_query;
-          const int v = __ldg(g.idx + mo);
-          rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
-          const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
-          uint32_t mk = 0;
-          for (int a = 0; a < g.k; ++a) {
-            mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
-            mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
-            mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
-          }
-          rmsk[it] = mk;
-        }
-      }
-      const Seq q = make_seq(mt, 0);
-      for (int qi = 0; qi < q.cnt; ++qi) {
-        const int kb = kb_of(q, qi);
-        mbar_wait(&ctl->empty[s], ph ^ 1);
-        const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-        uint32_t code; int32_t delta;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
-        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
-        const uint32_t dst0 = (uint32_t)(sub * 128 + (chunk & 1) * 8);
-        const uint32_t c16 = (uint32_t)(chunk >> 1);
-        if (code < LUT_OFFS) {
-          const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
-#pragma unroll
-          for (int it = 0; it < NIT; ++it) {
-            const int r = it * ROWS_PER_IT + sub;
-            const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
-            const uint32_t ok = (rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u;
-            const size_t el = ok ? (size_t)(rel[it] + delta) : 0;
-            const uint32_t nbytes = ok ? 4u * ELEM : 0u;
-            cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
-            cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
-          }
-        } else {
-#pragma unroll
-          for (int it = 0; it < NIT; ++it) {
-            const int r = it * ROWS_PER_IT + sub;
-            const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
-            const bool ok = (code == LUT_OFFS) && rel[it] >= 0;
-            size_t m = ok ? (size_t)row_base + r : 0;
-            if (ok && g.perm) m = (size_t)__ldg(g.perm + m);
-            const uint32_t nbytes = ok ? 4u * ELEM : 0u;
-            cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
-            cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
-          }
-        }
-        cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
-        if (++s == STAGES2) { s = 0; ph ^= 1; }
       }
     }
   }
