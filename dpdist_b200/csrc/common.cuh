@@ -78,6 +78,34 @@ struct ProfScope {
     __VA_ARGS__;                             \
   } while (0)
 
+// Operand order of layer 1 in the fp16 tensor-core path (head_tc_kernel2.cuh).  Logical order = channel-split:
+// [taps x CX | taps x (C - CX) | 3 offsets | padding], CX = C & ~7.  The first nX = taps * CX / 64 K-blocks (64 elements)
+// are pure X (16-byte bypass copies, fast to gather), the remaining nY hold the last X units, the Y part, the offsets and
+// the padding (8-byte copies, about 2.5 x slower to issue).  Physical order = the K-blocks permuted so that the slow ones
+// are spread out, one after every s - 1 fast ones, instead of forming a tail the 4-deep gather ring cannot absorb; the
+// last logical K-block (the one that may be partially skipped, KernelArgs::last_ks) stays last.
+__host__ __device__ inline int tc_kb_logical(int b, int nkb, int nX) {
+  const int nY = nkb - nX;
+  if (nY <= 1 || nX <= 0 || b == nkb - 1) return b;
+  const int s = (nkb - 1) / (nY - 1) > 1 ? (nkb - 1) / (nY - 1) : 1;    // a slow K-block at b = s - 1, 2 s - 1, ...
+  const int slots_upto = ((b + 1) / s) < (nY - 1) ? ((b + 1) / s) : (nY - 1);     // slow slots among positions 0 .. b
+  if ((b + 1) % s == 0 && (b + 1) / s <= nY - 1) return nX + (b + 1) / s - 1;
+  return b - slots_upto;
+}
+// position k of the channel-split (logical) order -> position tap * C + c of the reference's tap-major patch order;
+// positions from taps * C on (offsets, padding) are unchanged
+__host__ __device__ inline int tc_split_to_patch_k(int k, int taps, int C) {
+  const int cx = C & ~7, nx = taps * cx;
+  if (k < nx) return (k / cx) * C + k % cx;
+  if (k < taps * C) { const int i = k - nx, cy = C - cx; return (i / cy) * C + cx + i % cy; }
+  return k;
+}
+// physical position k of the packed operand row (length Kp, a multiple of 64) -> reference patch-order position
+__host__ __device__ inline int tc_k_to_patch_k(int k, int taps, int C, int Kp) {
+  const int lb = tc_kb_logical(k / 64, Kp / 64, taps * (C & ~7) / 64);
+  return tc_split_to_patch_k(lb * 64 + k % 64, taps, C);
+}
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <typename T>

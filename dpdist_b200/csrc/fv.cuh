@@ -13,9 +13,12 @@ struct FvParams {
   float c[DPD_MAX_GRID];
   // optional second output for the tensor-core head (flatten = 0 only): fv * split_scale as an fp16 (hi, lo) pair,
   // hi = fp16(s*x), lo = fp16(s*x - hi).  |fv| <= 1 after the per-channel L2 normalisation, so s = 2^15 cannot overflow.
+  // The copy is channel-split for the head's gather: channels 0 .. CX-1 (CX = C & ~7) as [cloud][voxel][CX] at element 0,
+  // channels CX .. C-1 as [cloud][voxel][C - CX] at element split_y_off.
   void* fv_hi;
   void* fv_lo;
   float split_scale;
+  long long split_y_off;
 };
 
 // sign(x) * pow(max(|x|, 1e-12), 0.5)   (reference utils/dpdist_util.py:118-121); sign(0) = 0
@@ -31,7 +34,7 @@ inline void fill_fv_params(FvParams& p, const float* points, int n_clouds, int n
   p.C = full_fv ? DPD_FV_CHANNELS_FULL : DPD_FV_CHANNELS_SMALL;
   p.sigma = sigma;
   for (int i = 0; i < DPD_MAX_GRID; ++i) p.c[i] = i < G ? h_centers[i] : 0.f;
-  p.fv_hi = nullptr; p.fv_lo = nullptr; p.split_scale = 0.f;
+  p.fv_hi = nullptr; p.fv_lo = nullptr; p.split_scale = 0.f; p.split_y_off = 0;
 }
 
 // fv_g8.cu: specialised kernel for G = 8, full FV.  Returns 1 if the configuration is not covered.

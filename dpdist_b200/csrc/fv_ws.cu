@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(NT, 1) fv_g8_ws_kernel(const FvParams p, const
             const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
-            const size_t e4 = (size_t)cloud * (V8 * C20 / 4) + F;
+            // channel-split layout (fv.cuh): quads 0..3 -> X record of 16 channels, quad 4 -> Y record of 4 channels
+            const size_t rec = (size_t)cloud * V8 + g;
+            const size_t e4 = c4 < 4 ? rec * 4 + c4 : (size_t)(p.split_y_off / 4) + rec;
             uint2 uh, ul;
             uh.x = *reinterpret_cast<const unsigned*>(&h01); uh.y = *reinterpret_cast<const unsigned*>(&h23);
             ul.x = *reinterpret_cast<const unsigned*>(&l01); ul.y = *reinterpret_cast<const unsigned*>(&l23);

@@ -319,7 +319,7 @@ extern "C" int dpd_model_forward(const dpd_head_config* cfg, const float* d_poin
   fill_fv_params(p, d_points, cfg->n_clouds, n_points, cfg->G, h_fv_centers, sigma, cfg->C == DPD_FV_CHANNELS_FULL, 0, d_fv);
   int fv_mode = 1;   // a 3DmFV tensor is L2-normalised per channel: |fv| <= 1
   if (is_f16(L.impl)) {
-    tc_fv_split_ptrs(*cfg, true, (char*)d_workspace + W.tc, chunk, &p.fv_hi, &p.fv_lo);
+    tc_fv_split_ptrs(*cfg, true, (char*)d_workspace + W.tc, chunk, &p.fv_hi, &p.fv_lo, &p.split_y_off);
     p.split_scale = TC_FV_UNIT_SCALE;
   }
   bool split_done = false;

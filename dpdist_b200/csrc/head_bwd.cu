@@ -234,15 +234,17 @@ __global__ void __launch_bounds__(NT) simt_gemm_tn_kernel(const TnParams p) {
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias, int Kp,
                                        int K_valid, int N, int E, int unpermute, float* __restrict__ gw, float* __restrict__ gb,
-                                       int nslices) {
+                                       int nslices, int tc_taps, int tc_C) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)Kp * N;
   if (i < total) {
     const int k = (int)(i / N), n = (int)(i % N);
-    if (k < K_valid) {
+    // tc_taps > 0: the partials' rows are in the physical operand order of the fp16 tensor-core gather
+    const int kp = tc_taps > 0 ? tc_k_to_patch_k(k, tc_taps, tc_C, Kp) : k;
+    if (kp < K_valid) {
       float a = 0.f;
       for (int s = 0; s < nslices; ++s) a += partial[(size_t)s * total + i];
-      const int row = unpermute ? (k < E ? 3 + k : k - E) : k;
+      const int row = unpermute ? (kp < E ? 3 + kp : kp - E) : kp;
       gw[(size_t)row * N + n] = a;
     }
   }
@@ -367,10 +369,10 @@ int launch_simt_gemm_tn(const TnParams& p, bool gather, cudaStream_t st) {
 }
 
 int launch_reduce_partials(const float* partial, const float* partial_bias, int Kp, int K_valid, int N, int E, int unpermute,
-                           float* gw, float* gb, cudaStream_t st, int nslices) {
+                           float* gw, float* gb, cudaStream_t st, int nslices, int tc_taps, int tc_C) {
   const size_t total = (size_t)Kp * N;
   DPD_LAUNCH("bwd_reduce_dw", st, reduce_partials_kernel<<<(unsigned)ceil_div<size_t>(total, 256), 256, 0, st>>>(
-      partial, partial_bias, Kp, K_valid, N, E, unpermute, gw, gb, nslices));
+      partial, partial_bias, Kp, K_valid, N, E, unpermute, gw, gb, nslices, tc_taps, tc_C));
   DPD_CUDA_CHECK_LAUNCH("reduce_partials_kernel");
   return 0;
 }

@@ -34,9 +34,10 @@ struct TnParams {
 int launch_simt_gemm_tn(const TnParams& p, bool gather, cudaStream_t st);
 
 // grad[row_map(k)][n] = sum_s partial[s][k][n]; unpermute != 0 maps packed layer-1 rows (patch | offset | pad)
-// back to the reference's (offset | patch) order and drops the padding rows.
+// back to the reference's (offset | patch) order and drops the padding rows; with tc_taps > 0 the patch part of the
+// partials is in the channel-split operand order of the fp16 tensor-core gather (common.cuh tc_k_to_patch_k).
 int launch_reduce_partials(const float* partial, const float* partial_bias, int Kp, int K_valid, int N, int E, int unpermute,
-                           float* gw, float* gb, cudaStream_t st, int nslices = BWD_SLICES);
+                           float* gw, float* gb, cudaStream_t st, int nslices = BWD_SLICES, int tc_taps = 0, int tc_C = 0);
 
 int launch_add_inplace(float* a, const float* b, size_t n, cudaStream_t st);
 

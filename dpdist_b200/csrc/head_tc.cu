@@ -208,11 +208,12 @@ __global__ void __launch_bounds__(1024) colsum_blocks_final_kernel(const float* 
   }
 }
 
-// Per query row: {element offset of its own voxel record in the FV tensor (or -1 past the end), validity bits of the k
+// Per query row: {index of its own voxel record = cloud * V + voxel (or -1 past the end), validity bits of the k
 // taps per axis (bit a: i0 + a - pb in range, bit 8 + a: i1, bit 16 + a: i2)} -- what the forward gather producers
 // compute per tile, prepared once per backward pass for the gather producers of the dW1 product.
 __global__ void rowinfo_kernel(const int32_t* __restrict__ idx, long long row0, int n_query, int G, int Cc, int k, int rows,
-                               int2* __restrict__ out) {
+                               int2* __restrict__ out, int2* __restrict__ lut, int lut_chunks, int E) {
+  if (lut != nullptr && blockIdx.x == 0) build_gather_lut(lut, lut_chunks, Cc, k, G, E, threadIdx.x, blockDim.x);
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
   const int V = G * G * G, pb = (k - 1) >> 1;
@@ -225,7 +226,7 @@ __global__ void rowinfo_kernel(const int32_t* __restrict__ idx, long long row0, 
     mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
     mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
   }
-  out[m] = make_int2((int)(cloud * V * Cc) + v * Cc, (int)mk);
+  out[m] = make_int2((int)(cloud * V) + v, (int)mk);
 }
 
 // rows covered by the active blocks: (index of the last active 128-row block + 1) * 128, clipped to `rows`
@@ -256,15 +257,17 @@ __global__ void debug_scales_kernel(float* __restrict__ sc) {   // one thread (t
 }
 
 
-// Wt_hi/lo[n][k] (fp16, [N, Kp], zero beyond K) from W[k][n] times *scale
+// Wt_hi/lo[n][k] (fp16, [N, Kp], zero beyond K) from W[k][n] times *scale.  With taps > 0 (layer 1 of the 2-CTA kernel)
+// column k of the result is row tc_k_to_patch_k(k) of W: the physical operand order of the gather producers (common.cuh).
 __global__ void transpose_split_f16_kernel(const float* __restrict__ w, int K, int Kp, int N, const float* __restrict__ scale,
-                                           __half* __restrict__ t_hi, __half* __restrict__ t_lo) {
+                                           __half* __restrict__ t_hi, __half* __restrict__ t_lo, int taps, int C) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   const float s = *scale;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int k = k0 + i, n = n0 + threadIdx.x;
-    tile[i][threadIdx.x] = (k < K && n < N) ? w[(size_t)k * N + n] * s : 0.f;
+    const int ks = (taps > 0 && k < Kp) ? tc_k_to_patch_k(k, taps, C, Kp) : k;
+    tile[i][threadIdx.x] = (ks < K && n < N) ? w[(size_t)ks * N + n] * s : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -285,12 +288,25 @@ __global__ void split_f16_kernel(const float* __restrict__ x, size_t n, const fl
   split_half(x[i] * *scale, hi[i], lo[i]);
 }
 
+// 3DmFV tensor [records, C] fp32 -> scaled fp16 (hi, lo) copy in the channel-split layout of the 2-CTA gather:
+// X part [records, CX] (CX = C & ~7) at element 0, Y part [records, C - CX] at element y_off
+__global__ void split_fv_f16_kernel(const float* __restrict__ x, size_t n, int C, long long y_off, const float* __restrict__ scale,
+                                    __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t rec = i / C;
+  const int c = (int)(i - rec * C), cx = C & ~7;
+  const size_t o = c < cx ? rec * cx + c : (size_t)y_off + rec * (C - cx) + (c - cx);
+  split_half(x[i] * *scale, hi[o], lo[o]);
+}
+
 // offsets of rows outside the unit cube are zeroed: their output is masked to 0 anyway (:697-698) and an
 // arbitrary far-away query must not be able to overflow fp16
 __global__ void split_off4_f16_kernel(const float* __restrict__ off, const float* __restrict__ mask, int rows,
                                       const float* __restrict__ scale, __half* __restrict__ hi, __half* __restrict__ lo,
                                       const int32_t* __restrict__ idx, long long row0, int n_query, int G, int Cc, int k,
-                                      int2* __restrict__ rowinfo) {
+                                      int2* __restrict__ rowinfo, int2* __restrict__ lut, int lut_chunks, int E) {
+  if (lut != nullptr && blockIdx.x == 0) build_gather_lut(lut, lut_chunks, Cc, k, G, E, threadIdx.x, blockDim.x);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   if (rowinfo != nullptr) {     // the gather producers' per-row words, same contents as rowinfo_kernel
@@ -304,7 +320,7 @@ __global__ void split_off4_f16_kernel(const float* __restrict__ off, const float
       mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
       mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
     }
-    rowinfo[i] = make_int2((int)(cloud * V * Cc) + v * Cc, (int)mk);
+    rowinfo[i] = make_int2((int)(cloud * V) + v, (int)mk);
   }
   const float s = mask[i] != 0.f ? *scale : 0.f;
 #pragma unroll
@@ -325,11 +341,9 @@ __global__ void merge_f16_kernel(const __half* __restrict__ hi, const __half* __
 }
 
 // output layer finish for the fused layer-3/4 kernel: sums the per-(N-tile, half) partial dot products in
-// fixed order, adds b4, relu6(x)/3 and the in-cube mask (utils/dpdist_util.py:690-691, 697-698).  With `perm` the GEMM
-// rows were visited in class-sorted order: row r of part4 belongs to query perm[r].
+// fixed order, adds b4, relu6(x)/3 and the in-cube mask (utils/dpdist_util.py:690-691, 697-698).
 __global__ void head_out_finish_kernel(const float4* __restrict__ part4, int nslots, const float* __restrict__ b4,
-                                       const float* __restrict__ mask, float* __restrict__ out, int M,
-                                       const int32_t* __restrict__ perm) {
+                                       const float* __restrict__ mask, float* __restrict__ out, int M) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -337,102 +351,13 @@ __global__ void head_out_finish_kernel(const float4* __restrict__ part4, int nsl
     const float4 v = part4[(size_t)row * nslots + i];
     s0 += v.x; s1 += v.y; s2 += v.z;
   }
-  const int orow = perm ? perm[row] : row;
+  const int orow = row;
   const float m = mask[orow];
   out[(size_t)orow * 3 + 0] = fminf(fmaxf(s0 + b4[0], 0.f), 6.f) / 3.0f * m;
   out[(size_t)orow * 3 + 1] = fminf(fmaxf(s1 + b4[1], 0.f), 6.f) / 3.0f * m;
   out[(size_t)orow * 3 + 2] = fminf(fmaxf(s2 + b4[2], 0.f), 6.f) / 3.0f * m;
 }
 
-// ---------------------------------------------------------------------------------------------
-// structurally-zero K-blocks of layer 1 (inference)
-// ---------------------------------------------------------------------------------------------
-// extract_volume_patches pads with zeros (utils/dpdist_util.py:922-924, 932-957): for a query whose voxel has
-// i0 < pb the a0 slabs 0 .. pb-i0-1 of its patch are zero, for i0 > G-1-(k-1-pb) the last i0+(k-1-pb)-(G-1) are.  The
-// operand's K order is a0-major, so those are a prefix / suffix of the patch part of the row.  Class of a row =
-// pb - (zero prefix slabs) + (zero suffix slabs), in [0, 2 pb'] : sorted ascending, the zero prefix shrinks and the zero
-// suffix grows along the rows, and a 256-row tile can skip the K-blocks that are zero for its first / last row's class.
-__device__ __forceinline__ void slab_zeros(int i0, int G, int k, int* pre, int* suf) {
-  const int pb = (k - 1) >> 1;
-  *pre = max(0, pb - i0);
-  *suf = max(0, i0 + (k - 1 - pb) - (G - 1));
-}
-constexpr int SORT_THREADS = 1024, SORT_MAX_CLASSES = 2 * DPD_MAX_GRID + 1;
-
-__device__ __forceinline__ int row_class(const int32_t* idx, int r, int rows, int G, int k, int mid) {
-  if (r >= rows) return -1;
-  int pre, suf;
-  slab_zeros(idx[r] / (G * G), G, k, &pre, &suf);
-  return mid - pre + suf;
-}
-
-// Stable counting sort of the rows by class in three small launches: per-block class counts, a scan over
-// (class major, block minor), and a scatter whose in-block ranks come from warp ballots (thread order = row order).
-__global__ void __launch_bounds__(SORT_THREADS) class_count_kernel(const int32_t* __restrict__ idx, int rows, int G, int k, int ncls,
-                                                                  int* __restrict__ hist) {
-  const int r = blockIdx.x * SORT_THREADS + threadIdx.x;
-  const int c = row_class(idx, r, rows, G, k, ncls / 2);
-  for (int j = 0; j < ncls; ++j) {
-    const int n = __syncthreads_count(c == j);
-    if (threadIdx.x == 0) hist[j * gridDim.x + blockIdx.x] = n;
-  }
-}
-__global__ void class_scan_kernel(int* __restrict__ hist, int n) {      // exclusive scan in place, n = ncls * blocks (small)
-  __shared__ int part[SORT_THREADS];
-  const int t = threadIdx.x, per = (n + SORT_THREADS - 1) / SORT_THREADS;
-  const int lo = min(n, t * per), hi = min(n, lo + per);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += hist[i];
-  part[t] = s;
-  __syncthreads();
-  if (t == 0) { int run = 0; for (int i = 0; i < SORT_THREADS; ++i) { const int v = part[i]; part[i] = run; run += v; } }
-  __syncthreads();
-  int run = part[t];
-  for (int i = lo; i < hi; ++i) { const int v = hist[i]; hist[i] = run; run += v; }
-}
-__global__ void __launch_bounds__(SORT_THREADS) class_scatter_kernel(const int32_t* __restrict__ idx, int rows, int G, int k, int ncls,
-                                                                    const int* __restrict__ offs, int32_t* __restrict__ perm) {
-  __shared__ int warp_cnt[SORT_MAX_CLASSES][32];
-  const int r = blockIdx.x * SORT_THREADS + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = row_class(idx, r, rows, G, k, ncls / 2);
-  int my_rank = 0;
-  for (int j = 0; j < ncls; ++j) {
-    const unsigned m = __ballot_sync(0xffffffffu, c == j);
-    if (c == j) my_rank = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) warp_cnt[j][warp] = __popc(m);
-  }
-  __syncthreads();
-  if (c >= 0) {
-    int base = offs[c * gridDim.x + blockIdx.x];
-    for (int w = 0; w < warp; ++w) base += warp_cnt[c][w];
-    perm[base + my_rank] = r;
-  }
-}
-
-// tile_range[t] = {lo, hi, tail_lo, 0}: K-blocks [lo, hi) and [tail_lo, num_kb) can be non-zero for the rows of tile t.
-// One warp per tile: min / max over all of its rows (sorted rows make the ranges tight, any order keeps them correct).
-__global__ void tile_range_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ perm, int rows, int G, int k, int C,
-                                  int num_kb, int4* __restrict__ tile_range) {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int ntiles = (rows + 2 * BM - 1) / (2 * BM);
-  if (t >= ntiles) return;
-  const int slab = k * k * C, E = k * slab;
-  const int tail_lo = min(E / 64, num_kb);                       // the block that holds the end of the patch and the offsets
-  int lo = tail_lo, hi = 0;
-  for (int r = t * 2 * BM + lane; r < min(rows, (t + 1) * 2 * BM); r += 32) {
-    int pre, suf;
-    slab_zeros(idx[perm[r]] / (G * G), G, k, &pre, &suf);
-    lo = min(lo, (pre * slab) / 64);
-    hi = max(hi, (E - suf * slab + 63) / 64);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-  }
-  hi = max(lo, min(hi, tail_lo));
-  if (lane == 0) tile_range[t] = make_int4(lo, hi, tail_lo, 0);
-}
 
 // ---------------------------------------------------------------------------------------------
 // launch
@@ -496,21 +421,9 @@ static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const C
   return 0;
 }
 
-// 2-CTA (cta_group::2) fp16x3 kernel: 256x256 tiles on CTA pairs.  DPD_TC_2CTA=0 selects the single-CTA kernel.
-static bool use_2cta() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DPD_TC_2CTA"); v = e ? (atoi(e) != 0) : 1; }
-  return v != 0;
-}
-
-// DPD_TC_ZSKIP=1 sorts the rows of an inference chunk by voxel boundary class and skips the structurally-zero K-blocks of
-// layer 1 per tile.  Off by default: 8.2 % fewer MMAs and gathers on the bench distribution, but the class-sorted rows no
-// longer share clouds within a tile, the gather's L1 / L2 locality drops (DRAM reads 97 -> 209 MB per launch) and the step
-// time does not move (profiles/ncu_r2_summary.md section 3).  Read per call: tools/ab_env.py alternates it in one process.
-static bool zskip_env() {
-  const char* e = getenv("DPD_TC_ZSKIP");
-  return e ? (atoi(e) != 0) : false;
-}
+// The fp16x3 path always runs on the 2-CTA (cta_group::2) kernel, 256x256 tiles on CTA pairs: the fp16 copy of the 3DmFV
+// tensor is stored in the layout its gather producers read.  The single-CTA kernel serves the 3xTF32 format.
+static bool use_2cta() { return true; }
 
 // DPD_TC_FUSE_L4=0 keeps the separate output-layer kernel (A/B measurements)
 static bool fuse_l4() {
@@ -528,7 +441,6 @@ struct BwdExtras {
   const int* k_limit = nullptr;
   long long slice_stride = 0;
   unsigned* absmax_bits = nullptr;
-  const int2* rowinfo = nullptr;    // gather + mn_major (dW1): per-row gather info, see rowinfo_kernel
   int lut_chunks = 0;
   int mn_major = 0;          // A [K, M] and B [K, N] row-major (K = reduction): D = A^T . B
   unsigned long long mn_rows = 0;   // valid rows of A and B in that case
@@ -573,6 +485,8 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   const bool gather_mn = gather && bx && bx->mn_major;
   { const char* e = getenv("DPD_TC_EPI_BACKOFF"); ka.epi_backoff_ns = e ? (unsigned)atoi(e) : 0u; }
   { const char* e = getenv("DPD_TC_DBG"); ka.dbg = e ? atoi(e) : 0; }
+  // forward products only (bx == nullptr): the backward's chain of products keeps the short segments
+  { const char* e = getenv("DPD_TC_SEG_HEAD"); ka.seg_head = bx ? 0 : (e ? atoi(e) : 5); }
   if (g) {
     ka.g = *g;
     if (gather && !gather_mn) {   // valid operand length E + 3; everything from there to K is zero padding
@@ -584,7 +498,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   if (bx) {
     DPD_REQUIRE((!gather || gather_mn) && !split && part4 == nullptr, DPD_E_UNSUPPORTED,
                 "tc gemm2: backward modes need the fp32-output kernel (gather only with MN-major operands)");
-    ka.rowinfo = bx->rowinfo; ka.lut_chunks = bx->lut_chunks; ka.g_rows = (int)bx->mn_rows;
+    ka.lut_chunks = bx->lut_chunks; ka.g_rows = (int)bx->mn_rows;
     ka.mode = bx->mode; ka.relu_bits_in = bx->relu_bits_in; ka.active = bx->active; ka.k_limit = bx->k_limit;
     ka.slices = bx->slices; ka.slice_stride = bx->slice_stride; ka.absmax_bits = bx->absmax_bits; ka.mn_major = bx->mn_major;
     // K-blocks per slice: a multiple of the promotion segment so that segments never straddle slices
@@ -592,8 +506,7 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
     tiles *= bx->slices > 1 ? bx->slices : 1;
   }
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  const size_t lut_entries = gather ? (gather_mn ? (size_t)bx->lut_chunks : (size_t)(K / 4)) : 0;
-  const size_t smem = 1024 + (size_t)STAGES2 * STAGE2_BYTES + sizeof(SharedCtl2) + 2 * lut_entries * sizeof(uint32_t);
+  const size_t smem = 1024 + (gather ? (size_t)GATHER_RING_BYTES : (size_t)STAGES2 * STAGE2_BYTES) + sizeof(SharedCtl2);
   const int gm = gather ? 1 : 0;
   const size_t smem_use = smem;
   auto go = [&]() -> int {
@@ -628,10 +541,10 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
 static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo,
                   int N, const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
                   const GatherArgs* g, cudaStream_t st, uint4* relu_bits_out = nullptr) {
-  if (f16 && use_2cta())
+  if (f16)
     return launch2(gather, a_hi, a_lo, M, K, bt_hi, bt_lo, N, bias, out0, out1, split, acc_scale, out_scale, g, st, nullptr, nullptr,
                    nullptr, relu_bits_out);
-  const int kb = f16 ? 64 : 32;
+  const int kb = 32;
   DPD_REQUIRE(K % kb == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm: need K %% %d == 0, N %% 256 == 0 (K=%d N=%d)", kb, K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm: K=%d too large", K);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -652,10 +565,9 @@ static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int
   const int tiles = ceil_div(M, BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SharedCtl) + 2 * (size_t)(K / 4) * sizeof(uint32_t);
-  if (gather) return f16 ? launch_t<true, true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st)
-                         : launch_t<true, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
-  return f16 ? launch_t<false, true>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st)
-             : launch_t<false, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
+  // the single-CTA kernel serves the 3xTF32 format only (its F16 flavour read the interleaved fp16 copy that no longer exists)
+  if (gather) return launch_t<true, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
+  return launch_t<false, false>(ta_hi, ta_lo, tb_hi, tb_lo, ka, grid, smem, st);
 }
 
 }  // namespace tc
@@ -700,7 +612,7 @@ TcBlob tc_blob_layout(const dpd_head_config& c, bool f16) {
 }
 constexpr int TC_DW_SLICES = 9;       // dW2 / dW3: 16 tiles x 9 slices = 144 work items on 74 clusters (1.95 waves)
 constexpr int TC_DW1_SLICES = 11;     // dW1: 40 tiles x 11 = 440 (5.95 waves)
-struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, rinfo, part, cpart, rb1, rb2, bsc, scales, total; };
+struct TcWs { size_t fvh, fvl, o4h, o4l, xh, xl, yh, yl, gh, gl, rinfo, lut, part, cpart, rb1, rb2, bsc, scales, total; };
 TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   TcWs w; size_t o = 0; const size_t e = f16 ? 2 : 4;
   const size_t nfv = (size_t)c.n_clouds * c.G * c.G * c.G * c.C;
@@ -711,6 +623,8 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   if (f16) { w.yh = o; o += up256(rows * (size_t)c.H * e); w.yl = o; o += up256(rows * (size_t)c.H * e); }
   w.rinfo = o;
   if (f16) o += up256(rows * 8);      // per-row gather info (forward: split_off4_f16_kernel, backward: rowinfo_kernel)
+  w.lut = o;
+  if (f16) o += up256((size_t)tc::MAX_LUT * 8);   // gather LUT of the 2-CTA kernel, {code, delta} per 4-element chunk
   w.gh = w.gl = w.part = w.cpart = w.rb1 = w.rb2 = w.bsc = o;
   if (f16 && tc_train(c)) {   // backward: (hi, lo) of the upstream gradient, partials
     const size_t act = up256(rows * (size_t)c.H * e), Kp1 = kp1_of(c, true);
@@ -727,6 +641,9 @@ TcWs tc_ws_layout(const dpd_head_config& c, bool f16, size_t rows) {
   w.total = o; return w;
 }
 }  // namespace
+
+// element offset of the Y part (channels C & ~7 .. C-1) in the channel-split fp16 copy of the 3DmFV tensor
+long long tc_fv_y_off(const dpd_head_config& c) { return (long long)c.n_clouds * c.G * c.G * c.G * (c.C & ~7); }
 
 size_t tc_packed_bytes(const dpd_head_config& c, bool f16) { return tc_blob_layout(c, f16).total; }
 size_t tc_workspace_bytes(const dpd_head_config& c, bool f16, size_t rows) { return tc_ws_layout(c, f16, rows).total; }
@@ -760,12 +677,13 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
   DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 32), 1024, 0, st>>>(w1p, Kp1_src, H, pb + tc::P_C1_BITS));
   DPD_LAUNCH("tc_pack_stats", st, tc::col_l1_max_kernel<<<ceil_div(H, 32), 1024, 0, st>>>(w2, H, H, pb + tc::P_C2_BITS));
   DPD_LAUNCH("tc_pack_stats", st, tc::weight_scales_kernel<<<1, 1, 0, st>>>(ps));
+  // W1: K-major rows in the channel-split operand order of the gather producers
   DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(Kp1, 32)), blk, 0, st>>>(
-      w1p, Kp1_src, Kp1, H, ps + tc::P_W1, (__half*)(base + b.w1h), (__half*)(base + b.w1l)));
+      w1p, Kp1_src, Kp1, H, ps + tc::P_W1, (__half*)(base + b.w1h), (__half*)(base + b.w1l), c.k * c.k * c.k, c.C));
   DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
-      w2, H, H, H, ps + tc::P_W2, (__half*)(base + b.w2h), (__half*)(base + b.w2l)));
+      w2, H, H, H, ps + tc::P_W2, (__half*)(base + b.w2h), (__half*)(base + b.w2l), 0, 0));
   DPD_LAUNCH("tc_pack_w", st, tc::transpose_split_f16_kernel<<<dim3(ceil_div(H, 32), ceil_div(H, 32)), blk, 0, st>>>(
-      w3, H, H, H, ps + tc::P_W3, (__half*)(base + b.w3h), (__half*)(base + b.w3l)));
+      w3, H, H, H, ps + tc::P_W3, (__half*)(base + b.w3h), (__half*)(base + b.w3l), 0, 0));
   if (tc_train(c) && (c.flags & DPD_HEAD_INPUT_GRAD)) {
     // rows [Kp1_src, Kp1) of the kernel-order operand are padding: zero them, split the rest in place
     DPD_CUDA_CALL(cudaMemsetAsync(base + b.w1nh, 0, (size_t)Kp1 * H * 2, st));
@@ -824,16 +742,18 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
     int Mo;       // rows of the weight gradient in kernel order
     if (layer == 1) {
       tc::GatherArgs ga;
-      ga.perm = nullptr; ga.tile_range = nullptr; ga.rowinfo = nullptr;
+      ga.rowinfo = nullptr; ga.lut = nullptr; ga.y_off = 0;
       ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g->idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g->row0;
+      ga.y_off = tc_fv_y_off(c);
       ga.n_query = g->n_query; ga.G = g->G; ga.C = g->C; ga.k = g->k; ga.E = g->E;
       // the gather warps of the GEMM kernel assemble the MN-major A tiles on the fly: nothing is materialised
       int2* rinfo = (int2*)(ws + w.rinfo);
       DPD_LAUNCH("bwd_rowinfo", st, tc::rowinfo_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
-          g->idx, g->row0, g->n_query, g->G, g->C, g->k, rows, rinfo));
+          g->idx, g->row0, g->n_query, g->G, g->C, g->k, rows, rinfo, (int2*)(ws + w.lut), Kp1 / 4, g->E));
+      ga.lut = (const int2*)(ws + w.lut);
       DPD_CUDA_CHECK_LAUNCH("rowinfo_kernel");
       tc::BwdExtras bx;
-      bx.mn_major = 1; bx.mn_rows = (unsigned long long)rows; bx.rowinfo = rinfo; bx.lut_chunks = Kp1 / 4;
+      bx.mn_major = 1; bx.mn_rows = (unsigned long long)rows; ga.rowinfo = rinfo; bx.lut_chunks = Kp1 / 4;
       const int by_rows1 = Mp / (64 * 8) > 0 ? Mp / (64 * 8) : 1;
       bx.mode = 2; bx.slices = by_rows1 < TC_DW1_SLICES ? by_rows1 : TC_DW1_SLICES; bx.k_limit = extent;
       bx.slice_stride = (long long)Kp1 * H;
@@ -842,7 +762,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
                             nullptr, nullptr, &bx))) return rc;
       DPD_LAUNCH("bwd_colsum", st, tc::colsum_blocks_final_kernel<<<H / 64, 1024, 0, st>>>(cpart, extent, H, gb));
       DPD_CUDA_CHECK_LAUNCH("tc_backward_layer colsum");
-      return launch_reduce_partials(part1, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices);
+      return launch_reduce_partials(part1, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices, g->k * g->k * g->k, g->C);
     } else {
       ah = (const __half*)(ws + (layer == 3 ? w.yh : w.xh)); al = (const __half*)(ws + (layer == 3 ? w.yl : w.xl)); Mo = H;
     }
@@ -858,7 +778,7 @@ int tc_backward_layer(const dpd_head_config& c, int layer, const void* tc_blob, 
     // gb = column sums of dZ over the active rows: per-block partials came out of the split pass
     DPD_LAUNCH("bwd_colsum", st, tc::colsum_blocks_final_kernel<<<H / 64, 1024, 0, st>>>(cpart, extent, H, gb));
     DPD_CUDA_CHECK_LAUNCH("tc_backward_layer colsum");
-    if (layer == 1) rc = launch_reduce_partials(part, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices);
+    if (layer == 1) rc = launch_reduce_partials(part, nullptr, Kp1, g->E + 3, H, g->E, 1, gw, nullptr, st, bx.slices, g->k * g->k * g->k, g->C);
     else rc = launch_reduce_partials(part, nullptr, H, H, H, 0, 0, gw, nullptr, st, bx.slices);
     if (rc) return rc;
   }
@@ -936,16 +856,17 @@ int tc_prepare_fv(const dpd_head_config& c, bool f16, const float* fv, const voi
   // with the unit bound in1 = max(|fv|max, 1) = 1 exactly as the measured path would find for a 3DmFV tensor
   DPD_LAUNCH("tc_scales", st, tc::activation_scales_kernel<<<1, 1, 0, st>>>(sc, (const float*)((const char*)tc_blob + b.scales), mode != 0));
   if (mode != 2)
-    DPD_LAUNCH("tc_split_fv", st, tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
-        fv, nfv, sc + tc::S_A1, (__half*)(ws + w.fvh), (__half*)(ws + w.fvl)));
+    DPD_LAUNCH("tc_split_fv", st, tc::split_fv_f16_kernel<<<(unsigned)ceil_div<size_t>(nfv, 256), 256, 0, st>>>(
+        fv, nfv, c.C, tc_fv_y_off(c), sc + tc::S_A1, (__half*)(ws + w.fvh), (__half*)(ws + w.fvl)));
   DPD_CUDA_CHECK_LAUNCH("tc_prepare_fv f16");
   return 0;
 }
 
-void tc_fv_split_ptrs(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, void** hi, void** lo) {
+void tc_fv_split_ptrs(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, void** hi, void** lo, long long* y_off) {
   const TcWs w = tc_ws_layout(c, f16, ws_rows);
   *hi = (char*)tc_ws + w.fvh;
   *lo = (char*)tc_ws + w.fvl;
+  *y_off = tc_fv_y_off(c);
 }
 
 int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, const float* mask, int rows, size_t ws_rows,
@@ -959,8 +880,9 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
   const int H = c.H, Kp1 = kp1_of(c, f16);
   const float* sc = (const float*)(ws + w.scales);
   tc::GatherArgs ga;
-  ga.perm = nullptr; ga.tile_range = nullptr; ga.rowinfo = nullptr;
+  ga.rowinfo = nullptr; ga.lut = nullptr; ga.y_off = 0;
   ga.fv_hi = ws + w.fvh; ga.fv_lo = ws + w.fvl; ga.idx = g.idx; ga.off4_hi = ws + w.o4h; ga.off4_lo = ws + w.o4l; ga.row0 = g.row0;
+  ga.y_off = f16 ? tc_fv_y_off(c) : 0;
   ga.n_query = g.n_query; ga.G = g.G; ga.C = g.C; ga.k = g.k; ga.E = g.E;
   float* out3 = h3_out ? h3_out : ha;
   int rc;
@@ -974,29 +896,10 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
   } else {
     DPD_LAUNCH("tc_split_off", st, tc::split_off4_f16_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
         g.offset, mask, rows, sc + tc::S_A1, (__half*)(ws + w.o4h), (__half*)(ws + w.o4l),
-        g.idx, g.row0, g.n_query, g.G, g.C, g.k, (int2*)(ws + w.rinfo)));
+        g.idx, g.row0, g.n_query, g.G, g.C, g.k, (int2*)(ws + w.rinfo), (int2*)(ws + w.lut), Kp1 / 4, g.E));
     DPD_CUDA_CHECK_LAUNCH("split_off4_f16_kernel");
-    ga.rowinfo = (const int2*)(ws + w.rinfo);
-    // Inference with the fused output layer: rows sorted by the boundary class of their voxel so that whole tiles can skip
-    // the structurally-zero K-blocks of layer 1; the permutation is undone by head_out_finish_kernel.  `hb` is not used by
-    // this path and holds perm [rows] and tile_range.
+    ga.rowinfo = (const int2*)(ws + w.rinfo); ga.lut = (const int2*)(ws + w.lut);
     const bool fused = fused_out != nullptr && tc::use_2cta() && tc::fuse_l4();
-    const int32_t* perm = nullptr;
-    if (fused && !tc_train(c) && tc::zskip_env() && rows >= 2048 && g.k >= 3 && (g.k * g.k * g.C) % 4 == 0) {
-      int32_t* pm = (int32_t*)hb;
-      int4* tr = (int4*)(hb + round_up<size_t>((size_t)rows, 256));
-      const int pbk = (g.k - 1) >> 1, ncls = 2 * (g.k - 1 - pbk > pbk ? g.k - 1 - pbk : pbk) + 1;
-      const int nsb = ceil_div(rows, tc::SORT_THREADS);
-      int* hist = (int*)(tr + ceil_div(rows, 2 * tc::BM) + 1);
-      DPD_LAUNCH("tc_class_sort", st, tc::class_count_kernel<<<nsb, tc::SORT_THREADS, 0, st>>>(g.idx, rows, g.G, g.k, ncls, hist));
-      DPD_LAUNCH("tc_class_sort", st, tc::class_scan_kernel<<<1, tc::SORT_THREADS, 0, st>>>(hist, ncls * nsb));
-      DPD_LAUNCH("tc_class_sort", st, tc::class_scatter_kernel<<<nsb, tc::SORT_THREADS, 0, st>>>(g.idx, rows, g.G, g.k, ncls, hist, pm));
-      const int ntiles = ceil_div(rows, 2 * tc::BM);
-      DPD_LAUNCH("tc_tile_range", st, tc::tile_range_kernel<<<ceil_div(ntiles * 32, 128), 128, 0, st>>>(g.idx, pm, rows, g.G, g.k, g.C, Kp1 / 64, tr));
-      DPD_CUDA_CHECK_LAUNCH("class_sort / tile_range");
-      ga.perm = pm; ga.tile_range = tr;
-      perm = pm;
-    }
     // layer 1: gathered A -> (xh, xl) scaled by sA2; layer 2 -> (yh, yl) scaled by sA3; layer 3 -> fp32
     const bool bits = tc_train(c) && tc::use_2cta();    // ReLU' bit masks for the tensor-core backward
     if ((rc = tc::launch(true, true, nullptr, nullptr, rows, Kp1, blob + b.w1h, blob + b.w1l, H, b1, ws + w.xh, ws + w.xl, 1,
@@ -1012,7 +915,7 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
       if ((rc = tc::launch2(false, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, h3_out, nullptr, 0,
                             sc + tc::S_ACC3, nullptr, nullptr, st, w4, part4))) return rc;
       DPD_LAUNCH("head_out_finish", st, tc::head_out_finish_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
-          (const float4*)part4, nslots, b4, mask, fused_out, rows, perm));
+          (const float4*)part4, nslots, b4, mask, fused_out, rows));
       DPD_CUDA_CHECK_LAUNCH("head_out_finish_kernel");
       *h3 = nullptr;
       return 0;
@@ -1069,7 +972,7 @@ int tc_debug_gemm(const float* a, int M, int K, const float* w, int N, const flo
   tc::absmax_kernel<<<256, 256, 0, st>>>(w, (size_t)N * K, (unsigned*)sc + 5);
   tc::debug_scales_kernel<<<1, 1, 0, st>>>(sc);
   tc::split_f16_kernel<<<(unsigned)ceil_div<size_t>((size_t)M * K, 256), 256, 0, st>>>(a, (size_t)M * K, sc + 0, ah, al);
-  tc::transpose_split_f16_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), dim3(32, 8), 0, st>>>(w, K, K, N, sc + 1, bh, bl);
+  tc::transpose_split_f16_kernel<<<dim3(ceil_div(N, 32), ceil_div(K, 32)), dim3(32, 8), 0, st>>>(w, K, K, N, sc + 1, bh, bl, 0, 0);
   DPD_CUDA_CHECK_LAUNCH("tc_debug_gemm f16 prep");
   return tc::launch(false, true, ah, al, M, K, bh, bl, N, bias, out, nullptr, 0, sc + 2, nullptr, nullptr, st);
 }

@@ -19,7 +19,9 @@ int tc_pack_weights(const dpd_head_config& c, bool f16, int Kp1_src, const float
 constexpr float TC_FV_UNIT_SCALE = 32768.0f;   // pow2_floor_scale(1): largest power of two s with s*1 <= 32768
 int tc_prepare_fv(const dpd_head_config& c, bool f16, const float* fv, const void* tc_blob, void* tc_ws, size_t ws_rows,
                   cudaStream_t st, int mode = 0);
-void tc_fv_split_ptrs(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, void** hi, void** lo);
+// The fp16 copy is CHANNEL-SPLIT: X part [cloud][voxel][C & ~7] at element 0 of hi / lo, Y part [cloud][voxel][C - (C & ~7)]
+// at element *y_off (head_tc_kernel2.cuh, gather role).
+void tc_fv_split_ptrs(const dpd_head_config& c, bool f16, void* tc_ws, size_t ws_rows, void** hi, void** lo, long long* y_off);
 
 // runs layers 1..3 for `rows` chunk-local rows; *h3 points at the fp32 [rows,H] layer-3 activations.
 // If fused_out != nullptr and the configuration allows it (fp16x3, 2-CTA kernel, inference) the output layer is

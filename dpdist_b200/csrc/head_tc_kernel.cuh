@@ -27,19 +27,42 @@ struct GatherArgs {
   const void* off4_lo;
   long long row0;          // global row of chunk-local row 0
   int n_query, G, C, k, E;
-  // Optional (2-CTA kernel, K-major operand, inference): rows visited in the order perm[] (sorted by the boundary class of
-  // their voxel along i0, class_sort_kernel) and, per 256-row tile, the K-blocks that can be non-zero for any of its rows:
-  // tile_range[t] = {lo, hi, tail_lo, 0} -> K-blocks [lo, hi) and [tail_lo, num_kb).  SAME padding makes the leading /
-  // trailing a0 slabs of the patch of a voxel near the i0 boundary structurally zero; the MMAs and the gather of those
-  // K-blocks are skipped by every warp role.
-  const int32_t* perm;
-  const int4* tile_range;
-  // per query row {element offset of its voxel record in the FV tensor, tap validity bits}: written by the kernel that
-  // splits the offsets (split_off4_f16_kernel), so the gather warps load two words per row at a tile boundary instead of
-  // decoding the voxel index (64-bit division by n_query, three divisions by G, 3k range tests per row: the timeline showed
-  // the MMAs idle for ~26 k cycles per tile behind that decode, profiles/ncu_r3_summary.md)
+  // 2-CTA fp16 kernel: fv_hi / fv_lo hold the CHANNEL-SPLIT copy (see the gather role in head_tc_kernel2.cuh): the X part
+  // [cloud][voxel][C & ~7] at element 0 and the Y part [cloud][voxel][C - (C & ~7)] at element y_off
+  long long y_off;
+  // per query row {index of its voxel record = cloud * V + voxel (or -1), tap validity bits}: written by the kernel that
+  // splits the offsets (split_off4_f16_kernel) / rowinfo_kernel, so the gather warps load two words per row at a tile
+  // boundary instead of decoding the voxel index (64-bit division by n_query, three divisions by G, 3k range tests per
+  // row: the timeline showed the MMAs idle for ~26 k cycles per tile behind that decode, profiles/ncu_r3_summary.md)
   const int2* rowinfo;
+  // 2-CTA kernel: {code, delta} per 4-element chunk of the operand row (build_gather_lut), in global memory
+  const int2* lut;
 };
+
+// Gather LUT of the 2-CTA kernel, entry q = the 4 operand elements [4q, 4q + 4) of a row in the physical operand order
+// (common.cuh: channel-split [taps x CX | taps x CY | offsets | padding] with the K-blocks permuted): code = tap coordinates a0 | a1 << 8 | a2 << 16 (| LUT_YSEL for the Y part),
+// LUT_OFFS for the offset chunk, LUT_ZERO for padding; delta = element offset of the chunk relative to the row's own voxel
+// record inside the X (stride CX) or Y (stride CY) part.  Called by the kernels that prepare the per-row words.
+__device__ __forceinline__ void build_gather_lut(int2* __restrict__ lut, int nchunks, int C, int k, int G, int E, int tid, int nthreads) {
+  const int cx = C & ~7, ech = E / 4, pb = (k - 1) >> 1, nxc = k * k * k * cx / 4;
+  const int nkb = nchunks / 16, nX = k * k * k * cx / 64;
+  for (int qp = tid; qp < nchunks; qp += nthreads) {
+    const int q = tc_kb_logical(qp / 16, nkb, nX) * 16 + qp % 16;      // physical -> logical chunk (K-block permutation)
+    uint32_t code;
+    int32_t delta = 0;
+    if (q < ech) {
+      const bool isy = q >= nxc;
+      const int cw = isy ? C - cx : cx;
+      const int e = (isy ? q - nxc : q) * 4, j = e / cw, part = e - j * cw;
+      const int a2 = j % k, a1 = (j / k) % k, a0 = j / (k * k);
+      code = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16) | (isy ? LUT_YSEL : 0u);
+      delta = (((a0 - pb) * G + (a1 - pb)) * G + (a2 - pb)) * cw + part;
+    } else {
+      code = (q == ech) ? LUT_OFFS : LUT_ZERO;
+    }
+    lut[qp] = make_int2((int)code, delta);
+  }
+}
 
 struct KernelArgs {
   int M, N, num_kb;        // rows, output features, K-blocks
@@ -67,7 +90,6 @@ struct KernelArgs {
   long long slice_stride;  // elements between the fp32 outputs of consecutive slices
   // gather kernel in MN-major mode (dW1 = patches^T . dZ1): per-row {FV element offset or -1, tap validity mask} prepared
   // by rowinfo_kernel, number of 4-element chunks of the operand row, number of valid rows
-  const int2* rowinfo;
   int lut_chunks;
   int g_rows;
   int mn_major;            // 2-CTA kernel: A and B are [reduction, M] / [reduction, N] row-major arrays (MN-major operands):
@@ -77,6 +99,7 @@ struct KernelArgs {
   int last_ks;             // 2-CTA kernel: K-steps (16 elements) of the LAST K-block that hold data; 0 = all four.  The padded
                            // tail of the layer-1 operand (2503 -> 2560) is zero on both sides: its MMAs are not issued.
   unsigned long long* trace;   // timing experiments only (DPD_TC_TRACE): per-role clock64 stamps of cluster 0's leader CTA, see tools/tc_trace.py
+  int seg_head;            // 2-CTA kernel: K-blocks in each of the first two promotion segments of an item (0 = SEG)
   int dbg;                 // timing experiments only (DPD_TC_DBG): 1 = staged gather without the copies, 2 = without the proxy fence
   unsigned epi_backoff_ns; // 2-CTA kernel: nanosleep between the epilogue warps' polls of seg_full (0 = tight spin)
   GatherArgs g;

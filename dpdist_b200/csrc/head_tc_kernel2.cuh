@@ -5,12 +5,22 @@
 // traffic per MMA drops by a third - the single-CTA kernel is bound by exactly that traffic
 // (10-11 TB/s of L2->SM reads at 54 % tensor-pipe utilisation, profiles/ncu_r1_summary.md).
 //
+// Shared memory.  Dense layers: STAGES2 = 3 stages of (A tile 32 KB, B half tile 32 KB).  Layer 1 (gathered A): a ring of
+// NA2 = 4 gathered A tiles and a ring of 3 B half tiles, 224 KB: the chain  K-block retired -> gather issue (1.1 k cycles)
+// -> last cp.async byte lands (2.2 k)  is longer than the two K-blocks of look-ahead a 3-deep ring gives, while the TMA
+// chain of the weight tiles (1.7 k) fits; the timeline (profiles/ncu_r3_summary.md) showed the MMAs waiting 20 % of the
+// time for the gathered tile and never for B.  The gather LUT lives in global memory to make room.
+//
 // Synchronisation (leader = cluster rank 0, peer = rank 1):
-//   full[s]      leader only.  Completed by: leader TMA thread (arrive.expect_tx for BOTH CTAs' bytes),
-//                the TMA loads of both CTAs (cta_group::2 loads signal the leader's barrier), and for layer 1
-//                the leader's gather threads (cp.async arrive) + one relay arrive from the peer.
-//   gfull[s]     peer only (layer 1): the peer's gather threads; a relay thread forwards it to full[s].
-//   empty[s], seg_full[b]   both CTAs, completed by tcgen05.commit ... multicast::cluster from the leader.
+//   full[s]      leader only.  Completed by: leader TMA thread (arrive.expect_tx for BOTH CTAs' bytes) and the TMA loads
+//                of both CTAs (cta_group::2 loads signal the leader's barrier).  Dense: A and B; layer 1: B only.
+//   afull[a]     leader only (layer 1): gathered A tile a complete: the leader's gather threads (cp.async arrive) + one
+//                relay arrive from the peer.
+//   gfull[a]     peer only (layer 1): the peer's gather threads; a relay thread forwards it to afull[a].
+//   done[d]      both CTAs: K-block number d (mod DONE_RING) of this cluster's sequence has been consumed (ONE
+//                tcgen05.commit ... multicast::cluster per K-block).  The TMA producer reuses a B buffer after the K-block
+//                STAGES2 back is done, the gather producers an A buffer after the K-block NA2 back is done.
+//   seg_full[b]  both CTAs, completed by tcgen05.commit ... multicast::cluster from the leader.
 //   seg_empty[b] leader only: 8 local + 8 remote epilogue-warp arrivals.
 #pragma once
 #include "head_tc_kernel.cuh"
@@ -19,12 +29,15 @@ namespace dpd {
 namespace tc {
 
 constexpr int STAGES2 = 3;
+constexpr int NA2 = 4;                                       // layer 1: ring of gathered A tiles
+constexpr int DONE_RING = 12;                                // a common multiple of STAGES2 and NA2
 constexpr int B_HALF = (BN / 2) * ROW_BYTES;                 // 16 KB
 constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF;        // 64 KB
+constexpr int GATHER_RING_BYTES = NA2 * 2 * A_TILE + STAGES2 * 2 * B_HALF;   // 224 KB
 constexpr uint32_t IDESC_F16_M256 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 struct __align__(8) SharedCtl2 {
-  uint64_t full[STAGES2], empty[STAGES2], gfull[STAGES2], seg_full[2], seg_empty[2];
+  uint64_t full[STAGES2], done[DONE_RING], afull[NA2], gfull[NA2], seg_full[2], seg_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -109,8 +122,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   constexpr int STG = STAGES2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  SharedCtl2* ctl = (SharedCtl2*)(smem + STG * STAGE2_BYTES);
-  uint32_t* lut = (uint32_t*)(ctl + 1);
+  SharedCtl2* ctl = (SharedCtl2*)(smem + (GATHER ? GATHER_RING_BYTES : STG * STAGE2_BYTES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
@@ -148,25 +160,29 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (tracing && trace_n < 65536) args.trace[(size_t)role * 65536 + trace_n++] = (tag << 56) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFFFull);
   };
 
-  // K-blocks an item visits: a main run [lo, lo + n_main) and a tail run [tail_lo, ...), cnt in total.  Forward: all of
-  // them, or (layer 1 with row classes) the tile's non-zero range; backward: the item's K slice.
-  struct Seq { int lo, n_main, tail_lo, cnt; };
+  // K-blocks an item visits: [lo, lo + cnt).  Forward: all of them; backward weight gradients: the item's K slice.
+  struct Seq { int lo, cnt; };
   auto make_seq = [&](int mt, int sl) -> Seq {
-    Seq q;
-    if (GATHER && !args.mn_major && args.g.tile_range != nullptr) {
-      const int4 r = __ldg(args.g.tile_range + mt);
-      q.lo = r.x; q.n_main = r.y - r.x; q.tail_lo = r.z; q.cnt = q.n_main + (args.num_kb - r.z);
-    } else {
-      const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
-      q.lo = kb_lo; q.n_main = max(kb_hi - kb_lo, 0); q.tail_lo = 0; q.cnt = q.n_main;
-    }
+    (void)mt;
+    const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
+    Seq q; q.lo = kb_lo; q.cnt = max(kb_hi - kb_lo, 0);
     return q;
   };
-  auto kb_of = [&](const Seq& q, int i) -> int { return i < q.n_main ? q.lo + i : q.tail_lo + (i - q.n_main); };
+  auto kb_of = [&](const Seq& q, int i) -> int { return q.lo + i; };
+  // Promotion segments of an item (MMA issuer and epilogue walk the same list): SEG K-blocks each, except that the first
+  // two segments of a long item take args.seg_head (forward layers only: longer unpromoted runs cost accuracy).  The issuer can run two segments (the two TMEM buffers) ahead of the
+  // epilogue, and at a tile boundary the epilogue is busy storing the previous tile for 12-15 k cycles: two segments of 4
+  // K-blocks (12.3 k cycles) were not enough, the timeline showed the issuer waiting 7-18 % of the time for a free buffer.
+  const int seg_head = args.seg_head > SEG ? args.seg_head : SEG;
+  auto seg_end = [&](int i0, int cnt) -> int { return min(i0 + ((cnt >= 4 * SEG && i0 < 2 * seg_head) ? seg_head : SEG), cnt); };
 
-  auto stage_ptr = [&](int s, int which) -> uint8_t* {   // which: 0 Ah, 1 Al, 2 Bh (half), 3 Bl (half)
-    uint8_t* b = smem + s * STAGE2_BYTES;
-    return which == 0 ? b : which == 1 ? b + A_TILE : which == 2 ? b + 2 * A_TILE : b + 2 * A_TILE + B_HALF;
+  // operand buffers; which: 0 hi, 1 lo.  Dense: ring position s of both; layer 1: A ring position / B ring position.
+  auto a_ptr = [&](int sa, int which) -> uint8_t* {
+    return GATHER ? smem + sa * (2 * A_TILE) + which * A_TILE : smem + sa * STAGE2_BYTES + which * A_TILE;
+  };
+  auto b_ptr = [&](int sb, int which) -> uint8_t* {
+    return GATHER ? smem + NA2 * (2 * A_TILE) + sb * (2 * B_HALF) + which * B_HALF
+                  : smem + sb * STAGE2_BYTES + 2 * A_TILE + which * B_HALF;
   };
 
   if (warp == 0 && lane == 0) {
@@ -174,10 +190,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (!GATHER) { prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STG; ++s) {
-      mbar_init(&ctl->full[s], GATHER ? (2 + NUM_GATHER_THREADS) : 1);
-      mbar_init(&ctl->empty[s], 1);
-      mbar_init(&ctl->gfull[s], NUM_GATHER_THREADS);
+    for (int s = 0; s < STG; ++s) mbar_init(&ctl->full[s], 1);
+    for (int d = 0; d < DONE_RING; ++d) mbar_init(&ctl->done[d], 1);
+    for (int a = 0; a < NA2; ++a) {
+      mbar_init(&ctl->afull[a], NUM_GATHER_THREADS + 1);
+      mbar_init(&ctl->gfull[a], NUM_GATHER_THREADS);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&ctl->seg_full[a], 1);
@@ -186,25 +203,6 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg2(&ctl->tmem_base, TMEM_COLS);
-  if (GATHER) {
-    const int nchunks = args.mn_major ? args.lut_chunks : args.num_kb * CHUNKS;
-    const int Cc = args.g.C, kk = args.g.k, ech = args.g.E / 4, Gg = args.g.G, pbb = (args.g.k - 1) >> 1;
-    int32_t* lutd = (int32_t*)(lut + nchunks);
-    for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
-      uint32_t code;
-      int32_t delta = 0;
-      if (q < ech) {
-        const int e = q * 4, j = e / Cc, part = e - j * Cc;
-        const int a2 = j % kk, a1 = (j / kk) % kk, a0 = j / (kk * kk);
-        code = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16);
-        delta = (((a0 - pbb) * Gg + (a1 - pbb)) * Gg + (a2 - pbb)) * Cc + part;
-      } else {
-        code = (q == ech) ? LUT_OFFS : LUT_ZERO;
-      }
-      lut[q] = code;
-      lutd[q] = delta;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
@@ -215,7 +213,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     reg_dec<56>();
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
-      int s = 0; uint32_t ph = 0;
+      int s = 0, cnt = 0, wd = 0; uint32_t wph = 0;
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         const int mt = t / num_n_tiles, nt = t % num_n_tiles;
         if (item_skipped(mt)) continue;
@@ -225,7 +223,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         for (int i = 0; i < q.cnt; ++i) {
           const int kb = kb_of(q, i);
           stamp(0, 14);
-          mbar_wait(&ctl->empty[s], ph ^ 1);
+          if (cnt >= STG) {                 // the K-block that last used this buffer has been consumed
+            mbar_wait(&ctl->done[wd], wph);
+            if (++wd == DONE_RING) { wd = 0; wph ^= 1; }
+          }
+          ++cnt;
           stamp(0, 15);
           const uint32_t lbar = map_to_rank(smem_u32(&ctl->full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&ctl->full[s], 2 * (GATHER ? 2 * B_HALF : STAGE2_BYTES));
@@ -234,50 +236,54 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             // 128 N columns are two such groups each (8 KB apart in the tile).  GATHER: A comes from the gather warps.
 #pragma unroll
             for (int gI = 0; gI < 2; ++gI) {
-              tma_load_2d_cg2(stage_ptr(s, 2) + gI * 8192, &tm_b_hi, lbar, brow0 + gI * 64, kb * KB_ELEMS);
-              tma_load_2d_cg2(stage_ptr(s, 3) + gI * 8192, &tm_b_lo, lbar, brow0 + gI * 64, kb * KB_ELEMS);
+              tma_load_2d_cg2(b_ptr(s, 0) + gI * 8192, &tm_b_hi, lbar, brow0 + gI * 64, kb * KB_ELEMS);
+              tma_load_2d_cg2(b_ptr(s, 1) + gI * 8192, &tm_b_lo, lbar, brow0 + gI * 64, kb * KB_ELEMS);
               if (!GATHER) {
-                tma_load_2d_cg2(stage_ptr(s, 0) + gI * 8192, &tm_a_hi, lbar, row0 + gI * 64, kb * KB_ELEMS);
-                tma_load_2d_cg2(stage_ptr(s, 1) + gI * 8192, &tm_a_lo, lbar, row0 + gI * 64, kb * KB_ELEMS);
+                tma_load_2d_cg2(a_ptr(s, 0) + gI * 8192, &tm_a_hi, lbar, row0 + gI * 64, kb * KB_ELEMS);
+                tma_load_2d_cg2(a_ptr(s, 1) + gI * 8192, &tm_a_lo, lbar, row0 + gI * 64, kb * KB_ELEMS);
               }
             }
           } else {
-            tma_load_2d_cg2(stage_ptr(s, 2), &tm_b_hi, lbar, kb * KB_ELEMS, brow0);
-            tma_load_2d_cg2(stage_ptr(s, 3), &tm_b_lo, lbar, kb * KB_ELEMS, brow0);
+            tma_load_2d_cg2(b_ptr(s, 0), &tm_b_hi, lbar, kb * KB_ELEMS, brow0);
+            tma_load_2d_cg2(b_ptr(s, 1), &tm_b_lo, lbar, kb * KB_ELEMS, brow0);
             if (!GATHER) {
-              tma_load_2d_cg2(stage_ptr(s, 0), &tm_a_hi, lbar, kb * KB_ELEMS, row0);
-              tma_load_2d_cg2(stage_ptr(s, 1), &tm_a_lo, lbar, kb * KB_ELEMS, row0);
+              tma_load_2d_cg2(a_ptr(s, 0), &tm_a_hi, lbar, kb * KB_ELEMS, row0);
+              tma_load_2d_cg2(a_ptr(s, 1), &tm_a_lo, lbar, kb * KB_ELEMS, row0);
             }
           }
-          if (++s == STG) { s = 0; ph ^= 1; }
+          if (++s == STG) s = 0;
         }
       }
     } else if (warp == 1 && lane == 0 && leader) {
       // ===================== MMA issuer (leader only) =====================
-      int s = 0; uint32_t ph = 0;
+      int s = 0; uint32_t ph = 0;          // B ring (dense: the stage ring)
+      int sa = 0; uint32_t pha = 0;        // layer 1: ring of gathered A tiles
+      int d = 0;                           // done ring
       int sb = 0; uint32_t sb_ph = 0;
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         if (item_skipped(t / num_n_tiles)) continue;
         const Seq q = make_seq(t / num_n_tiles, sl);
-        for (int i0 = 0; i0 < q.cnt; i0 += SEG) {
+        for (int i0 = 0, i1; i0 < q.cnt; i0 = i1) {
+          i1 = seg_end(i0, q.cnt);
           stamp(1, 4);
           mbar_wait_cluster(&ctl->seg_empty[sb], sb_ph ^ 1);
           stamp(1, 5);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(sb * BN);
           uint32_t accumulate = 0;
-          const int i1 = min(i0 + SEG, q.cnt);
           for (int i = i0; i < i1; ++i) {
             const int kb = kb_of(q, i);
             stamp(1, 1);
             mbar_wait_cluster(&ctl->full[s], ph);
+            if (GATHER) mbar_wait_cluster(&ctl->afull[sa], pha);
             stamp(1, 2);
             tc_fence_after();
             const bool mn = args.mn_major != 0;
-            const uint64_t ah = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 0)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 0)));
-            const uint64_t al = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 1)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 1)));
-            const uint64_t bh = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 2)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 2)));
-            const uint64_t bl = mn ? make_desc_mn_sw128(smem_u32(stage_ptr(s, 3)), 8192) : make_desc_sw128(smem_u32(stage_ptr(s, 3)));
+            const int as = GATHER ? sa : s;
+            const uint64_t ah = mn ? make_desc_mn_sw128(smem_u32(a_ptr(as, 0)), 8192) : make_desc_sw128(smem_u32(a_ptr(as, 0)));
+            const uint64_t al = mn ? make_desc_mn_sw128(smem_u32(a_ptr(as, 1)), 8192) : make_desc_sw128(smem_u32(a_ptr(as, 1)));
+            const uint64_t bh = mn ? make_desc_mn_sw128(smem_u32(b_ptr(s, 0)), 8192) : make_desc_sw128(smem_u32(b_ptr(s, 0)));
+            const uint64_t bl = mn ? make_desc_mn_sw128(smem_u32(b_ptr(s, 1)), 8192) : make_desc_sw128(smem_u32(b_ptr(s, 1)));
             // K-major: a K step of 16 elements is 32 bytes along the row; MN-major: 16 reduction rows of 128 bytes
             const uint64_t kstep = mn ? (uint64_t)(16 * 128 >> 4) : (uint64_t)2;
             const uint32_t idesc = IDESC_F16_M256 | (mn ? (3u << 15) : 0u);      // a_major, b_major = MN
@@ -291,25 +297,27 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               umma_f16_cg2(d_tmem, ah + o, bh + o, idesc, 1);
               accumulate = 1;
             }
-            umma_commit_cg2_mcast(&ctl->empty[s]);
+            umma_commit_cg2_mcast(&ctl->done[d]);
             stamp(1, 3);
             if (++s == STG) { s = 0; ph ^= 1; }
+            if (GATHER && ++sa == NA2) { sa = 0; pha ^= 1; }
+            if (++d == DONE_RING) d = 0;
           }
           umma_commit_cg2_mcast(&ctl->seg_full[sb]);
           if (++sb == 2) { sb = 0; sb_ph ^= 1; }
         }
       }
     } else if (GATHER && warp == 3 && lane == 0 && !leader) {
-      // ===================== gather relay (peer only): local gfull[s] -> leader's full[s] =====================
-      int s = 0; uint32_t ph = 0;
+      // ===================== gather relay (peer only): local gfull[a] -> leader's afull[a] =====================
+      int sa = 0; uint32_t pha = 0;
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         if (item_skipped(t / num_n_tiles)) continue;
         const Seq q = make_seq(t / num_n_tiles, sl);
         for (int i = 0; i < q.cnt; ++i) {
-          mbar_wait(&ctl->gfull[s], ph);
+          mbar_wait(&ctl->gfull[sa], pha);
           fence_proxy_async();
-          mbar_arrive_remote(map_to_rank(smem_u32(&ctl->full[s]), 0));
-          if (++s == STG) { s = 0; ph ^= 1; }
+          mbar_arrive_remote(map_to_rank(smem_u32(&ctl->afull[sa]), 0));
+          if (++sa == NA2) { sa = 0; pha ^= 1; }
         }
       }
     }
@@ -333,7 +341,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < EPI_COLS; ++j) sum[j] = 0.f;
       }
-      for (int i0 = 0; i0 < sq.cnt; i0 += SEG) {
+      for (int i0 = 0; i0 < sq.cnt; i0 = seg_end(i0, sq.cnt)) {
         if (e == 0 && lane == 0) stamp(2, 6);
         mbar_wait_backoff(&ctl->seg_full[sb], sb_ph, args.epi_backoff_ns);
         if (e == 0 && lane == 0) stamp(2, 7);
@@ -431,13 +439,22 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const bool upper = (ql >> 1) != 0;          // lanes 2,3 of the quad take the words of group j+1
         uint32_t rb[4] = {0u, 0u, 0u, 0u};          // ReLU' bits of this thread's 128 outputs, bit index = index into sum[]
         const bool want_bits = args.relu_bits_out != nullptr;
+        // all 16 bias pairs of the thread's columns in flight at once (the registers of the TMEM staging are free here):
+        // loaded one pair per column group they cost eight L2 round trips per tile on the critical path of the store phase
+        float2 br[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) br[i] = __ldg(reinterpret_cast<const float2*>(args.bias + col0 + i * 8));
 #pragma unroll
         for (int cg = 0; cg < 2; ++cg) {
 #pragma unroll
           for (int jp = 0; jp < 4; ++jp) {
+            if (cg == 0 && jp == 2) {     // half of the first column group's sums are dead by now: room for the second group's pairs
+#pragma unroll
+              for (int i = 8; i < 16; ++i) br[i] = __ldg(reinterpret_cast<const float2*>(args.bias + col0 + 64 + (i & 7) * 8));
+            }
             const int colj = col0 + cg * 64 + (2 * jp) * 8;
-            const float2 b0 = __ldg(reinterpret_cast<const float2*>(args.bias + colj));
-            const float2 b1 = __ldg(reinterpret_cast<const float2*>(args.bias + colj + 8));
+            const float2 b0 = br[cg * 8 + 2 * jp];
+            const float2 b1 = br[cg * 8 + 2 * jp + 1];
 #pragma unroll
             for (int rh = 0; rh < 2; ++rh) {
 #pragma unroll
@@ -528,20 +545,33 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
   } else if (GATHER) {
     // ===================== patch-gather producers (both CTAs, own 128 rows) =====================
+    // Source: the fp16 (hi, lo) copy of the 3DmFV tensor in its CHANNEL-SPLIT layout: X = [cloud][voxel][CX] (CX = C & ~7
+    // channels: 16 of 20, 32-byte records, one aligned sector per tap) and Y = [cloud][voxel][C - CX] at element offset
+    // g.y_off.  The operand row is ordered [taps x CX | taps x CY | offsets | 0], W1 is packed to match (tc_pack_weights).
+    // X units (8 elements) are 16 bytes, 16-byte aligned, never straddle a tap: they are copied with cp.async.cg 16
+    // (SASS LDGSTS.BYPASS.128), which goes straight from L2 to shared memory.  The 8-byte cp.async.ca of the former
+    // interleaved layout allocated every line in L1 first: three data-bank passes per byte (L1 fill, L1 read, shared
+    // write) on the array the tensor core reads its operands from (profiles/ncu_r3_summary.md, gather micro-benchmark).
     reg_dec<96>();
     const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
     const GatherArgs& g = args.g;
-    const int G = g.G, Cc = g.C, pb = (g.k - 1) >> 1;
-    const int V = G * G * G;
+    const int cx = g.C & ~7, cy = g.C - cx;
     const uint8_t* fv_hi = (const uint8_t*)g.fv_hi; const uint8_t* fv_lo = (const uint8_t*)g.fv_lo;
     const uint8_t* o4_hi = (const uint8_t*)g.off4_hi; const uint8_t* o4_lo = (const uint8_t*)g.off4_lo;
-    const uint32_t lut_s = smem_u32(lut), lutd_s = lut_s + (uint32_t)((args.mn_major ? args.lut_chunks : args.num_kb * CHUNKS)) * 4u;
-    int s = 0; uint32_t ph = 0;
+    int sa = 0, cnt = 0, wd = 0; uint32_t wph = 0;
+    // reuse of A buffer sa: the K-block NA2 back in this cluster's sequence has been consumed
+    auto wait_free = [&]() {
+      if (cnt >= NA2) {
+        mbar_wait(&ctl->done[wd], wph);
+        if (++wd == DONE_RING) { wd = 0; wph ^= 1; }
+      }
+      ++cnt;
+    };
     if (args.mn_major) {
       // dW1 = patches^T . dZ1: the tile's M range is a range of operand elements, fixed per tile, so this thread's
-      // 4-element chunk (tap, channel quad) is decoded once per tile; what changes per stage are the 64 reduction rows,
-      // whose {FV offset, tap validity} come precomputed (rowinfo).  Tile layout = MN-major: group (64 elements) major,
-      // then reduction row (128 bytes), 16-byte units XOR-swizzled with the row.
+      // 4-element chunk (array, tap, channel quad) is decoded once per tile; what changes per stage are the 64 reduction
+      // rows, whose {voxel record, tap validity} come precomputed (rowinfo).  Tile layout = MN-major: group (64 elements)
+      // major, then reduction row (128 bytes), 16-byte units XOR-swizzled with the row.
       const int chunk32 = p & 31, sub = p >> 5;                 // 32 chunk columns (2 groups x 16) x 4 row lanes
       const uint32_t c16 = (uint32_t)((chunk32 & 15) >> 1);
       const uint32_t dst0 = (uint32_t)((chunk32 >> 4) * 8192 + (chunk32 & 1) * 8);
@@ -549,21 +579,21 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int mt = t / num_n_tiles;
         const int q = (mt * 2 * BM + (int)rank * BM) / 4 + chunk32;
         uint32_t code = LUT_ZERO; int32_t delta = 0;
-        if (q < args.lut_chunks) {
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)q * 4u));
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)q * 4u));
-        }
+        if (q < args.lut_chunks) { const int2 e = __ldg(g.lut + q); code = (uint32_t)e.x; delta = e.y; }
         const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
+        const bool isy = code < LUT_OFFS && (code & LUT_YSEL) != 0;
+        const int stride = isy ? cy : cx;
+        const long long base = isy ? g.y_off : 0;
         const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           int2 ri[16];
 #pragma unroll
           for (int it = 0; it < 16; ++it) {
             const int m = kb * KB_ELEMS + it * 4 + sub;
-            ri[it] = (m < args.g_rows) ? __ldg(args.rowinfo + m) : make_int2(-1, 0);
+            ri[it] = (m < args.g_rows) ? __ldg(g.rowinfo + m) : make_int2(-1, 0);
           }
-          mbar_wait(&ctl->empty[s], ph ^ 1);
-          const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
+          wait_free();
+          const uint32_t a_hi = smem_u32(a_ptr(sa, 0)), a_lo = smem_u32(a_ptr(sa, 1));
 #pragma unroll
           for (int it = 0; it < 16; ++it) {
             const int r = it * 4 + sub;
@@ -571,7 +601,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             if (code < LUT_OFFS) {
               const uint32_t mk = (uint32_t)ri[it].y;
               const uint32_t ok = (ri[it].x >= 0 ? 1u : 0u) & (mk >> s0) & (mk >> s1) & (mk >> s2) & 1u;
-              const size_t el = ok ? (size_t)(ri[it].x + delta) : 0;
+              const size_t el = ok ? (size_t)(base + (long long)ri[it].x * stride + delta) : 0;
               const uint32_t nbytes = ok ? 4u * ELEM : 0u;
               cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
               cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
@@ -583,86 +613,88 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
               cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
             }
           }
-          cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
-          if (++s == STG) { s = 0; ph ^= 1; }
+          cp_async_arrive_noinc(leader ? &ctl->afull[sa] : &ctl->gfull[sa]);
+          if (++sa == NA2) sa = 0;
         }
       }
     } else {
-      // K-major operand (forward).  Thread (sub = p / 16, chunk = p % 16) copies the 8-byte chunk `chunk` of rows
-      // it * 8 + sub; half a warp covers one row's 128 bytes contiguously.
-      constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / CHUNKS;
-      constexpr int NIT = BM / ROWS_PER_IT;
-      const int sub = p / CHUNKS, chunk = p % CHUNKS;
-      const uint32_t dst0 = (uint32_t)(sub * 128 + (chunk & 1) * 8);
-      const uint32_t c16 = (uint32_t)(chunk >> 1);
+      // K-major operand (forward).  Thread (sub = p / 8, u = p % 8) fills the 16-byte unit u of rows it * 16 + sub; a
+      // quarter warp covers one row's 128 bytes.  The leading num_xkb K-blocks consist of X units only.
+      constexpr int UNITS = CHUNKS / 2;                       // 8 units of 8 elements per row and K-block
+      constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / UNITS; // 16
+      constexpr int NIT = BM / ROWS_PER_IT;                   // 8
+      const int sub = p / UNITS, u = p % UNITS;
+      const int num_xkb = (g.k * g.k * g.k * cx) / KB_ELEMS;
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         const int mt = t / num_n_tiles;
         if (item_skipped(mt)) continue;
         const int row_base = mt * 2 * BM + (int)rank * BM;
-        int32_t rel[NIT];
+        int32_t relx[NIT], rely[NIT];      // element offset of the row's own voxel record in the X / Y part
         uint32_t rmsk[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
           const int m = row_base + it * ROWS_PER_IT + sub;
-          rel[it] = -1; rmsk[it] = 0;
+          relx[it] = -1; rely[it] = -1; rmsk[it] = 0;
           if (m < args.M) {
-            const int mo = g.perm ? __ldg(g.perm + m) : m;
-            if (g.rowinfo != nullptr) {
-              const int2 ri = __ldg(g.rowinfo + mo);
-              rel[it] = ri.x; rmsk[it] = (uint32_t)ri.y;
-            } else {
-              const long long cloud = (g.row0 + mo) / g.n_query;
-              const int v = __ldg(g.idx + mo);
-              rel[it] = (int32_t)(cloud * V * Cc) + v * Cc;
-              const int i0 = v / (G * G), i1 = (v / G) % G, i2 = v % G;
-              uint32_t mk = 0;
-              for (int a = 0; a < g.k; ++a) {
-                mk |= ((unsigned)(i0 + a - pb) < (unsigned)G ? 1u : 0u) << a;
-                mk |= ((unsigned)(i1 + a - pb) < (unsigned)G ? 1u : 0u) << (8 + a);
-                mk |= ((unsigned)(i2 + a - pb) < (unsigned)G ? 1u : 0u) << (16 + a);
-              }
-              rmsk[it] = mk;
-            }
+            const int2 ri = __ldg(g.rowinfo + m);
+            relx[it] = ri.x * cx; rely[it] = (int32_t)g.y_off + ri.x * cy; rmsk[it] = (uint32_t)ri.y;
           }
         }
         const Seq q = make_seq(mt, 0);
         for (int qi = 0; qi < q.cnt; ++qi) {
           const int kb = kb_of(q, qi);
-          uint32_t code; int32_t delta;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(lut_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(delta) : "r"(lutd_s + (uint32_t)(kb * CHUNKS + chunk) * 4u));
+          // the unit's two chunks: {code, delta} x 2 = one 16-byte load from the LUT (built by build_gather_lut)
+          const int4 le = __ldg(reinterpret_cast<const int4*>(g.lut + kb * CHUNKS + 2 * u));
+          const uint32_t code[2] = {(uint32_t)le.x, (uint32_t)le.z};
+          const int32_t delta[2] = {le.y, le.w};
           if (p == 0) stamp(3, 11);
-          mbar_wait(&ctl->empty[s], ph ^ 1);
+          wait_free();
           if (p == 0) stamp(3, 12);
-          const uint32_t a_hi = smem_u32(stage_ptr(s, 0)), a_lo = smem_u32(stage_ptr(s, 1));
-          if (code < LUT_OFFS) {
-            const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
+          const uint32_t a_hi = smem_u32(a_ptr(sa, 0)), a_lo = smem_u32(a_ptr(sa, 1));
+          if (tc_kb_logical(kb, args.num_kb, num_xkb) < num_xkb) {
+            // X units: one 16-byte bypass copy per unit and array
+            const uint32_t s0 = code[0] & 255u, s1 = 8u + ((code[0] >> 8) & 255u), s2 = 16u + ((code[0] >> 16) & 255u);
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
               const int r = it * ROWS_PER_IT + sub;
-              const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+              const uint32_t dst = (uint32_t)(r * 128) + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4);
               const uint32_t ok = (rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u;
-              const size_t el = ok ? (size_t)(rel[it] + delta) : 0;
-              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
-              cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
-              cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
+              const size_t el = ok ? (size_t)(relx[it] + delta[0]) : 0;
+              const uint32_t nbytes = ok ? 8u * ELEM : 0u;
+              cp_async16(a_hi + dst, fv_hi + el * ELEM, nbytes);
+              cp_async16(a_lo + dst, fv_lo + el * ELEM, nbytes);
             }
           } else {
+            // mixed K-blocks (last X units, the Y part, the offsets, the zero padding): two 8-byte chunks per unit
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-              const int r = it * ROWS_PER_IT + sub;
-              const uint32_t dst = dst0 + (uint32_t)(it * ROWS_PER_IT * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
-              const bool ok = (code == LUT_OFFS) && rel[it] >= 0;
-              size_t m = ok ? (size_t)row_base + r : 0;
-              if (ok && g.perm) m = (size_t)__ldg(g.perm + m);
-              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
-              cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
-              cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint32_t c = code[hf];
+              const uint32_t s0 = c & 255u, s1 = 8u + ((c >> 8) & 255u), s2 = 16u + ((c >> 16) & 255u);
+              const bool isy = (c & LUT_YSEL) != 0;
+#pragma unroll
+              for (int it = 0; it < NIT; ++it) {
+                const int r = it * ROWS_PER_IT + sub;
+                const uint32_t dst = (uint32_t)(r * 128) + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4) + (uint32_t)hf * 8u;
+                const uint8_t *sh, *sl2;
+                bool ok;
+                if (c < LUT_OFFS) {
+                  ok = ((rmsk[it] >> s0) & (rmsk[it] >> s1) & (rmsk[it] >> s2) & 1u) != 0;
+                  const size_t el = ok ? (size_t)((isy ? rely[it] : relx[it]) + delta[hf]) : 0;
+                  sh = fv_hi + el * ELEM; sl2 = fv_lo + el * ELEM;
+                } else {
+                  ok = (c == LUT_OFFS) && relx[it] >= 0;
+                  const size_t m = ok ? (size_t)row_base + r : 0;
+                  sh = o4_hi + m * 4 * ELEM; sl2 = o4_lo + m * 4 * ELEM;
+                }
+                const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+                cp_async8(a_hi + dst, sh, nbytes);
+                cp_async8(a_lo + dst, sl2, nbytes);
+              }
             }
           }
-          cp_async_arrive_noinc(leader ? &ctl->full[s] : &ctl->gfull[s]);
+          cp_async_arrive_noinc(leader ? &ctl->afull[sa] : &ctl->gfull[sa]);
           if (p == 0) stamp(3, 13);
-          if (++s == STG) { s = 0; ph ^= 1; }
+          if (++sa == NA2) sa = 0;
         }
       }
     }

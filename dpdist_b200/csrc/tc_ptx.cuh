@@ -17,6 +17,7 @@ constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_GATHER_THREADS = 128;
 constexpr uint32_t LUT_ZERO = 0xFFFFFFFFu, LUT_OFFS = 0xFFFFFFFEu;
+constexpr uint32_t LUT_YSEL = 1u << 24;   // 2-CTA kernel: the chunk comes from the Y part (channels CX..C-1) of the fp16 3DmFV copy
 constexpr int MAX_LUT = 4096;  // chunks of 4 floats: Kp1 <= 16384
 
 // ---------------------------------------------------------------------------------------------
