@@ -416,7 +416,7 @@ static int launch2_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const C
     DPD_CUDA_CALL(cudaFuncSetAttribute(tc_gemm2_kernel<GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
   }
   DPD_LAUNCH(GM ? (ka.mn_major ? "tc_gemm2_bwd_dw1_gather_f16" : "tc_gemm2_gather_l1_f16") : (ka.part4 ? "tc_gemm2_dense_l3_l4_f16" : (ka.mode == 1 ? "tc_gemm2_bwd_dx_f16" : (ka.mode == 2 ? "tc_gemm2_bwd_dw_f16" : "tc_gemm2_dense_f16"))), st,
-             tc_gemm2_kernel<GM><<<grid, GM ? 512 : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
+             tc_gemm2_kernel<GM><<<grid, GM ? THREADS2_GATHER : 384, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, ka));
   DPD_CUDA_CHECK_LAUNCH("tc_gemm2_kernel");
   return 0;
 }
@@ -486,7 +486,8 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   { const char* e = getenv("DPD_TC_EPI_BACKOFF"); ka.epi_backoff_ns = e ? (unsigned)atoi(e) : 0u; }
   { const char* e = getenv("DPD_TC_DBG"); ka.dbg = e ? atoi(e) : 0; }
   // forward products only (bx == nullptr): the backward's chain of products keeps the short segments
-  { const char* e = getenv("DPD_TC_SEG_HEAD"); ka.seg_head = bx ? 0 : (e ? atoi(e) : 5); }
+  // (layer 1: 6 of its 40 K-blocks; the store phase of its epilogue is longer, its warps share the schedulers with the gather)
+  { const char* e = getenv("DPD_TC_SEG_HEAD"); ka.seg_head = bx ? 0 : (e ? atoi(e) : (gather ? 6 : 5)); }
   if (g) {
     ka.g = *g;
     if (gather && !gather_mn) {   // valid operand length E + 3; everything from there to K is zero padding

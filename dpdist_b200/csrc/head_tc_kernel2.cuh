@@ -30,6 +30,8 @@ namespace tc {
 
 constexpr int STAGES2 = 3;
 constexpr int NA2 = 4;                                       // layer 1: ring of gathered A tiles
+constexpr int NGT2 = 256;                                    // layer 1: gather threads (8 warps; the single-CTA kernel has 4)
+constexpr int THREADS2_GATHER = (4 + NUM_EPI_WARPS) * 32 + NGT2;   // 640
 constexpr int DONE_RING = 12;                                // a common multiple of STAGES2 and NA2
 constexpr int B_HALF = (BN / 2) * ROW_BYTES;                 // 16 KB
 constexpr int STAGE2_BYTES = 2 * A_TILE + 2 * B_HALF;        // 64 KB
@@ -110,10 +112,10 @@ __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols)
 }
 
 // warps: 0 TMA producer | 1 MMA issuer (leader) | 2 TMEM allocator | 3 gather relay (peer, layer 1) |
-//        4-11 epilogue | 12-15 gather (layer 1)
+//        4-11 epilogue | 12-19 gather (layer 1)
 // GM: 0 = dense (A by TMA) | 1 = A gathered from the 3DmFV records by cp.async (layer 1 and its weight gradient)
 template <int GM>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM ? 512 : 384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM ? THREADS2_GATHER : 384, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 const KernelArgs args) {
@@ -193,8 +195,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     for (int s = 0; s < STG; ++s) mbar_init(&ctl->full[s], 1);
     for (int d = 0; d < DONE_RING; ++d) mbar_init(&ctl->done[d], 1);
     for (int a = 0; a < NA2; ++a) {
-      mbar_init(&ctl->afull[a], NUM_GATHER_THREADS + 1);
-      mbar_init(&ctl->gfull[a], NUM_GATHER_THREADS);
+      mbar_init(&ctl->afull[a], NGT2 + 1);
+      mbar_init(&ctl->gfull[a], NGT2);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&ctl->seg_full[a], 1);
@@ -210,7 +212,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp < 4) {
-    reg_dec<56>();
+    if (GATHER) reg_dec<48>(); else reg_dec<56>();     // layer 1: the CTA owns 640 x 96 registers = 4 x 48 + 8 x 176 + 8 x 40 (x 32 lanes)
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
       int s = 0, cnt = 0, wd = 0; uint32_t wph = 0;
@@ -552,8 +554,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     // (SASS LDGSTS.BYPASS.128), which goes straight from L2 to shared memory.  The 8-byte cp.async.ca of the former
     // interleaved layout allocated every line in L1 first: three data-bank passes per byte (L1 fill, L1 read, shared
     // write) on the array the tensor core reads its operands from (profiles/ncu_r3_summary.md, gather micro-benchmark).
-    reg_dec<96>();
-    const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;
+    reg_dec<40>();
+    const int p = threadIdx.x - (4 + NUM_EPI_WARPS) * 32;      // 0 .. NGT2 - 1
     const GatherArgs& g = args.g;
     const int cx = g.C & ~7, cy = g.C - cx;
     const uint8_t* fv_hi = (const uint8_t*)g.fv_hi; const uint8_t* fv_lo = (const uint8_t*)g.fv_lo;
@@ -572,7 +574,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       // 4-element chunk (array, tap, channel quad) is decoded once per tile; what changes per stage are the 64 reduction
       // rows, whose {voxel record, tap validity} come precomputed (rowinfo).  Tile layout = MN-major: group (64 elements)
       // major, then reduction row (128 bytes), 16-byte units XOR-swizzled with the row.
-      const int chunk32 = p & 31, sub = p >> 5;                 // 32 chunk columns (2 groups x 16) x 4 row lanes
+      constexpr int RL = NGT2 / 32, NITM = 64 / RL;              // 8 row lanes, 8 reduction rows per thread and K-block
+      const int chunk32 = p & 31, sub = p >> 5;                 // 32 chunk columns (2 groups x 16) x 8 row lanes
       const uint32_t c16 = (uint32_t)((chunk32 & 15) >> 1);
       const uint32_t dst0 = (uint32_t)((chunk32 >> 4) * 8192 + (chunk32 & 1) * 8);
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
@@ -586,17 +589,17 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const long long base = isy ? g.y_off : 0;
         const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
-          int2 ri[16];
+          int2 ri[NITM];
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int m = kb * KB_ELEMS + it * 4 + sub;
+          for (int it = 0; it < NITM; ++it) {
+            const int m = kb * KB_ELEMS + it * RL + sub;
             ri[it] = (m < args.g_rows) ? __ldg(g.rowinfo + m) : make_int2(-1, 0);
           }
           wait_free();
           const uint32_t a_hi = smem_u32(a_ptr(sa, 0)), a_lo = smem_u32(a_ptr(sa, 1));
 #pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int r = it * 4 + sub;
+          for (int it = 0; it < NITM; ++it) {
+            const int r = it * RL + sub;
             const uint32_t dst = dst0 + (uint32_t)(r * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
             if (code < LUT_OFFS) {
               const uint32_t mk = (uint32_t)ri[it].y;
@@ -618,11 +621,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         }
       }
     } else {
-      // K-major operand (forward).  Thread (sub = p / 8, u = p % 8) fills the 16-byte unit u of rows it * 16 + sub; a
+      // K-major operand (forward).  Thread (sub = p / 8, u = p % 8) fills the 16-byte unit u of rows it * 32 + sub; a
       // quarter warp covers one row's 128 bytes.  The leading num_xkb K-blocks consist of X units only.
       constexpr int UNITS = CHUNKS / 2;                       // 8 units of 8 elements per row and K-block
-      constexpr int ROWS_PER_IT = NUM_GATHER_THREADS / UNITS; // 16
-      constexpr int NIT = BM / ROWS_PER_IT;                   // 8
+      constexpr int ROWS_PER_IT = NGT2 / UNITS;               // 32
+      constexpr int NIT = BM / ROWS_PER_IT;                   // 4
       const int sub = p / UNITS, u = p % UNITS;
       const int num_xkb = (g.k * g.k * g.k * cx) / KB_ELEMS;
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
