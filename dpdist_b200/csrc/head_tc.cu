@@ -450,7 +450,7 @@ struct BwdExtras {
 static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo, int N,
                    const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
                    const GatherArgs* g, cudaStream_t st, const float* w4 = nullptr, float* part4 = nullptr,
-                   const BwdExtras* bx = nullptr, uint4* relu_bits_out = nullptr) {
+                   const BwdExtras* bx = nullptr, uint4* relu_bits_out = nullptr, bool long_head = false) {
   DPD_REQUIRE(K % 64 == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm2: need K %% 64 == 0, N %% 256 == 0 (K=%d N=%d)", K, N);
   DPD_REQUIRE(!gather || (bx && bx->mn_major ? bx->lut_chunks : K / 4) <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm2: operand row too long");
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -483,11 +483,9 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
   ka.M = M; ka.N = N; ka.num_kb = K / 64; ka.bias = bias; ka.out0 = out0; ka.out1 = out1; ka.split = split;
   ka.acc_scale = acc_scale; ka.out_scale = out_scale; ka.w4 = w4; ka.part4 = part4; ka.relu_bits_out = relu_bits_out;
   const bool gather_mn = gather && bx && bx->mn_major;
-  { const char* e = getenv("DPD_TC_EPI_BACKOFF"); ka.epi_backoff_ns = e ? (unsigned)atoi(e) : 0u; }
-  { const char* e = getenv("DPD_TC_DBG"); ka.dbg = e ? atoi(e) : 0; }
-  // forward products only (bx == nullptr): the backward's chain of products keeps the short segments
-  // (layer 1: 6 of its 40 K-blocks; the store phase of its epilogue is longer, its warps share the schedulers with the gather)
-  { const char* e = getenv("DPD_TC_SEG_HEAD"); ka.seg_head = bx ? 0 : (e ? atoi(e) : (gather ? 6 : 5)); }
+  // Longer first promotion segments (see seg_end in the kernel): inference forward only.  Training keeps the short
+  // segments everywhere: the gradient tests compare ReLU gates with the fp64 oracle's, and the backward is a chain of products.
+  { const char* e = getenv("DPD_TC_SEG_HEAD"); ka.seg_head = (bx || !long_head) ? 0 : (e ? atoi(e) : (gather ? 6 : 5)); }
   if (g) {
     ka.g = *g;
     if (gather && !gather_mn) {   // valid operand length E + 3; everything from there to K is zero padding
@@ -541,10 +539,10 @@ static int launch2(bool gather, const void* a_hi, const void* a_lo, int M, int K
 // D[M,N] = relu(acc_scale * A[M,K] * B[N,K]^T + bias), operands pre-split (hi, lo); K % kb == 0, N % 256 == 0
 static int launch(bool gather, bool f16, const void* a_hi, const void* a_lo, int M, int K, const void* bt_hi, const void* bt_lo,
                   int N, const float* bias, void* out0, void* out1, int split, const float* acc_scale, const float* out_scale,
-                  const GatherArgs* g, cudaStream_t st, uint4* relu_bits_out = nullptr) {
+                  const GatherArgs* g, cudaStream_t st, uint4* relu_bits_out = nullptr, bool long_head = false) {
   if (f16)
     return launch2(gather, a_hi, a_lo, M, K, bt_hi, bt_lo, N, bias, out0, out1, split, acc_scale, out_scale, g, st, nullptr, nullptr,
-                   nullptr, relu_bits_out);
+                   nullptr, relu_bits_out, long_head);
   const int kb = 32;
   DPD_REQUIRE(K % kb == 0 && N % BN == 0 && M > 0, DPD_E_UNSUPPORTED, "tc gemm: need K %% %d == 0, N %% 256 == 0 (K=%d N=%d)", kb, K, N);
   DPD_REQUIRE(K / 4 <= MAX_LUT, DPD_E_UNSUPPORTED, "tc gemm: K=%d too large", K);
@@ -904,9 +902,9 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
     // layer 1: gathered A -> (xh, xl) scaled by sA2; layer 2 -> (yh, yl) scaled by sA3; layer 3 -> fp32
     const bool bits = tc_train(c) && tc::use_2cta();    // ReLU' bit masks for the tensor-core backward
     if ((rc = tc::launch(true, true, nullptr, nullptr, rows, Kp1, blob + b.w1h, blob + b.w1l, H, b1, ws + w.xh, ws + w.xl, 1,
-                         sc + tc::S_ACC1, sc + tc::S_A2, &ga, st, bits ? (uint4*)(ws + w.rb1) : nullptr))) return rc;
+                         sc + tc::S_ACC1, sc + tc::S_A2, &ga, st, bits ? (uint4*)(ws + w.rb1) : nullptr, !tc_train(c)))) return rc;
     if ((rc = tc::launch(false, true, ws + w.xh, ws + w.xl, rows, H, blob + b.w2h, blob + b.w2l, H, b2, ws + w.yh, ws + w.yl, 1,
-                         sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st, bits ? (uint4*)(ws + w.rb2) : nullptr))) return rc;
+                         sc + tc::S_ACC2, sc + tc::S_A3, nullptr, st, bits ? (uint4*)(ws + w.rb2) : nullptr, !tc_train(c)))) return rc;
     if (fused) {
       // layer 3 with the output layer fused into its epilogue.  Inference: H3 never reaches HBM.  Training (h3_out set):
       // the fp32 activations are stored as well, for the backward pass.  `ha` (not read by this path; the SIMT backward
@@ -914,7 +912,7 @@ int tc_head_layers(const dpd_head_config& c, bool f16, const GatherDesc& g, cons
       const int nslots = 2 * (H / tc::BN);
       float* part4 = ha;
       if ((rc = tc::launch2(false, ws + w.yh, ws + w.yl, rows, H, blob + b.w3h, blob + b.w3l, H, b3, h3_out, nullptr, 0,
-                            sc + tc::S_ACC3, nullptr, nullptr, st, w4, part4))) return rc;
+                            sc + tc::S_ACC3, nullptr, nullptr, st, w4, part4, nullptr, nullptr, !tc_train(c)))) return rc;
       DPD_LAUNCH("head_out_finish", st, tc::head_out_finish_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(
           (const float4*)part4, nslots, b4, mask, fused_out, rows));
       DPD_CUDA_CHECK_LAUNCH("head_out_finish_kernel");

@@ -100,8 +100,6 @@ struct KernelArgs {
                            // tail of the layer-1 operand (2503 -> 2560) is zero on both sides: its MMAs are not issued.
   unsigned long long* trace;   // timing experiments only (DPD_TC_TRACE): per-role clock64 stamps of cluster 0's leader CTA, see tools/tc_trace.py
   int seg_head;            // 2-CTA kernel: K-blocks in each of the first two promotion segments of an item (0 = SEG)
-  int dbg;                 // timing experiments only (DPD_TC_DBG): 1 = staged gather without the copies, 2 = without the proxy fence
-  unsigned epi_backoff_ns; // 2-CTA kernel: nanosleep between the epilogue warps' polls of seg_full (0 = tight spin)
   GatherArgs g;
 };
 

@@ -70,22 +70,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   } while (!done);
 }
-// wait of a role that is off the critical path (the epilogue's wait for a finished segment: one per four K-blocks): back
-// off between polls so that the spinning warps do not take issue slots from the gather / TMA warps of the same scheduler
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  for (;;) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) break;
-    if (ns) __nanosleep(ns);
-  }
-}
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -345,7 +329,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       }
       for (int i0 = 0; i0 < sq.cnt; i0 = seg_end(i0, sq.cnt)) {
         if (e == 0 && lane == 0) stamp(2, 6);
-        mbar_wait_backoff(&ctl->seg_full[sb], sb_ph, args.epi_backoff_ns);
+        mbar_wait(&ctl->seg_full[sb], sb_ph);
         if (e == 0 && lane == 0) stamp(2, 7);
         tc_fence_after();
 #pragma unroll
