@@ -1,8 +1,8 @@
 """Interleaved A/B of one library switch inside ONE process (drift of clocks / power state cancels): the forward step of
 configs[1] is timed in alternating blocks with the environment variable set to each value.
-    python tools/ab_env.py DPD_TC_ZSKIP 0 1 [blocks] [steps per block] [idle seconds before every block]
+    python tools/ab_env.py DPD_TC_SEG_HEAD 4 6 [blocks] [steps per block] [idle seconds before every block]
 With an idle time (e.g. 1.0) every block is a cold burst at the boost clock - what a 20-step bench run measures; without
-it the blocks run back to back at the power-capped clock.  Only switches the library reads per call can be compared this way (DPD_TC_ZSKIP, DPD_FV_IMPL)."""
+it the blocks run back to back at the power-capped clock.  Only switches the library reads per call can be compared this way (DPD_TC_SEG_HEAD, DPD_FV_IMPL)."""
 import os
 import sys
 

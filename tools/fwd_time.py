@@ -1,5 +1,5 @@
 """Forward step (configs[1]: 1024 pairs, N=NP=64, G=8, k=5) timing with the per-kernel device times of the library's
-profiler.  Environment switches (DPD_TC_GATHER_LDG, DPD_FV_IMPL, ...) are read by the library at first use.
+profiler.  Environment switches (DPD_TC_SEG_HEAD, DPD_FV_IMPL, DPD_TC_TRACE ...) are read by the library at first use.
     python tools/fwd_time.py [steps] [pairs]"""
 import os
 import sys

@@ -1,6 +1,6 @@
-"""profiles/sass_r2.txt: per-kernel census of the Blackwell-native SASS mnemonics in libdpdist_b200.so (cuobjdump -sass)
+"""profiles/sass_r<N>.txt: per-kernel census of the Blackwell-native SASS mnemonics in libdpdist_b200.so (cuobjdump -sass)
 and the ptxas register / spill / shared-memory table of the same build (dpdist_b200/build/*.ptxas.txt).
-    python tools/sass_census.py > profiles/sass_r2.txt"""
+    python tools/sass_census.py > profiles/sass_r3.txt"""
 import collections
 import glob
 import os
