@@ -67,6 +67,7 @@ SIGNATURES.update({
     "dpd_debug_tc_gemm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                          ctypes.c_int, ctypes.c_void_p]),
+    "dpd_debug_tc_operand_order": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "dpd_model_forward": (ctypes.c_int, [ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_float, c_float_p,
                                          ctypes.c_void_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -119,7 +120,7 @@ def lib_path():
     return _build.LIB_PATH
 
 
-ABI_VERSION = 3          # must equal DPD_ABI_VERSION in include/dpdist_b200.h
+ABI_VERSION = 4          # must equal DPD_ABI_VERSION in include/dpdist_b200.h
 
 
 def load():

@@ -462,6 +462,14 @@ extern "C" int dpd_head_backward_inputs(const dpd_head_config* cfg, const void* 
   return 0;
 }
 
+extern "C" int dpd_debug_tc_operand_order(int taps, int C, int Kp, int* h_out) {
+  using namespace dpd;
+  DPD_REQUIRE(h_out != nullptr && taps > 0 && C > 0 && C % 4 == 0 && Kp > 0 && Kp % 64 == 0 && Kp >= taps * C + 3, DPD_E_INVALID,
+              "dpd_debug_tc_operand_order: need C %% 4 == 0, Kp %% 64 == 0, Kp >= taps * C + 3 (taps=%d C=%d Kp=%d)", taps, C, Kp);
+  for (int k = 0; k < Kp; ++k) h_out[k] = tc_k_to_patch_k(k, taps, C, Kp);
+  return 0;
+}
+
 extern "C" int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
                                  float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream) {
   using namespace dpd;

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DPD_ABI_VERSION 3
+#define DPD_ABI_VERSION 4
 #define DPD_MAX_GRID 16
 #define DPD_FV_CHANNELS_FULL 20
 #define DPD_FV_CHANNELS_SMALL 7
@@ -194,6 +194,13 @@ int dpd_adam_step_dev(float* d_param, const float* d_grad, float* d_m, float* d_
  * d_scratch >= 8*(M*K + N*K) + 256 bytes.                                                      */
 int dpd_debug_tc_gemm(const float* d_a, int M, int K, const float* d_w, int N, const float* d_bias,
                       float* d_out, void* d_scratch, size_t scratch_bytes, int f16, void* stream);
+
+/* Test hook (host only, no launch): the physical order of the layer-1 operand row in the fp16 tensor-core path.
+ *   h_out[k] = position in the reference's row [patch (taps*C, tap-major) | offsets (3) | padding] of the element the
+ * packed row of length Kp (a multiple of 64) holds at k.  The reference concatenates [offset | patch]
+ * (utils/dpdist_util.py:455); the packed order is patch-first, channel-split (16 + 4 channels at C = 20) with its
+ * 64-element blocks permuted; W1 is packed and the dW1 partials are mapped back with this map. */
+int dpd_debug_tc_operand_order(int taps, int C, int Kp, int* h_out);
 
 /* ---- layer-by-layer fp32 path for training-mode batch norm (--BN 1) --------------------------------------------------
  * Replaces, for `bn` truthy and is_training True, what utils/tf_util.py:213-227 builds per conv layer: conv2d + bias_add

@@ -27,7 +27,7 @@ def test_header_symbols_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), "libdpdist_b200.so does not export %s" % name
     assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and include/dpdist_b200.h disagree"
-    assert lib.dpd_version() == _lib.ABI_VERSION == 3     # DPD_ABI_VERSION
+    assert lib.dpd_version() == _lib.ABI_VERSION == 4     # DPD_ABI_VERSION
 
 
 def test_header_cites_reference_lines():
@@ -134,3 +134,31 @@ def test_layer_and_batch_norm_entry_points_validate_their_arguments():
     assert lib.dpd_gather_rows(p, p, p, 0, 64, 8, 20, 5, p, None) == -1
     assert lib.dpd_relu_backward(None, p, 16, None) == -1
     assert lib.dpd_add_inplace(p, p, 6, None) == -1                                                               # n % 4
+
+
+def test_tensor_core_operand_order_is_a_permutation_of_the_reference_row():
+    """dpd_debug_tc_operand_order (host only): the packed layer-1 row of the fp16 tensor-core path -- channel-split with
+    permuted 64-element blocks -- must hold every element of the reference row [patch | offsets] exactly once, padding
+    everywhere else, the offsets and the padding tail in the LAST block (the kernel may skip that block's unused K-steps),
+    and 16-byte units of the 16-channel part must not straddle a tap (they are copied with one 16-byte cp.async)."""
+    import ctypes
+    lib = _lib.load()
+    for k, C, Kp in ((5, 20, 2560), (3, 20, 576), (5, 16, 2048), (3, 8, 256), (5, 4, 512), (2, 20, 192), (5, 12, 1536), (7, 20, 6912)):
+        taps, E = k ** 3, k ** 3 * C
+        out = (ctypes.c_int * Kp)()
+        assert lib.dpd_debug_tc_operand_order(taps, C, Kp, out) == 0
+        o = np.array(out[:])
+        data = o[o < E + 3]
+        assert sorted(data.tolist()) == list(range(E + 3)), (k, C, Kp)            # every element once
+        assert (o >= 0).all() and len(set(o.tolist())) == Kp                       # padding positions are distinct too
+        last = o[Kp - 64:]
+        assert set(range(E, E + 3)) <= set(last.tolist()), "offsets live in the last block"
+        cx = C & ~7
+        if cx:
+            x_pos = np.nonzero((o < E) & ((o % C) < cx))[0]
+            for p0 in x_pos[::8][:200]:                                             # units of 8 start at multiples of 8
+                unit = o[p0 - p0 % 8: p0 - p0 % 8 + 8]
+                if ((unit < E) & ((unit % C) < cx)).all():
+                    assert len(set((unit // C).tolist())) == 1 and (np.diff(unit) == 1).all()
+    assert lib.dpd_debug_tc_operand_order(125, 20, 2500, (ctypes.c_int * 2500)()) != 0      # Kp % 64 != 0
+    assert lib.dpd_debug_tc_operand_order(125, 20, 2560, None) != 0
