@@ -554,75 +554,50 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       ++cnt;
     };
     if (args.mn_major) {
-      // dW1 = patches^T . dZ1.  Tile layout = MN-major: group (64 operand elements) major, then reduction row = query
-      // (128 bytes), 16-byte units XOR-swizzled with the row.  A group of a tile is ONE physical 64-element K-block of the
-      // operand row (block (mt * 256 + rank * 128) / 64 + group), i.e. per query exactly the 128 bytes the forward gathers
-      // for that K-block: X blocks with one 16-byte bypass copy per unit, the others with two 8-byte copies.  Thread
-      // (u = p % 8, sub = (p / 8) % 16, group = p / 128, warp-uniform) fills unit u of reduction rows it * 16 + sub; its
-      // unit's LUT entries are fixed per tile, what changes per stage are the rows' {voxel record, tap validity} words.
-      constexpr int NITM = 4;
-      const int u = p & 7, sub = (p >> 3) & 15, gI = p >> 7;
-      const int nkb_op = args.lut_chunks / CHUNKS;                 // physical K-blocks of the operand row
-      const int num_xkb = (g.k * g.k * g.k * cx) / KB_ELEMS;
+      // dW1 = patches^T . dZ1: the tile's M range is a range of operand elements, fixed per tile, so this thread's
+      // 4-element chunk (array, tap, channel quad) is decoded once per tile; what changes per stage are the 64 reduction
+      // rows, whose {voxel record, tap validity} come precomputed (rowinfo).  Tile layout = MN-major: group (64 elements)
+      // major, then reduction row (128 bytes), 16-byte units XOR-swizzled with the row.
+      constexpr int RL = NGT2 / 32, NITM = 64 / RL;              // 8 row lanes, 8 reduction rows per thread and K-block
+      const int chunk32 = p & 31, sub = p >> 5;                 // 32 chunk columns (2 groups x 16) x 8 row lanes
+      const uint32_t c16 = (uint32_t)((chunk32 & 15) >> 1);
+      const uint32_t dst0 = (uint32_t)((chunk32 >> 4) * 8192 + (chunk32 & 1) * 8);
       for (int j_it = 0, t, sl; get_item(j_it, t, sl); ++j_it) {
         const int mt = t / num_n_tiles;
-        const int kbt = (mt * 2 * BM + (int)rank * BM) / KB_ELEMS + gI;
-        uint32_t code[2] = {LUT_ZERO, LUT_ZERO}; int32_t delta[2] = {0, 0};
-        bool xblk = false;
-        if (kbt < nkb_op) {
-          const int4 le = __ldg(reinterpret_cast<const int4*>(g.lut + kbt * CHUNKS + 2 * u));
-          code[0] = (uint32_t)le.x; delta[0] = le.y; code[1] = (uint32_t)le.z; delta[1] = le.w;
-          xblk = tc_kb_logical(kbt, nkb_op, num_xkb) < num_xkb;
-        }
+        const int q = (mt * 2 * BM + (int)rank * BM) / 4 + chunk32;
+        uint32_t code = LUT_ZERO; int32_t delta = 0;
+        if (q < args.lut_chunks) { const int2 e = __ldg(g.lut + q); code = (uint32_t)e.x; delta = e.y; }
+        const uint32_t s0 = code & 255u, s1 = 8u + ((code >> 8) & 255u), s2 = 16u + ((code >> 16) & 255u);
+        const bool isy = code < LUT_OFFS && (code & LUT_YSEL) != 0;
+        const int stride = isy ? cy : cx;
+        const long long base = isy ? g.y_off : 0;
         const int kb_lo = sl * kbps, kb_hi = min(kb_lo + kbps, nkb_eff);
         for (int kb = kb_lo; kb < kb_hi; ++kb) {
           int2 ri[NITM];
 #pragma unroll
           for (int it = 0; it < NITM; ++it) {
-            const int m = kb * KB_ELEMS + it * 16 + sub;
+            const int m = kb * KB_ELEMS + it * RL + sub;
             ri[it] = (m < args.g_rows) ? __ldg(g.rowinfo + m) : make_int2(-1, 0);
           }
           wait_free();
-          const uint32_t a_hi = smem_u32(a_ptr(sa, 0)) + (uint32_t)gI * 8192u, a_lo = smem_u32(a_ptr(sa, 1)) + (uint32_t)gI * 8192u;
-          if (xblk) {
-            const uint32_t s0 = code[0] & 255u, s1 = 8u + ((code[0] >> 8) & 255u), s2 = 16u + ((code[0] >> 16) & 255u);
+          const uint32_t a_hi = smem_u32(a_ptr(sa, 0)), a_lo = smem_u32(a_ptr(sa, 1));
 #pragma unroll
-            for (int it = 0; it < NITM; ++it) {
-              const int r = it * 16 + sub;
-              const uint32_t dst = (uint32_t)(r * 128) + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4);
+          for (int it = 0; it < NITM; ++it) {
+            const int r = it * RL + sub;
+            const uint32_t dst = dst0 + (uint32_t)(r * 128) + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            if (code < LUT_OFFS) {
               const uint32_t mk = (uint32_t)ri[it].y;
               const uint32_t ok = (ri[it].x >= 0 ? 1u : 0u) & (mk >> s0) & (mk >> s1) & (mk >> s2) & 1u;
-              const size_t el = ok ? (size_t)((long long)ri[it].x * cx + delta[0]) : 0;
-              const uint32_t nbytes = ok ? 8u * ELEM : 0u;
-              cp_async16(a_hi + dst, fv_hi + el * ELEM, nbytes);
-              cp_async16(a_lo + dst, fv_lo + el * ELEM, nbytes);
-            }
-          } else {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint32_t c = code[hf];
-              const uint32_t s0 = c & 255u, s1 = 8u + ((c >> 8) & 255u), s2 = 16u + ((c >> 16) & 255u);
-              const bool isy = (c & LUT_YSEL) != 0;
-#pragma unroll
-              for (int it = 0; it < NITM; ++it) {
-                const int r = it * 16 + sub;
-                const uint32_t dst = (uint32_t)(r * 128) + (((uint32_t)u ^ (uint32_t)(r & 7)) << 4) + (uint32_t)hf * 8u;
-                const uint8_t *sh, *sl2;
-                bool ok;
-                if (c < LUT_OFFS) {
-                  const uint32_t mk = (uint32_t)ri[it].y;
-                  ok = ((ri[it].x >= 0 ? 1u : 0u) & (mk >> s0) & (mk >> s1) & (mk >> s2) & 1u) != 0;
-                  const size_t el = ok ? (size_t)((isy ? g.y_off + (long long)ri[it].x * cy : (long long)ri[it].x * cx) + delta[hf]) : 0;
-                  sh = fv_hi + el * ELEM; sl2 = fv_lo + el * ELEM;
-                } else {
-                  ok = (c == LUT_OFFS) && ri[it].x >= 0;
-                  const size_t m = ok ? (size_t)(kb * KB_ELEMS + r) : 0;
-                  sh = o4_hi + m * 4 * ELEM; sl2 = o4_lo + m * 4 * ELEM;
-                }
-                const uint32_t nbytes = ok ? 4u * ELEM : 0u;
-                cp_async8(a_hi + dst, sh, nbytes);
-                cp_async8(a_lo + dst, sl2, nbytes);
-              }
+              const size_t el = ok ? (size_t)(base + (long long)ri[it].x * stride + delta) : 0;
+              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+              cp_async8(a_hi + dst, fv_hi + el * ELEM, nbytes);
+              cp_async8(a_lo + dst, fv_lo + el * ELEM, nbytes);
+            } else {
+              const bool ok = (code == LUT_OFFS) && ri[it].x >= 0;
+              const size_t m = ok ? (size_t)(kb * KB_ELEMS + r) : 0;
+              const uint32_t nbytes = ok ? 4u * ELEM : 0u;
+              cp_async8(a_hi + dst, o4_hi + m * 4 * ELEM, nbytes);
+              cp_async8(a_lo + dst, o4_lo + m * 4 * ELEM, nbytes);
             }
           }
           cp_async_arrive_noinc(leader ? &ctl->afull[sa] : &ctl->gfull[sa]);
