@@ -162,3 +162,20 @@ def test_tensor_core_operand_order_is_a_permutation_of_the_reference_row():
                     assert len(set((unit // C).tolist())) == 1 and (np.diff(unit) == 1).all()
     assert lib.dpd_debug_tc_operand_order(125, 20, 2500, (ctypes.c_int * 2500)()) != 0      # Kp % 64 != 0
     assert lib.dpd_debug_tc_operand_order(125, 20, 2560, None) != 0
+
+
+def test_tensor_core_operand_order_random_shapes():
+    """The same permutation property over random (k, C, padding) combinations, including rows whose padding spans several
+    64-element blocks and channel counts without a 16-channel part (C = 4) or without a remainder (C = 8, 16, 24)."""
+    import ctypes
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        k = int(rng.integers(1, 8)); C = 4 * int(rng.integers(1, 9))
+        E = k ** 3 * C
+        Kp = ((E + 3 + 63) // 64 + int(rng.integers(0, 3))) * 64
+        out = (ctypes.c_int * Kp)()
+        assert lib.dpd_debug_tc_operand_order(k ** 3, C, Kp, out) == 0
+        o = np.array(out[:])
+        assert sorted(o[o < E + 3].tolist()) == list(range(E + 3)), (k, C, Kp)
+        assert len(set(o.tolist())) == Kp and int(o.max()) < Kp
